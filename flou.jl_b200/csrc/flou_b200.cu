@@ -1,0 +1,702 @@
+// C-ABI implementation (include/flou_b200.h): handle, table upload, partition/halo
+// bookkeeping, stage scheduling (streams, CUDA graph, NCCL halo exchange).
+//
+// Reference behaviour mirrored here (paths relative to the reference root):
+//   MultielementDisc ctor        src/FlouSpatial/MultielementDiscontinuous.jl:29-92
+//   rhs! orchestration           src/FlouSpatial/Equations/Hyperbolic.jl:31-69
+//   timeintegrate                src/FlouTime/FlouTime.jl:34-54
+//   Cartesian metrics            src/FlouSpatial/PhysicalRegions.jl:370-408, 541-696
+// No CPU compute path exists in this file: without a usable CUDA device every entry point
+// returns FLOU_B200_ECUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "flou_b200.h"
+#include "launch.h"
+
+using namespace flou;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int32_t fail(int32_t code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t err__ = (expr);                                                          \
+        if (err__ != cudaSuccess)                                                            \
+            return fail(FLOU_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+// ---------------------------------------------------------------- NCCL through dlopen
+// (keeps single-GPU use free of any NCCL dependency; with torch in the process this
+// resolves to the libnccl.so.2 torch already loaded)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8 };
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load()
+    {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+#define SYM(field, name) field = (decltype(field))dlsym(lib, name); if (!field) return false;
+        SYM(GetUniqueId, "ncclGetUniqueId")
+        SYM(CommInitRank, "ncclCommInitRank")
+        SYM(CommDestroy, "ncclCommDestroy")
+        SYM(GroupStart, "ncclGroupStart")
+        SYM(GroupEnd, "ncclGroupEnd")
+        SYM(Send, "ncclSend")
+        SYM(Recv, "ncclRecv")
+        SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+        return true;
+    }
+} g_nccl;
+
+#define NCCL_TRY(expr)                                                                        \
+    do {                                                                                      \
+        ncclResult_t r__ = (expr);                                                            \
+        if (r__ != 0)                                                                         \
+            return fail(FLOU_B200_ENCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+template <class T>
+cudaError_t upload(T **dst, const std::vector<T> &src)
+{
+    *dst = nullptr;
+    const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)dst, bytes);
+    if (e != cudaSuccess) return e;
+    if (!src.empty()) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+struct Peer {
+    int rank;
+    int64_t offset;   // first slot in the ghost / send buffers
+    int64_t nslots;
+};
+
+}  // namespace
+
+struct flou_b200_handle {
+    int nd = 0, nv = 0, np = 0, npts = 0, nfp = 0, nfaces = 0;
+    int device = 0, flags = 0;
+    int rank = 0, nranks = 1;
+    int64_t ne_local = 0, ndof = 0;
+    const StageLauncher *stage = nullptr;
+    const EmitLauncher *emit = nullptr;
+    KParams base;
+    // device memory
+    double *u[2] = {nullptr, nullptr}, *tmp = nullptr, *k = nullptr;
+    int cur = 0;
+    Conn *conn = nullptr;
+    int *faceid = nullptr;
+    double *jac = nullptr, *metric = nullptr, *fjac = nullptr, *frames = nullptr;
+    int *bc_kind = nullptr;
+    double *bc_state = nullptr, *bc_table = nullptr;
+    int *status = nullptr;
+    double *d_lm = nullptr, *d_lp = nullptr;
+    // halo
+    std::vector<Peer> peers;
+    int64_t nghost = 0;
+    double *ghost = nullptr, *sendbuf = nullptr;
+    int *send_list = nullptr;          // [slot] = local element*2nd + local face
+    int *interior_list = nullptr, *boundary_list = nullptr;
+    int n_interior = 0, n_boundary = 0;
+    ncclComm_t comm = nullptr;
+    // streams / events
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_emit = nullptr, ev_recv = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    // CUDA graph of two consecutive RK steps (returns to the same ping-pong buffer)
+    cudaGraphExec_t graph = nullptr;
+    std::vector<double> graph_key;
+    int64_t launches = 0;
+};
+
+namespace {
+
+// one RHS / stage pass over the owned elements (halo exchange included when partitioned)
+int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
+                 const double *u_in, double *u_out)
+{
+    KParams P = h->base;
+    P.u_in = u_in;
+    P.u_out = u_out;
+    P.tmp = h->tmp;
+    P.k_out = h->k;
+    P.mode = mode;
+    P.rkA = A;
+    P.rkB = B;
+    P.dt = dt;
+    if (h->nranks == 1 || h->nghost == 0) {
+        P.elem_first = 0;
+        P.elem_count = (int)h->ne_local;
+        P.elem_list = nullptr;
+        CUDA_TRY(h->stage->launch(P, h->stream));
+        h->launches += 1;
+        return FLOU_B200_OK;
+    }
+    if (!h->comm) return fail(FLOU_B200_EINVAL, "partitioned handle used before flou_b200_comm_init");
+    // 1. pack the traces the neighbours need, 2. exchange on the comm stream,
+    // 3. interior elements meanwhile, 4. partition-boundary elements after the receive
+    CUDA_TRY(h->emit->launch(u_in, h->ndof, h->send_list, (int)h->nghost, h->base.colloc,
+                             h->d_lm, h->d_lp, h->sendbuf, h->stream));
+    h->launches += 1;
+    CUDA_TRY(cudaEventRecord(h->ev_emit, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_emit, 0));
+    const size_t per_slot = (size_t)h->nv * h->nfp;
+    NCCL_TRY(g_nccl.GroupStart());
+    for (const Peer &p : h->peers) {
+        NCCL_TRY(g_nccl.Send(h->sendbuf + p.offset * per_slot, p.nslots * per_slot, ncclFloat64,
+                             p.rank, h->comm, h->comm_stream));
+        NCCL_TRY(g_nccl.Recv(h->ghost + p.offset * per_slot, p.nslots * per_slot, ncclFloat64,
+                             p.rank, h->comm, h->comm_stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
+    P.elem_first = 0;
+    P.elem_list = h->interior_list;
+    P.elem_count = h->n_interior;
+    CUDA_TRY(h->stage->launch(P, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
+    P.elem_list = h->boundary_list;
+    P.elem_count = h->n_boundary;
+    CUDA_TRY(h->stage->launch(P, h->stream));
+    h->launches += 2;
+    return FLOU_B200_OK;
+}
+
+int32_t run_steps_direct(flou_b200_handle *h, int nstages, const double *A, const double *B,
+                         double dt, int64_t nsteps)
+{
+    for (int64_t it = 0; it < nsteps; it++)
+        for (int s = 0; s < nstages; s++) {
+            const int32_t rc = run_pass(h, s == 0 ? MODE_STAGE_FIRST : MODE_STAGE, A[s], B[s], dt,
+                                        h->u[h->cur], h->u[h->cur ^ 1]);
+            if (rc) return rc;
+            h->cur ^= 1;
+        }
+    return FLOU_B200_OK;
+}
+
+void destroy_graph(flou_b200_handle *h)
+{
+    if (h->graph) cudaGraphExecDestroy(h->graph);
+    h->graph = nullptr;
+    h->graph_key.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *flou_b200_last_error(void) { return g_last_error.c_str(); }
+
+int32_t flou_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int vol_kind(int32_t divop, int32_t tpflux)
+{
+    if (divop == FLOU_B200_OP_STRONG) return VOL_STRONG;
+    return tpflux == FLOU_B200_FLUX_CHANDRASEKHAR ? VOL_SPLIT_CHA : VOL_SPLIT_STD;
+}
+
+int32_t flou_b200_supported(int32_t nd, int32_t np, int32_t equation, int32_t divop,
+                            int32_t tpflux, int32_t geometry)
+{
+    if (equation != FLOU_B200_EQ_LINEAR_ADVECTION && equation != FLOU_B200_EQ_EULER) return 0;
+    if (divop != FLOU_B200_OP_STRONG && divop != FLOU_B200_OP_SPLIT) return 0;
+    if (divop == FLOU_B200_OP_SPLIT && tpflux != FLOU_B200_FLUX_STDAVERAGE &&
+        tpflux != FLOU_B200_FLUX_CHANDRASEKHAR) return 0;
+    return get_stage_launcher(nd, np, equation, vol_kind(divop, tpflux),
+                              geometry == FLOU_B200_GEOM_CARTESIAN) != nullptr;
+}
+
+int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
+{
+    if (!d || !out) return fail(FLOU_B200_EINVAL, "null argument");
+    *out = nullptr;
+    if (d->struct_size != (int32_t)sizeof(flou_b200_desc))
+        return fail(FLOU_B200_EINVAL, "flou_b200_desc size mismatch (ABI)");
+    if (d->nd < 1 || d->nd > 3) return fail(FLOU_B200_EINVAL, "nd must be 1, 2 or 3");
+    const int nd = d->nd, np = d->np;
+    const int nv_expected = d->equation == FLOU_B200_EQ_EULER ? nd + 2 : 1;
+    if (d->nv != nv_expected) return fail(FLOU_B200_EINVAL, "nv does not match the equation");
+    if (d->equation == FLOU_B200_EQ_LINEAR_ADVECTION &&
+        (d->numflux != FLOU_B200_FLUX_STDAVERAGE && d->numflux != FLOU_B200_FLUX_LXF))
+        return fail(FLOU_B200_EINVAL, "linear advection supports StdAverage and LxF fluxes only");
+    if (d->equation == FLOU_B200_EQ_LINEAR_ADVECTION && d->divop == FLOU_B200_OP_SPLIT &&
+        d->tpflux != FLOU_B200_FLUX_STDAVERAGE)
+        return fail(FLOU_B200_EINVAL, "linear advection split form needs the StdAverage two-point flux");
+    if (d->numflux < 0 || d->numflux > FLOU_B200_FLUX_MATRIXDISSIPATION)
+        return fail(FLOU_B200_EINVAL, "unknown numerical flux");
+    const bool has_avg = d->numflux == FLOU_B200_FLUX_LXF ||
+                         d->numflux == FLOU_B200_FLUX_SCALARDISSIPATION ||
+                         d->numflux == FLOU_B200_FLUX_MATRIXDISSIPATION;
+    if (has_avg && d->numflux_avg != FLOU_B200_FLUX_STDAVERAGE &&
+        d->numflux_avg != FLOU_B200_FLUX_CHANDRASEKHAR)
+        return fail(FLOU_B200_EINVAL, "numflux.avg must be StdAverage or ChandrasekharAverage");
+    if (!flou_b200_supported(nd, np, d->equation, d->divop, d->tpflux, d->geometry))
+        return fail(FLOU_B200_EUNSUPPORTED, "no kernel compiled for this (nd, np, equation, operator)");
+    if (d->ne <= 0 || d->nf <= 0 || !d->faceinds || !d->facepos || !d->eleminds || !d->elempos ||
+        !d->orientation)
+        return fail(FLOU_B200_EINVAL, "connectivity tables missing");
+    if (!d->Ds || !d->Dsharp || !d->lminus || !d->lplus || !d->dgminus || !d->dgplus)
+        return fail(FLOU_B200_EINVAL, "operator tables missing");
+    if (d->geometry == FLOU_B200_GEOM_GENERAL && (!d->jac || !d->metric || !d->fjac || !d->frames))
+        return fail(FLOU_B200_EINVAL, "general geometry tables missing");
+    const int nranks = d->nranks <= 0 ? 1 : d->nranks;
+    if (d->elem_begin < 0 || d->elem_end > d->ne || d->elem_begin >= d->elem_end)
+        return fail(FLOU_B200_EINVAL, "bad owned element range");
+    if (nranks > 1 && !d->part_offsets) return fail(FLOU_B200_EINVAL, "part_offsets missing");
+    if (nranks == 1 && (d->elem_begin != 0 || d->elem_end != d->ne))
+        return fail(FLOU_B200_EINVAL, "single-rank handle must own every element");
+
+    if (flou_b200_device_count() <= d->device)
+        return fail(FLOU_B200_ECUDA, "no usable CUDA device (this library has no CPU path)");
+    CUDA_TRY(cudaSetDevice(d->device));
+
+    flou_b200_handle *h = new flou_b200_handle();
+    h->nd = nd; h->nv = d->nv; h->np = np;
+    h->npts = 1; for (int i = 0; i < nd; i++) h->npts *= np;
+    h->nfp = h->npts / np;
+    h->nfaces = 2 * nd;
+    h->device = d->device; h->flags = d->flags;
+    h->rank = d->rank; h->nranks = nranks;
+    h->ne_local = d->elem_end - d->elem_begin;
+    h->ndof = h->ne_local * h->npts;
+    const bool cart = d->geometry == FLOU_B200_GEOM_CARTESIAN;
+    h->stage = get_stage_launcher(nd, np, d->equation, vol_kind(d->divop, d->tpflux), cart);
+    h->emit = get_emit_launcher(nd, np, d->nv);
+    if (h->ne_local * (int64_t)h->nfaces > INT32_MAX)
+        { delete h; return fail(FLOU_B200_EINVAL, "too many elements for one handle"); }
+
+    // ---- boundary-face lookup: global face -> (boundary index, ordinal in bc_faces)
+    std::map<int64_t, std::pair<int, int64_t>> bdface;
+    for (int ib = 0; ib < d->nbound; ib++)
+        for (int64_t m = d->bc_offsets[ib]; m < d->bc_offsets[ib + 1]; m++)
+            bdface[d->bc_faces[m] - 1] = {ib, m};
+
+    // ---- element-face records, ghosts
+    const int NF = h->nfaces;
+    std::vector<Conn> conn((size_t)h->ne_local * NF);
+    struct Ghost { int peer; int64_t gf; int le, lf; };
+    std::vector<Ghost> ghosts;
+    std::map<int64_t, int> face_slot;            // global face -> local slot (general geometry)
+    std::vector<int64_t> slot_face;
+    std::vector<int> faceid((size_t)h->ne_local * NF, 0);
+    auto owner_of = [&](int64_t ge) {
+        int r = (int)(std::upper_bound(d->part_offsets, d->part_offsets + nranks + 1, ge) -
+                      d->part_offsets) - 1;
+        return r;
+    };
+    for (int64_t le = 0; le < h->ne_local; le++) {
+        const int64_t ge = d->elem_begin + le;
+        for (int lf = 0; lf < NF; lf++) {
+            const int64_t gf = d->faceinds[ge * NF + lf] - 1;
+            const int64_t pos = d->facepos[ge * NF + lf];
+            if (gf < 0 || gf >= d->nf || (pos != 1 && pos != 2))
+                { delete h; return fail(FLOU_B200_EINVAL, "faceinds/facepos out of range"); }
+            const int master = pos == 1;
+            if (d->eleminds[gf * 2 + (master ? 0 : 1)] - 1 != ge ||
+                d->elempos[gf * 2 + (master ? 0 : 1)] - 1 != lf)
+                { delete h; return fail(FLOU_B200_EINVAL, "element and face connectivity disagree"); }
+            const int64_t gn = d->eleminds[gf * 2 + (master ? 1 : 0)] - 1;
+            const int nlf = (int)d->elempos[gf * 2 + (master ? 1 : 0)] - 1;
+            const int orient = d->orientation[gf];
+            Conn c;
+            if (gn < 0) {
+                auto it = bdface.find(gf);
+                if (it == bdface.end())
+                    { delete h; return fail(FLOU_B200_EINVAL, "boundary face without a boundary condition"); }
+                c.nbr = (int)it->second.second;
+                c.info = conn_pack(0, 0, 1, FK_BOUNDARY, it->second.first);
+            } else if (gn >= d->elem_begin && gn < d->elem_end) {
+                c.nbr = (int)(gn - d->elem_begin);
+                c.info = conn_pack(nlf, orient, master, FK_INTERIOR, 0);
+            } else {
+                c.nbr = -1;   // slot assigned after sorting
+                c.info = conn_pack(nlf, orient, master, FK_GHOST, 0);
+                ghosts.push_back({owner_of(gn), gf, (int)le, lf});
+            }
+            conn[(size_t)le * NF + lf] = c;
+            if (!cart) {
+                auto it = face_slot.find(gf);
+                if (it == face_slot.end()) {
+                    it = face_slot.emplace(gf, (int)slot_face.size()).first;
+                    slot_face.push_back(gf);
+                }
+                faceid[(size_t)le * NF + lf] = it->second;
+            }
+        }
+    }
+    std::sort(ghosts.begin(), ghosts.end(), [](const Ghost &a, const Ghost &b) {
+        return a.peer != b.peer ? a.peer < b.peer : a.gf < b.gf;
+    });
+    std::vector<int> send_list(ghosts.size());
+    std::vector<char> is_boundary_elem((size_t)h->ne_local, 0);
+    for (size_t s = 0; s < ghosts.size(); s++) {
+        const Ghost &g = ghosts[s];
+        conn[(size_t)g.le * NF + g.lf].nbr = (int)s;
+        send_list[s] = g.le * NF + g.lf;
+        is_boundary_elem[g.le] = 1;
+        if (h->peers.empty() || h->peers.back().rank != g.peer)
+            h->peers.push_back({g.peer, (int64_t)s, 0});
+        h->peers.back().nslots++;
+    }
+    h->nghost = (int64_t)ghosts.size();
+    std::vector<int> interior, boundary;
+    for (int64_t le = 0; le < h->ne_local; le++)
+        (is_boundary_elem[le] ? boundary : interior).push_back((int)le);
+    h->n_interior = (int)interior.size();
+    h->n_boundary = (int)boundary.size();
+
+    // ---- kernel parameters
+    KParams &P = h->base;
+    std::memset(&P, 0, sizeof(P));
+    const double *Dvol = d->divop == FLOU_B200_OP_STRONG ? d->Ds : d->Dsharp;
+    for (int i = 0; i < np * np; i++) P.Dvol[i] = Dvol[i];
+    bool colloc = true;
+    for (int i = 0; i < np; i++) {
+        P.lm[i] = d->lminus[i]; P.lp[i] = d->lplus[i];
+        P.dgl[i] = d->dgminus[i]; P.dgr[i] = d->dgplus[i];
+        const double em = (i == 0) ? 1.0 : 0.0, ep = (i == np - 1) ? 1.0 : 0.0;
+        if (std::fabs(d->lminus[i] - em) > 1e-13 || std::fabs(d->lplus[i] - ep) > 1e-13) colloc = false;
+    }
+    P.colloc = colloc ? 1 : 0;
+    P.fp.gamma = d->gamma; P.fp.intensity = d->intensity;
+    for (int c = 0; c < 3; c++) P.fp.a[c] = d->a[c];
+    P.fp.numflux = d->numflux; P.fp.numflux_avg = d->numflux_avg;
+    if (cart) {
+        // PhysicalRegions.jl:370-408 (element) and :541-696 (faces)
+        double prod = 1.0;
+        for (int c = 0; c < nd; c++) prod *= d->dx[c];
+        P.cjac = prod / (double)(1 << nd);
+        if (nd == 1) { P.cmet[0] = 1.0; P.cfjac[0] = 1.0; }
+        else if (nd == 2) {
+            P.cmet[0] = d->dx[1] / 2; P.cmet[1] = d->dx[0] / 2;
+            P.cfjac[0] = d->dx[1] / 2; P.cfjac[1] = d->dx[0] / 2;
+        } else {
+            P.cmet[0] = d->dx[1] * d->dx[2] / 4; P.cmet[1] = d->dx[0] * d->dx[2] / 4;
+            P.cmet[2] = d->dx[0] * d->dx[1] / 4;
+            for (int c = 0; c < 3; c++) P.cfjac[c] = P.cmet[c];
+        }
+    }
+
+#define H_TRY(expr)                                                                            \
+    do {                                                                                       \
+        cudaError_t err__ = (expr);                                                            \
+        if (err__ != cudaSuccess) {                                                            \
+            std::string m__ = std::string(#expr) + ": " + cudaGetErrorString(err__);           \
+            flou_b200_destroy(h);                                                              \
+            return fail(FLOU_B200_ECUDA, m__);                                                 \
+        }                                                                                      \
+    } while (0)
+
+    H_TRY(upload(&h->conn, conn));
+    if (!cart) {
+        // re-lay geometry as plane-major SoA restricted to owned elements / touched faces
+        const int64_t ndof = h->ndof, npts = h->npts, nfp = h->nfp;
+        std::vector<double> jac((size_t)ndof), met((size_t)ndof * nd * nd);
+        for (int64_t i = 0; i < ndof; i++) {
+            const int64_t gi = d->elem_begin * npts + i;
+            jac[i] = d->jac[gi];
+            for (int m = 0; m < nd * nd; m++) met[(size_t)m * ndof + i] = d->metric[gi * nd * nd + m];
+        }
+        const int64_t nfd = (int64_t)slot_face.size() * nfp;
+        std::vector<double> fj((size_t)nfd), fr((size_t)nfd * 3 * nd);
+        for (size_t s = 0; s < slot_face.size(); s++)
+            for (int64_t i = 0; i < nfp; i++) {
+                const int64_t gi = slot_face[s] * nfp + i, li = (int64_t)s * nfp + i;
+                fj[li] = d->fjac[gi];
+                for (int c = 0; c < 3 * nd; c++) fr[(size_t)c * nfd + li] = d->frames[gi * 3 * nd + c];
+            }
+        H_TRY(upload(&h->jac, jac));
+        H_TRY(upload(&h->metric, met));
+        H_TRY(upload(&h->fjac, fj));
+        H_TRY(upload(&h->frames, fr));
+        H_TRY(upload(&h->faceid, faceid));
+        P.nfacedofs = nfd;
+    }
+    {
+        std::vector<int> kinds(d->bc_kind, d->bc_kind + d->nbound);
+        std::vector<double> state, table;
+        if (d->nbound > 0 && d->bc_state) state.assign(d->bc_state, d->bc_state + (size_t)d->nbound * d->nv);
+        if (d->nbound > 0 && d->bc_table)
+            table.assign(d->bc_table, d->bc_table + (size_t)d->bc_offsets[d->nbound] * h->nfp * d->nv);
+        bool need_table = false, need_state = false;
+        for (int k : kinds) { need_table |= k == FLOU_B200_BC_TABLE; need_state |= k == FLOU_B200_BC_INFLOW; }
+        if ((need_table && table.empty()) || (need_state && state.empty()))
+            { flou_b200_destroy(h); return fail(FLOU_B200_EINVAL, "boundary-condition data missing"); }
+        H_TRY(upload(&h->bc_kind, kinds));
+        H_TRY(upload(&h->bc_state, state));
+        H_TRY(upload(&h->bc_table, table));
+    }
+    {
+        std::vector<double> lm(P.lm, P.lm + 8), lp(P.lp, P.lp + 8);
+        H_TRY(upload(&h->d_lm, lm));
+        H_TRY(upload(&h->d_lp, lp));
+    }
+    H_TRY(upload(&h->send_list, send_list));
+    H_TRY(upload(&h->interior_list, interior));
+    H_TRY(upload(&h->boundary_list, boundary));
+    const size_t state_bytes = sizeof(double) * (size_t)h->ndof * h->nv;
+    H_TRY(cudaMalloc((void **)&h->u[0], state_bytes));
+    H_TRY(cudaMalloc((void **)&h->u[1], state_bytes));
+    H_TRY(cudaMalloc((void **)&h->tmp, state_bytes));
+    H_TRY(cudaMalloc((void **)&h->k, state_bytes));
+    H_TRY(cudaMemset(h->u[0], 0, state_bytes));
+    H_TRY(cudaMemset(h->u[1], 0, state_bytes));
+    H_TRY(cudaMemset(h->tmp, 0, state_bytes));
+    H_TRY(cudaMemset(h->k, 0, state_bytes));
+    const size_t halo_bytes = sizeof(double) * std::max<size_t>((size_t)h->nghost * h->nfp * h->nv, 1);
+    H_TRY(cudaMalloc((void **)&h->ghost, halo_bytes));
+    H_TRY(cudaMalloc((void **)&h->sendbuf, halo_bytes));
+    H_TRY(cudaMalloc((void **)&h->status, sizeof(int)));
+    H_TRY(cudaMemset(h->status, 0, sizeof(int)));
+    H_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    H_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    H_TRY(cudaEventCreateWithFlags(&h->ev_emit, cudaEventDisableTiming));
+    H_TRY(cudaEventCreateWithFlags(&h->ev_recv, cudaEventDisableTiming));
+    H_TRY(cudaEventCreate(&h->ev_t0));
+    H_TRY(cudaEventCreate(&h->ev_t1));
+    H_TRY(h->stage->prepare());
+#undef H_TRY
+    P.jac = h->jac; P.metric = h->metric; P.fjac = h->fjac; P.frames = h->frames;
+    P.faceid = h->faceid; P.conn = h->conn;
+    P.bc_kind = h->bc_kind; P.bc_state = h->bc_state; P.bc_table = h->bc_table;
+    P.ghost = h->ghost;
+    P.ndof = h->ndof;
+    P.status = h->status;
+    *out = h;
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_destroy(flou_b200_handle *h)
+{
+    if (!h) return FLOU_B200_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    destroy_graph(h);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    void *ptrs[] = {h->u[0], h->u[1], h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
+                    h->frames, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
+                    h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->ev_emit) cudaEventDestroy(h->ev_emit);
+    if (h->ev_recv) cudaEventDestroy(h->ev_recv);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    delete h;
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_upload_state(flou_b200_handle *h, const double *Q)
+{
+    if (!h || !Q) return fail(FLOU_B200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, sizeof(double) * (size_t)h->ndof * h->nv,
+                             cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_download_state(flou_b200_handle *h, double *Q)
+{
+    if (!h || !Q) return fail(FLOU_B200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(Q, h->u[h->cur], sizeof(double) * (size_t)h->ndof * h->nv,
+                             cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_synchronize(flou_b200_handle *h)
+{
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_status(flou_b200_handle *h, int32_t *flags)
+{
+    if (!h || !flags) return fail(FLOU_B200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int f = 0;
+    CUDA_TRY(cudaMemcpy(&f, h->status, sizeof(int), cudaMemcpyDeviceToHost));
+    *flags = f;
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_rhs(flou_b200_handle *h, const double *Q, double *dQ, double t)
+{
+    (void)t;   // no time-dependent boundary data or sources live on the device
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * (size_t)h->ndof * h->nv;
+    if (Q) CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, bytes, cudaMemcpyHostToDevice, h->stream));
+    const int32_t rc = run_pass(h, MODE_RHS, 0.0, 0.0, 0.0, h->u[h->cur], h->u[h->cur ^ 1]);
+    if (rc) return rc;
+    if (dQ) CUDA_TRY(cudaMemcpyAsync(dQ, h->k, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const double *A,
+                                 const double *B, const double *c, double dt, double t0,
+                                 int64_t nsteps)
+{
+    (void)c; (void)t0;
+    if (!h || !A || !B || nstages < 1 || nstages > 16 || nsteps < 0)
+        return fail(FLOU_B200_EINVAL, "bad RK arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    // CUDA graph of two steps (2*nstages passes bring u back to the same ping-pong buffer);
+    // only for single-rank handles: NCCL calls are issued directly.
+    const bool use_graph = !(h->flags & FLOU_B200_FLAG_NO_GRAPH) && h->nranks == 1 && nsteps >= 4;
+    int64_t done = 0;
+    if (use_graph) {
+        std::vector<double> key;
+        key.push_back((double)nstages); key.push_back(dt); key.push_back((double)h->cur);
+        key.insert(key.end(), A, A + nstages);
+        key.insert(key.end(), B, B + nstages);
+        if (!h->graph || key != h->graph_key) {
+            destroy_graph(h);
+            cudaGraph_t g = nullptr;
+            const int cur0 = h->cur;
+            const int64_t l0 = h->launches;
+            CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            const int32_t rc = run_steps_direct(h, nstages, A, B, dt, 2);
+            cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+            h->cur = cur0;
+            h->launches = l0;
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            CUDA_TRY(e);
+            e = cudaGraphInstantiate(&h->graph, g, 0);
+            cudaGraphDestroy(g);
+            CUDA_TRY(e);
+            h->graph_key = key;
+        }
+        while (nsteps - done >= 2) {
+            CUDA_TRY(cudaGraphLaunch(h->graph, h->stream));
+            h->launches += 2 * nstages;
+            done += 2;
+        }
+    }
+    return run_steps_direct(h, nstages, A, B, dt, nsteps - done);
+}
+
+int32_t flou_b200_timeintegrate(flou_b200_handle *h, double *Q, int32_t nstages, const double *A,
+                                const double *B, const double *c, double dt, double t0,
+                                int64_t nsteps)
+{
+    if (!h || !Q) return fail(FLOU_B200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * (size_t)h->ndof * h->nv;
+    CUDA_TRY(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, bytes, cudaMemcpyHostToDevice, h->stream));
+    const int32_t rc = flou_b200_lsrk2n_advance(h, nstages, A, B, c, dt, t0, nsteps);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(Q, h->u[h->cur], bytes, cudaMemcpyDeviceToHost, h->stream));
+    int f = 0;
+    CUDA_TRY(cudaMemcpyAsync(&f, h->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (f & 1) return fail(FLOU_B200_EDOMAIN, "non-positive density/pressure or NaN (Simulation crashed!)");
+    return FLOU_B200_OK;
+}
+
+int64_t flou_b200_ndofs_local(const flou_b200_handle *h) { return h ? h->ndof : 0; }
+void *flou_b200_stream(flou_b200_handle *h) { return h ? (void *)h->stream : nullptr; }
+void *flou_b200_device_state(flou_b200_handle *h) { return h ? (void *)h->u[h->cur] : nullptr; }
+int64_t flou_b200_kernel_launches(const flou_b200_handle *h) { return h ? h->launches : 0; }
+
+int32_t flou_b200_timer_start(flou_b200_handle *h)
+{
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventRecord(h->ev_t0, h->stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_timer_stop(flou_b200_handle *h, float *ms)
+{
+    if (!h || !ms) return fail(FLOU_B200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventRecord(h->ev_t1, h->stream));
+    CUDA_TRY(cudaEventSynchronize(h->ev_t1));
+    CUDA_TRY(cudaEventElapsedTime(ms, h->ev_t0, h->ev_t1));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_pin_host(void *ptr, uint64_t bytes)
+{
+    if (!ptr) return fail(FLOU_B200_EINVAL, "null argument");
+    CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_unpin_host(void *ptr)
+{
+    if (!ptr) return fail(FLOU_B200_EINVAL, "null argument");
+    CUDA_TRY(cudaHostUnregister(ptr));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_nccl_unique_id(char id[128])
+{
+    if (!id) return fail(FLOU_B200_EINVAL, "null argument");
+    if (!g_nccl.load()) return fail(FLOU_B200_ENCCL, "libnccl.so.2 not found");
+    ncclUniqueId uid;
+    NCCL_TRY(g_nccl.GetUniqueId(&uid));
+    std::memcpy(id, uid.internal, 128);
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_comm_init(flou_b200_handle *h, const char id[128])
+{
+    if (!h || !id) return fail(FLOU_B200_EINVAL, "null argument");
+    if (!g_nccl.load()) return fail(FLOU_B200_ENCCL, "libnccl.so.2 not found");
+    CUDA_TRY(cudaSetDevice(h->device));
+    ncclUniqueId uid;
+    std::memcpy(uid.internal, id, 128);
+    NCCL_TRY(g_nccl.CommInitRank(&h->comm, h->nranks, uid, h->rank));
+    return FLOU_B200_OK;
+}
+
+}  // extern "C"

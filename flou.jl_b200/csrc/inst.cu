@@ -1,0 +1,82 @@
+// Kernel instances for one (ND, NP) pair; compiled once per pair with
+//   -DFLOU_ND=<1|2|3> -DFLOU_NP=<2..8>
+// so the instances build in parallel.  dispatch.cu stitches the per-pair tables together.
+#include "launch.h"
+
+#ifndef FLOU_ND
+#error "compile with -DFLOU_ND=.. -DFLOU_NP=.."
+#endif
+
+namespace flou {
+
+template <class C>
+static cudaError_t do_prepare()
+{
+    return cudaFuncSetAttribute(stage_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)C::SMEM_BYTES);
+}
+
+template <class C>
+static cudaError_t do_launch(const KParams &P, cudaStream_t s)
+{
+    if (P.elem_count <= 0) return cudaSuccess;
+    const int grid = (P.elem_count + C::EPB - 1) / C::EPB;
+    stage_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(P);
+    return cudaGetLastError();
+}
+
+template <class C>
+static constexpr StageLauncher make()
+{
+    return StageLauncher{&do_launch<C>, &do_prepare<C>, C::EPB, C::THREADS, C::SMEM_BYTES};
+}
+
+#define ND FLOU_ND
+#define NP FLOU_NP
+
+// [eq][vol][cart]
+static const StageLauncher table[2][3][2] = {
+    {   // linear advection: strong, split (StdAverage two-point flux); no Chandrasekhar
+        {make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, true>>()},
+        {make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, true>>()},
+        {StageLauncher{nullptr, nullptr, 0, 0, 0}, StageLauncher{nullptr, nullptr, 0, 0, 0}},
+    },
+    {   // Euler
+        {make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, true>>()},
+        {make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, true>>()},
+        {make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
+    },
+};
+
+template <int NV>
+static cudaError_t emit_launch(const double *u, int64_t ndof, const int *list, int nslots,
+                               int colloc, const double *lm, const double *lp, double *out,
+                               cudaStream_t s)
+{
+    if (nslots <= 0) return cudaSuccess;
+    constexpr int NFP = ipow_c(NP, ND - 1);
+    const int64_t n = (int64_t)nslots * NFP;
+    const int threads = 128;
+    const int grid = (int)((n + threads - 1) / threads);
+    emit_traces_kernel<ND, NP, NV><<<grid, threads, 0, s>>>(u, ndof, list, nslots, colloc, lm, lp, out);
+    return cudaGetLastError();
+}
+
+static const EmitLauncher emit_adv = {&emit_launch<1>};
+static const EmitLauncher emit_euler = {&emit_launch<ND + 2>};
+
+#define CAT_(a, b, c) a##b##_##c
+#define CAT(a, b, c) CAT_(a, b, c)
+
+const StageLauncher *CAT(stage_table_, FLOU_ND, FLOU_NP)(int eq, int vol, int cart)
+{
+    const StageLauncher *l = &table[eq][vol][cart ? 1 : 0];
+    return l->launch ? l : nullptr;
+}
+
+const EmitLauncher *CAT(emit_table_, FLOU_ND, FLOU_NP)(int nv)
+{
+    return nv == 1 ? &emit_adv : &emit_euler;
+}
+
+}  // namespace flou

@@ -1,0 +1,24 @@
+// Host-side view of the compiled kernel instances (one translation unit per (ND, NP)).
+#pragma once
+#include <cuda_runtime.h>
+#include "stage_kernel.cuh"
+
+namespace flou {
+
+struct StageLauncher {
+    cudaError_t (*launch)(const KParams &, cudaStream_t);
+    cudaError_t (*prepare)();
+    int epb, threads;
+    size_t smem;
+};
+
+struct EmitLauncher {
+    cudaError_t (*launch)(const double *u, int64_t ndof, const int *list, int nslots, int colloc,
+                          const double *lm, const double *lp, double *out, cudaStream_t);
+};
+
+// eq: EQ_*, vol: VOL_*, cart: 0/1.  Returns nullptr when the combination is not compiled.
+const StageLauncher *get_stage_launcher(int nd, int np, int eq, int vol, int cart);
+const EmitLauncher *get_emit_launcher(int nd, int np, int nv);
+
+}  // namespace flou

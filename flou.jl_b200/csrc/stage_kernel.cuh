@@ -1,0 +1,585 @@
+// One fused kernel per RK stage:  k = rhs(u_in);  tmp = A*tmp + dt*k;  u_out = u_in + B*tmp.
+//
+// It replaces, in a single pass over the state, the reference's seven sweeps
+// (src/FlouSpatial/Equations/Hyperbolic.jl:31-69):
+//   project2faces!          Interfaces.jl:51-109      -> traces built on the fly (own element
+//                                                        from shared memory, neighbour from L2)
+//   volume_contribution!    OpDivergence.jl:105-160 (strong), :184-282 (split)
+//   applyBCs!               Interfaces.jl:25-49       -> evaluated inside the face task
+//   interface_fluxes!       Interfaces.jl:111-136     -> recomputed by both neighbours with the
+//                                                        same (master, slave) argument order,
+//                                                        hence bitwise equal on both sides
+//   surface_contribution!   OpDivergence.jl:42-100
+//   apply_massmatrix!       MultielementDiscontinuous.jl:132-137 (true division by jac)
+// plus OrdinaryDiffEq's LowStorageRK2N stage update (call site FlouTime.jl:34-38).
+// `u` is ping-ponged (u_in != u_out) because neighbours read the same-stage state.
+//
+// Thread mapping: a CTA owns EPB consecutive elements; thread t <-> (element t / NPTS,
+// node t % NPTS), node = ix + NP*iy + NP^2*iz (StdQuad.jl:46-50, StdHex.jl:48-54).  Face
+// work is a flat task list (element, local face, face dof) strided over the CTA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "physics.cuh"
+
+namespace flou {
+
+__host__ __device__ constexpr int ipow_c(int b, int e) { return e <= 0 ? 1 : b * ipow_c(b, e - 1); }
+
+enum : int { MODE_RHS = 0, MODE_STAGE = 1, MODE_STAGE_FIRST = 2 };
+enum : int { FK_INTERIOR = 0, FK_GHOST = 1, FK_BOUNDARY = 2 };
+
+// conn.info bit layout
+//   [0:3)  neighbour's local face (0-based)         [3:6) orientation
+//   [6]    this element is the face's master        [7:9) kind (FK_*)
+//   [9:..) boundary index (FK_BOUNDARY)
+__host__ __device__ inline int conn_pack(int nbrface, int orient, int master, int kind, int bc)
+{
+    return (nbrface & 7) | ((orient & 7) << 3) | ((master & 1) << 6) | ((kind & 3) << 7) | (bc << 9);
+}
+
+struct Conn {
+    int nbr;    // interior: local neighbour element; ghost: ghost slot; boundary: ordinal in bc_faces
+    int info;
+};
+
+struct KParams {
+    // operators, column-major NP x NP : Dvol = Ds (strong) or Dsharp (split)
+    double Dvol[64];
+    double lm[8], lp[8], dgl[8], dgr[8];
+    int colloc;                 // GLL: l(-1) = e_1, l(+1) = e_np up to round-off
+    FluxParams fp;
+    // Cartesian geometry (PhysicalRegions.jl:370-408, 541-696)
+    double cjac;                // prod(dx)/2^nd
+    double cmet[3];             // metric diagonal  Ja^d_d
+    double cfjac[3];            // face jac by direction
+    // general geometry, device SoA
+    const double *jac;          // [dof]
+    const double *metric;       // [(c + nd*d)][dof]  (plane-major)
+    const double *fjac;         // [lface*NFP + i]
+    const double *frames;       // [(r*nd + c)][lface*NFP + i], r = n,t,b
+    const int *faceid;          // [e*2nd + lf] -> local face slot
+    int64_t nfacedofs;          // plane stride of frames
+    // connectivity
+    const Conn *conn;           // [e*2nd + lf]
+    // boundary conditions
+    const int *bc_kind;
+    const double *bc_state;     // [ib*nv + v]
+    const double *bc_table;     // [(m*NFP + i)*nv + v]
+    // halo
+    const double *ghost;        // [(slot*nv + v)*NFP + k] in the sender's face-dof order
+    // state
+    const double *u_in;
+    double *u_out;
+    double *tmp;
+    double *k_out;
+    int64_t ndof;               // local dofs = plane stride of the state
+    int elem_first, elem_count;
+    const int *elem_list;       // optional indirection
+    int mode;
+    double rkA, rkB, dt;
+    int *status;
+};
+
+// ------------------------------------------------------------------ index helpers
+template <int ND, int NP>
+__device__ __forceinline__ void line_of(int d, int k, int &base, int &stride)
+{   // tpdofs order: StdQuad.jl:116-124, StdHex.jl:135-145
+    if (ND == 1) { base = 0; stride = 1; }
+    else if (ND == 2) {
+        if (d == 0) { base = NP * k; stride = 1; } else { base = k; stride = NP; }
+    } else {
+        if (d == 0) { base = NP * k; stride = 1; }
+        else if (d == 1) { base = (k % NP) + NP * NP * (k / NP); stride = NP; }
+        else { base = k; stride = NP * NP; }
+    }
+}
+
+// face-dof (line number) of `node` in direction d, and its position along the line
+template <int ND, int NP>
+__device__ __forceinline__ void node_line(int node, int d, int &k, int &ii)
+{
+    if (ND == 1) { k = 0; ii = node; }
+    else if (ND == 2) {
+        const int ix = node % NP, iy = node / NP;
+        if (d == 0) { k = iy; ii = ix; } else { k = ix; ii = iy; }
+    } else {
+        const int ix = node % NP, iy = (node / NP) % NP, iz = node / (NP * NP);
+        if (d == 0) { k = iy + NP * iz; ii = ix; }
+        else if (d == 1) { k = ix + NP * iz; ii = iy; }
+        else { k = ix + NP * iy; ii = iz; }
+    }
+}
+
+// master2slave / slave2master (0-based): StdSegment.jl:145-167, StdQuad.jl:139-181
+template <int ND, int NP>
+__device__ __forceinline__ int master2slave(int i, int o)
+{
+    if (ND <= 1 || o == 0) return i;
+    if (ND == 2) return NP - 1 - i;
+    const int m1 = i % NP, m2 = i / NP;     // 0-based; n - m + 1 (1-based) == NP-1-m (0-based)
+    int a, b;
+    switch (o) {
+    case 1: a = m2; b = NP - 1 - m1; break;
+    case 2: a = NP - 1 - m1; b = NP - 1 - m2; break;
+    case 3: a = NP - 1 - m2; b = m1; break;
+    case 4: a = m2; b = m1; break;
+    case 5: a = NP - 1 - m1; b = m2; break;
+    case 6: a = NP - 1 - m2; b = NP - 1 - m1; break;
+    default: a = m1; b = NP - 1 - m2; break;
+    }
+    return a + NP * b;
+}
+
+template <int ND, int NP>
+__device__ __forceinline__ int slave2master(int i, int o)
+{
+    if (ND <= 1 || o == 0) return i;
+    if (ND == 2) return NP - 1 - i;
+    const int s1 = i % NP, s2 = i / NP;
+    int a, b;
+    switch (o) {
+    case 1: a = NP - 1 - s2; b = s1; break;
+    case 2: a = NP - 1 - s1; b = NP - 1 - s2; break;
+    case 3: a = s2; b = NP - 1 - s1; break;
+    case 4: a = s2; b = s1; break;
+    case 5: a = NP - 1 - s1; b = s2; break;
+    case 6: a = NP - 1 - s2; b = NP - 1 - s1; break;
+    default: a = s1; b = NP - 1 - s2; break;
+    }
+    return a + NP * b;
+}
+
+// Cartesian face frame chosen by the master's element-local face position `pm` (0-based):
+// PhysicalRegions.jl:541-696.  fr = n[ND], t[ND], b[ND].
+template <int ND>
+__device__ __forceinline__ void cart_frame(int pm, double *fr)
+{
+    const int dm = pm >> 1;
+    const double s = (pm & 1) ? 1.0 : -1.0;
+#pragma unroll
+    for (int c = 0; c < 3 * ND; c++) fr[c] = 0.0;
+    fr[dm] = s;
+    if (ND == 2) {
+        // pos1: t=(0,-1)  pos2: t=(0,1)  pos3: t=(1,0)  pos4: t=(-1,0)
+        fr[ND + (1 - dm)] = (dm == 0) ? s : -s;
+    } else if (ND == 3) {
+        const int tm = (dm + 1) % 3, bm = (dm + 2) % 3;
+        fr[ND + tm] = s;
+        fr[2 * ND + bm] = 1.0;
+    }
+}
+
+template <int ND, int EQ>
+__device__ __forceinline__ void rotate2face(const double *Q, const double *fr, double *R)
+{
+    if (EQ == EQ_ADV) { R[0] = Q[0]; return; }
+    R[0] = Q[0];
+    if (ND == 1) { R[1] = Q[1] * fr[0]; }
+    else {
+#pragma unroll
+        for (int r = 0; r < ND; r++) {
+            double s = Q[1] * fr[r * ND];
+#pragma unroll
+            for (int c = 1; c < ND; c++) s += Q[1 + c] * fr[r * ND + c];
+            R[1 + r] = s;
+        }
+    }
+    R[ND + 1] = Q[ND + 1];
+}
+
+template <int ND, int EQ>
+__device__ __forceinline__ void rotate2phys(const double *R, const double *fr, double *Q)
+{
+    if (EQ == EQ_ADV) { Q[0] = R[0]; return; }
+    Q[0] = R[0];
+    if (ND == 1) { Q[1] = R[1] * fr[0]; }
+    else {
+#pragma unroll
+        for (int c = 0; c < ND; c++) {
+            double s = R[1] * fr[c];
+#pragma unroll
+            for (int r = 1; r < ND; r++) s += R[1 + r] * fr[r * ND + c];
+            Q[1 + c] = s;
+        }
+    }
+    Q[ND + 1] = R[ND + 1];
+}
+
+// ------------------------------------------------------------------ kernel configuration
+template <int ND_, int NP_, int EQ_, int VOL_, bool CART_>
+struct KCfg {
+    static constexpr int ND = ND_, NP = NP_, EQ = EQ_, VOL = VOL_;
+    static constexpr bool CART = CART_;
+    static constexpr int NV = (EQ == EQ_ADV) ? 1 : ND + 2;
+    static constexpr int NPTS = ipow_c(NP, ND);
+    static constexpr int NFP = ipow_c(NP, ND - 1);
+    static constexpr int NFACES = 2 * ND;
+    static constexpr int NFT = NFACES * NFP;           // face tasks per element
+    static constexpr int EPB = (NPTS >= 256) ? 1 : 256 / NPTS;
+    static constexpr int THREADS = ((EPB * NPTS + 31) / 32) * 32;
+    // shared-memory layout (doubles), per element
+    static constexpr int NAUX = (EQ == EQ_EULER && VOL != VOL_STRONG) ? ND + 2 : 0;
+    static constexpr int NFT_VOL = (VOL == VOL_STRONG) ? ND * NV : 0;   // contravariant fluxes
+    static constexpr int NMET = CART ? 0 : ND * ND;
+    static constexpr int PER_ELEM = (NV + NAUX + NFT_VOL + NMET) * NPTS + NFACES * NV * NFP;
+    static constexpr int OPS = NP * NP + 4 * NP;
+    static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OPS + EPB * PER_ELEM);
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS)
+stage_kernel(const __grid_constant__ KParams P)
+{
+    constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
+    constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NFT = C::NFT, EPB = C::EPB;
+    constexpr bool CART = C::CART;
+
+    extern __shared__ double smem[];
+    double *sD = smem;                       // [ii + NP*jj]
+    double *sLm = sD + NP * NP, *sLp = sLm + NP, *sGl = sLp + NP, *sGr = sGl + NP;
+    double *sElem = sGr + NP;
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NP * NP; i += C::THREADS) sD[i] = P.Dvol[i];
+    if (tid < NP) { sLm[tid] = P.lm[tid]; sLp[tid] = P.lp[tid]; sGl[tid] = P.dgl[tid]; sGr[tid] = P.dgr[tid]; }
+
+    const int el = tid / NPTS, node = tid - el * NPTS;
+    const int eidx = blockIdx.x * EPB + el;
+    const bool active = (el < EPB) && (eidx < P.elem_count);
+    int e = 0;
+    if (active) e = P.elem_list ? P.elem_list[eidx] : P.elem_first + eidx;
+
+    // per-element shared arrays
+    double *sQ = sElem + (size_t)(el < EPB ? el : 0) * C::PER_ELEM;   // [v][node]
+    double *sA = sQ + NV * NPTS;                                       // aux [a][node]
+    double *sFt = sA + C::NAUX * NPTS;                                 // [d][v][node]
+    double *sM = sFt + C::NFT_VOL * NPTS;                              // [c + ND*d][node]
+    // face fluxes of element `x`: sElem + x*PER_ELEM + FOFF : [lf][v][k]
+    constexpr int FOFF = (NV + C::NAUX + C::NFT_VOL + C::NMET) * NPTS;
+
+    const int64_t ndof = P.ndof;
+    const int64_t dof = (int64_t)e * NPTS + node;
+
+    // ---------------- phase 1: load the element, node primitives, contravariant fluxes
+    double Q[NV];
+    double met[CART ? 1 : ND * ND];
+    if (active) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) { Q[v] = P.u_in[dof + ndof * v]; sQ[v * NPTS + node] = Q[v]; }
+        if (!CART) {
+#pragma unroll
+            for (int m = 0; m < ND * ND; m++) { met[m] = P.metric[dof + ndof * m]; sM[m * NPTS + node] = met[m]; }
+        }
+        if (EQ == EQ_EULER) {
+            NodeAux<ND> A;
+            node_aux<ND>(Q, P.fp.gamma, A);
+            if (!(Q[0] > 0.0) || !(A.p > 0.0)) atomicOr(P.status, 1);
+            if (VOL != VOL_STRONG) {
+#pragma unroll
+                for (int d = 0; d < ND; d++) sA[d * NPTS + node] = A.vel[d];
+                sA[ND * NPTS + node] = A.p;
+                sA[(ND + 1) * NPTS + node] = A.beta;
+            } else {
+#pragma unroll
+                for (int d = 0; d < ND; d++) {
+                    double Fc[NV], Ft[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; v++) Ft[v] = 0.0;
+#pragma unroll
+                    for (int c = 0; c < ND; c++) {
+                        const double m = CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d];
+                        if (CART && c != d) continue;
+                        euler_flux_dir<ND>(Q, A.vel, A.p, c, Fc);
+#pragma unroll
+                        for (int v = 0; v < NV; v++) Ft[v] += Fc[v] * m;
+                    }
+#pragma unroll
+                    for (int v = 0; v < NV; v++) sFt[(d * NV + v) * NPTS + node] = Ft[v];
+                }
+            }
+        } else if (VOL == VOL_STRONG) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) {
+                double an = 0.0;
+#pragma unroll
+                for (int c = 0; c < ND; c++)
+                    an += P.fp.a[c] * (CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d]);
+                sFt[d * NPTS + node] = an * Q[0];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: volume term
+    double acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) acc[v] = 0.0;
+    if (active) {
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+            int k, ii, base, stride;
+            node_line<ND, NP>(node, d, k, ii);
+            line_of<ND, NP>(d, k, base, stride);
+            if (VOL == VOL_STRONG) {
+#pragma unroll
+                for (int jj = 0; jj < NP; jj++) {
+                    const double dij = sD[ii + NP * jj];
+                    const int l = base + jj * stride;
+#pragma unroll
+                    for (int v = 0; v < NV; v++) acc[v] -= dij * sFt[(d * NV + v) * NPTS + l];
+                }
+            } else {
+                // own metric column Ja^d (and primitives) of this node
+                double ni[ND];
+#pragma unroll
+                for (int c = 0; c < ND; c++) ni[c] = CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d];
+                double vi[ND > 0 ? ND : 1], pi = 0.0, bi = 0.0;
+                if (EQ == EQ_EULER) {
+#pragma unroll
+                    for (int c = 0; c < ND; c++) vi[c] = sA[c * NPTS + node];
+                    pi = sA[ND * NPTS + node];
+                    bi = sA[(ND + 1) * NPTS + node];
+                }
+#pragma unroll
+                for (int jj = 0; jj < NP; jj++) {
+                    const double dij = sD[ii + NP * jj];
+                    const int l = base + jj * stride;
+                    double F[NV];
+                    if (jj == ii) {
+                        // diagonal entry: the node's own contravariant flux (OpDivergence.jl:252)
+                        if (EQ == EQ_EULER) {
+#pragma unroll
+                            for (int v = 0; v < NV; v++) F[v] = 0.0;
+#pragma unroll
+                            for (int c = 0; c < ND; c++) {
+                                if (CART && c != d) continue;
+                                double Fc[NV];
+                                euler_flux_dir<ND>(Q, vi, pi, c, Fc);
+#pragma unroll
+                                for (int v = 0; v < NV; v++) F[v] += Fc[v] * ni[c];
+                            }
+                        } else {
+                            double an = 0.0;
+#pragma unroll
+                            for (int c = 0; c < ND; c++) an += P.fp.a[c] * ni[c];
+                            F[0] = an * Q[0];
+                        }
+                    } else {
+                        double n[ND];
+#pragma unroll
+                        for (int c = 0; c < ND; c++)
+                            n[c] = CART ? ni[c] : 0.5 * (ni[c] + sM[(c + ND * d) * NPTS + l]);
+                        if (EQ == EQ_EULER) {
+                            double vl[ND];
+#pragma unroll
+                            for (int c = 0; c < ND; c++) vl[c] = sA[c * NPTS + l];
+                            const double pl = sA[ND * NPTS + l];
+                            if (VOL == VOL_SPLIT_CHA) {
+                                const double bl = sA[(ND + 1) * NPTS + l];
+                                tp_chandrasekhar<ND>(Q[0], vi, pi, bi, sQ[l], vl, pl, bl,
+                                                     P.fp.gamma, n, F);
+                            } else {
+                                double Ql[NV];
+#pragma unroll
+                                for (int v = 0; v < NV; v++) Ql[v] = sQ[v * NPTS + l];
+                                tp_stdavg<ND>(Q, vi, pi, Ql, vl, pl, n, F);
+                            }
+                        } else {
+                            double an = 0.0;
+#pragma unroll
+                            for (int c = 0; c < ND; c++) an += P.fp.a[c] * n[c];
+                            F[0] = an * (Q[0] + sQ[l]) * 0.5;
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < NV; v++) acc[v] -= dij * F[v];
+                }
+            }
+        }
+    }
+
+    // ---------------- phase 3: face tasks (traces, BCs, Riemann flux) -> shared memory
+    {
+        const int nact = min(EPB, P.elem_count - blockIdx.x * EPB);
+        for (int task = tid; task < nact * NFT; task += C::THREADS) {
+            const int tel = task / NFT, r = task - tel * NFT;
+            const int lf = r / NFP, k = r - lf * NFP;
+            const int d = lf >> 1, side = lf & 1;
+            const int teidx = blockIdx.x * EPB + tel;
+            const int te = P.elem_list ? P.elem_list[teidx] : P.elem_first + teidx;
+            const double *tQ = sElem + (size_t)tel * C::PER_ELEM;
+            double *tF = sElem + (size_t)tel * C::PER_ELEM + FOFF;
+
+            // own trace
+            double Qown[NV];
+            int base, stride;
+            line_of<ND, NP>(d, k, base, stride);
+            if (P.colloc) {
+                const int n0 = base + (side ? (NP - 1) * stride : 0);
+#pragma unroll
+                for (int v = 0; v < NV; v++) Qown[v] = tQ[v * NPTS + n0];
+            } else {
+                const double *lv = side ? sLp : sLm;
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int ii = 0; ii < NP; ii++) s += lv[ii] * tQ[v * NPTS + base + ii * stride];
+                    Qown[v] = s;
+                }
+            }
+
+            const Conn cn = P.conn[(int64_t)te * NFACES + lf];
+            const int kind = (cn.info >> 7) & 3;
+            const int nlf = cn.info & 7, orient = (cn.info >> 3) & 7;
+            const bool master = (cn.info >> 6) & 1;
+            // face dof seen from the other side / from the master
+            const int kn = master ? master2slave<ND, NP>(k, orient) : slave2master<ND, NP>(k, orient);
+            const int im = master ? k : kn;          // master face dof: frame and jac index
+
+            double fr[3 * ND], fj;
+            if (CART) {
+                const int pm = master ? lf : nlf;
+                cart_frame<ND>(pm, fr);
+                fj = P.cfjac[pm >> 1];
+            } else {
+                const int64_t fi = (int64_t)P.faceid[(int64_t)te * NFACES + lf] * NFP + im;
+#pragma unroll
+                for (int c = 0; c < 3 * ND; c++) fr[c] = (c < ND * ND || ND == 3) ? P.frames[fi + P.nfacedofs * c] : 0.0;
+                fj = P.fjac[fi];
+            }
+
+            double Qnb[NV];
+            if (kind == FK_INTERIOR) {
+                const int dn = nlf >> 1, sn = nlf & 1;
+                int nb, ns;
+                line_of<ND, NP>(dn, kn, nb, ns);
+                const int64_t nbase = (int64_t)cn.nbr * NPTS + nb;
+                if (P.colloc) {
+                    const int64_t n0 = nbase + (sn ? (NP - 1) * ns : 0);
+#pragma unroll
+                    for (int v = 0; v < NV; v++) Qnb[v] = P.u_in[n0 + ndof * v];
+                } else {
+                    const double *lv = sn ? sLp : sLm;
+#pragma unroll
+                    for (int v = 0; v < NV; v++) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int ii = 0; ii < NP; ii++) s += lv[ii] * P.u_in[nbase + ii * ns + ndof * v];
+                        Qnb[v] = s;
+                    }
+                }
+            } else if (kind == FK_GHOST) {
+#pragma unroll
+                for (int v = 0; v < NV; v++) Qnb[v] = P.ghost[((int64_t)cn.nbr * NV + v) * NFP + kn];
+            } else {
+                // boundary face: exterior state from the BC functor (Interfaces.jl:44-48)
+                const int ib = cn.info >> 9;
+                const int bk = P.bc_kind[ib];
+                if (bk == FLOU_B200_BC_INFLOW) {
+#pragma unroll
+                    for (int v = 0; v < NV; v++) Qnb[v] = P.bc_state[ib * NV + v];
+                } else if (bk == FLOU_B200_BC_OUTFLOW) {
+#pragma unroll
+                    for (int v = 0; v < NV; v++) Qnb[v] = Qown[v];
+                } else if (bk == FLOU_B200_BC_SLIP) {
+                    double R[NV];
+                    rotate2face<ND, EQ>(Qown, fr, R);
+                    if (NV > 1) R[NV > 1 ? 1 : 0] = -R[NV > 1 ? 1 : 0];
+                    rotate2phys<ND, EQ>(R, fr, Qnb);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < NV; v++) Qnb[v] = P.bc_table[((int64_t)cn.nbr * NFP + k) * NV + v];
+                }
+            }
+
+            // Riemann flux with (left = master, right = slave) exactly like the reference
+            double Ql[NV], Qr[NV], Fn[NV], Fp[NV];
+            {
+                double Ro[NV], Rn[NV];
+                rotate2face<ND, EQ>(Qown, fr, Ro);
+                rotate2face<ND, EQ>(Qnb, fr, Rn);
+#pragma unroll
+                for (int v = 0; v < NV; v++) { Ql[v] = master ? Ro[v] : Rn[v]; Qr[v] = master ? Rn[v] : Ro[v]; }
+            }
+            if (EQ == EQ_EULER) {
+                euler_numflux<ND>(P.fp, Ql, Qr, Fn);
+            } else {
+                double an = 0.0;
+#pragma unroll
+                for (int c = 0; c < ND; c++) an += P.fp.a[c] * fr[c];
+                Fn[0] = an * (Ql[0] + Qr[0]) * 0.5;
+                if (P.fp.numflux == FX_LXF) Fn[0] += fabs(an) * (Ql[0] - Qr[0]) * 0.5 * P.fp.intensity;
+            }
+            rotate2phys<ND, EQ>(Fn, fr, Fp);
+            const double sgn = master ? fj : -fj;
+#pragma unroll
+            for (int v = 0; v < NV; v++) tF[(lf * NV + v) * NFP + k] = Fp[v] * sgn;
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 4: lift, mass matrix, RK stage update
+    if (active) {
+        const double *sF = sElem + (size_t)el * C::PER_ELEM + FOFF;
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+            int k, ii;
+            node_line<ND, NP>(node, d, k, ii);
+            const double gl = sGl[ii], gr = sGr[ii];
+#pragma unroll
+            for (int v = 0; v < NV; v++)
+                acc[v] -= gl * sF[((2 * d) * NV + v) * NFP + k] + gr * sF[((2 * d + 1) * NV + v) * NFP + k];
+        }
+        const double jac = CART ? P.cjac : P.jac[dof];
+        if (P.mode == MODE_RHS) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[v] / jac;
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                const double kv = acc[v] / jac;
+                double t;
+                if (P.mode == MODE_STAGE_FIRST) t = P.dt * kv;
+                else t = fma(P.dt, kv, P.rkA * P.tmp[dof + ndof * v]);
+                P.tmp[dof + ndof * v] = t;
+                P.u_out[dof + ndof * v] = fma(P.rkB, t, Q[v]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ halo trace emit
+// Traces of the partition-boundary faces, in this side's face-dof order, packed for
+// ncclSend:  out[(slot*NV + v)*NFP + k].   list[slot] = local element * 2nd + local face.
+template <int ND, int NP, int NV>
+__global__ void emit_traces_kernel(const double *__restrict__ u, int64_t ndof,
+                                   const int *__restrict__ list, int nslots, int colloc,
+                                   const double *__restrict__ lm, const double *__restrict__ lp,
+                                   double *__restrict__ out)
+{
+    constexpr int NPTS = ipow_c(NP, ND), NFP = ipow_c(NP, ND - 1), NFACES = 2 * ND;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nslots * NFP) return;
+    const int slot = (int)(t / NFP), k = (int)(t - (int64_t)slot * NFP);
+    const int ef = list[slot];
+    const int e = ef / NFACES, lf = ef - e * NFACES;
+    const int d = lf >> 1, side = lf & 1;
+    int base, stride;
+    line_of<ND, NP>(d, k, base, stride);
+    const int64_t b0 = (int64_t)e * NPTS + base;
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        double s;
+        if (colloc) {
+            s = u[b0 + (side ? (NP - 1) * stride : 0) + ndof * v];
+        } else {
+            s = 0.0;
+            for (int ii = 0; ii < NP; ii++) s += (side ? lp[ii] : lm[ii]) * u[b0 + ii * stride + ndof * v];
+        }
+        out[((int64_t)slot * NV + v) * NFP + k] = s;
+    }
+}
+
+}  // namespace flou

@@ -1,0 +1,16 @@
+"""flou_b200 -- Python host mirror of Flou.jl's API over the B200 CUDA library.
+
+Same vocabulary as the reference (FlouCommon / FlouSpatial / FlouTime); every numerical
+operation is executed by libflou_b200.so (hand-written sm_100a kernels) through the C ABI
+in include/flou_b200.h.  No CPU fallback exists.
+"""
+from ._lib import DomainError, FlouB200Error, LIB_PATH, device_count, lib
+from .disc import EquationConfig, MultielementDisc, nccl_unique_id, rhs
+from .equations import (ChandrasekharAverage, EulerEquation, EulerInflowBC, EulerOutflowBC,
+                        EulerSlipBC, GenericBC, LinearAdvection, LxF, MatrixDissipation,
+                        ScalarDissipation, SplitDivOperator, StdAverage, StrongDivOperator,
+                        gaussian_bump, normal_shockwave, nvariables, soundvelocity, spatialdim,
+                        vars_prim2cons)
+from .mesh import CartesianMesh, apply_periodicBCs, partition_offsets
+from .stdregions import DGSEMrec, LagrangeBasis, StdHex, StdQuad, StdSegment
+from .time import CarpenterKennedy2N54, ORK256, Solution, advance, timeintegrate

@@ -1,0 +1,196 @@
+"""Host-side mirror of Flou.jl's equation, numerical-flux, operator and BC types.
+
+Same names and argument meaning as the reference so user scripts read alike:
+  LinearAdvection(a...)            src/FlouCommon/LinearAdvection.jl:16-26
+  EulerEquation{ND}(gamma)         src/FlouCommon/Euler.jl:16-24
+  StdAverage, LxF                  src/FlouSpatial/Interfaces.jl:16-23
+  ChandrasekharAverage, ScalarDissipation, MatrixDissipation
+                                   src/FlouSpatial/Equations/Euler.jl:167,228-231,303-306
+  StrongDivOperator, SplitDivOperator   src/FlouSpatial/Equations/OpDivergence.jl:105,184-194
+  EulerInflowBC/OutflowBC/SlipBC   src/FlouSpatial/Equations/Euler.jl:69-94
+  GenericBC                        src/FlouSpatial/FlouSpatial.jl:85-91
+These objects only carry parameters; all arithmetic happens in the CUDA library.
+"""
+from dataclasses import dataclass
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+# ------------------------------------------------------------------ equations
+class LinearAdvection:
+    def __init__(self, *velocity):
+        if not 1 <= len(velocity) <= 3:
+            raise ValueError("Linear advection is implemented in 1D, 2D and 3D.")
+        self.a = tuple(float(v) for v in velocity)
+        self.nd = len(velocity)
+        self.nv = 1
+        self.kind = L.EQ_LINEAR_ADVECTION
+
+    def variablenames(self, unicode=False):
+        return ("u",)
+
+
+class EulerEquation:
+    def __init__(self, nd, gamma):
+        if not 1 <= nd <= 3:
+            raise ValueError("The Euler equations are only implemented in 1D, 2D and 3D.")
+        self.nd = int(nd)
+        self.nv = self.nd + 2
+        self.gamma = float(gamma)
+        self.kind = L.EQ_EULER
+
+    def variablenames(self, unicode=False):
+        names = (("ρ", "ρu", "ρv", "ρw") if unicode else ("rho", "rhou", "rhov", "rhow"))[:self.nd + 1]
+        return names + (("ρe",) if unicode else ("rhoe",))
+
+
+def nvariables(eq):
+    return eq.nv
+
+
+def spatialdim(eq):
+    return eq.nd
+
+
+def vars_prim2cons(P, eq):
+    """src/FlouCommon/Euler.jl:255-271 (host helper for initial/boundary data)."""
+    P = np.asarray(P, dtype=np.float64)
+    nd = eq.nd
+    rho, vel, p = P[0], P[1:1 + nd], P[nd + 1]
+    rhoe = p / (eq.gamma - 1) + rho * float(np.sum(vel * vel)) / 2
+    return np.concatenate(([rho], rho * vel, [rhoe]))
+
+
+def soundvelocity(rho, p, eq):
+    return float(np.sqrt(eq.gamma * p / rho))
+
+
+def normal_shockwave(rho0, u0, p0, eq):
+    """src/FlouCommon/Euler.jl:337-358."""
+    g = eq.gamma
+    a = soundvelocity(rho0, p0, eq)
+    M0 = u0 / a
+    rho1 = rho0 * M0 ** 2 * (g + 1) / ((g - 1) * M0 ** 2 + 2)
+    p1 = p0 * (2 * g * M0 ** 2 - (g - 1)) / (g + 1)
+    M1 = np.sqrt(((g - 1) * M0 ** 2 + 2) / (2 * g * M0 ** 2 - (g - 1)))
+    return rho1, M1 * soundvelocity(rho1, p1, eq), p1
+
+
+def gaussian_bump(*args):
+    """src/FlouCommon/Utilities.jl:16-32: (x, x0, sx, h), (x, y, x0, y0, sx, sy, h) or 3-D."""
+    n = (len(args) - 1) // 3
+    x, x0, s, h = args[:n], args[n:2 * n], args[2 * n:3 * n], args[-1]
+    e = 0.0
+    for xi, x0i, si in zip(x, x0, s):
+        e = e - (xi - x0i) ** 2 / (2 * si ** 2)
+    return h * np.exp(e)
+
+
+# ------------------------------------------------------------------ numerical fluxes
+@dataclass(frozen=True)
+class StdAverage:
+    kind: int = L.FLUX_STDAVERAGE
+
+
+@dataclass(frozen=True)
+class ChandrasekharAverage:
+    kind: int = L.FLUX_CHANDRASEKHAR
+
+
+@dataclass(frozen=True)
+class LxF:
+    avg: object
+    intensity: float
+    kind: int = L.FLUX_LXF
+
+
+@dataclass(frozen=True)
+class ScalarDissipation:
+    avg: object
+    intensity: float
+    kind: int = L.FLUX_SCALARDISSIPATION
+
+
+@dataclass(frozen=True)
+class MatrixDissipation:
+    avg: object
+    intensity: float
+    kind: int = L.FLUX_MATRIXDISSIPATION
+
+
+# ------------------------------------------------------------------ divergence operators
+class StrongDivOperator:
+    def __init__(self, numflux):
+        self.numflux = numflux
+        self.tpflux = None
+        self.kind = L.OP_STRONG
+
+
+class SplitDivOperator:
+    """SplitDivOperator([tpflux=numflux.avg], numflux)  (OpDivergence.jl:184-194)."""
+
+    def __init__(self, *args):
+        if len(args) == 1:
+            (numflux,) = args
+            tpflux = numflux.avg
+        elif len(args) == 2:
+            tpflux, numflux = args
+        else:
+            raise TypeError("SplitDivOperator([tpflux], numflux)")
+        if not isinstance(tpflux, (StdAverage, ChandrasekharAverage)):
+            raise ValueError("the two-point flux must be StdAverage or ChandrasekharAverage")
+        self.tpflux, self.numflux = tpflux, numflux
+        self.kind = L.OP_SPLIT
+
+
+# ------------------------------------------------------------------ boundary conditions
+class EulerInflowBC:
+    def __init__(self, Qext: Sequence[float]):
+        if not 3 <= len(Qext) <= 5:
+            raise ValueError("`Qext` must have a length of 3, 4 or 5.")
+        self.Qext = np.asarray(Qext, dtype=np.float64)
+        self.kind = L.BC_INFLOW
+
+
+class EulerOutflowBC:
+    kind = L.BC_OUTFLOW
+
+
+class EulerSlipBC:
+    kind = L.BC_SLIP
+
+
+class GenericBC:
+    """GenericBC(Qext) with `Qext(Qin, x, frame, time, eq)`.
+
+    On the device only closures that depend on the position `x` alone are supported: they are
+    tabulated once per boundary-face node when the discretisation is built (this covers
+    every use in the reference's tests, test/tests.jl:103-113,152-159).  A closure reading
+    `Qin`, `frame` or `time` raises at construction time instead of silently falling back to
+    the host.
+    """
+    kind = L.BC_TABLE
+
+    def __init__(self, Qext: Callable):
+        self.Qext = Qext
+
+    def tabulate(self, x, eq):
+        return np.asarray(self.Qext(_Forbidden("Qin"), x, _Forbidden("frame"), _Forbidden("time"), eq),
+                          dtype=np.float64)
+
+
+class _Forbidden:
+    def __init__(self, what):
+        self._what = what
+
+    def _raise(self, *a, **k):
+        raise ValueError(
+            f"GenericBC closures may only depend on the coordinates on the B200 path; "
+            f"this one reads `{self._what}`")
+
+    __getitem__ = __iter__ = __float__ = __add__ = __radd__ = __mul__ = __rmul__ = _raise
+    __sub__ = __rsub__ = __neg__ = __lt__ = __gt__ = __le__ = __ge__ = __len__ = _raise
+    __truediv__ = __rtruediv__ = __array__ = _raise

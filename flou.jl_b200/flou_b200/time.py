@@ -1,0 +1,98 @@
+"""FlouTime on the B200 library.
+
+  timeintegrate(Q0, disc, equation, solver, tfinal; adaptive=false, dt, alias_u0=true, ...)
+                                   src/FlouTime/FlouTime.jl:34-54
+  ORK256 / CarpenterKennedy2N54    OrdinaryDiffEq v6.49.1 `LowStorageRK2N` tableaus
+                                   (third-party; used at test/tests.jl:19,56,93,139 and
+                                   examples/src/Convergence.jl:27)
+The 2N recurrence  tmp = A_s*tmp + dt*k ; u = u + B_s*tmp  runs fused with the RHS inside
+the stage kernel; the host only enqueues stages.
+"""
+import ctypes as C
+import time as _time
+
+import numpy as np
+
+from . import _lib as L
+from .disc import _ptr, _state
+
+
+class _LowStorageRK2N:
+    A = B = c = ()
+
+    def __init__(self, williamson_condition=False, stage_limiter=None, step_limiter=None):
+        if williamson_condition:
+            raise ValueError("williamson_condition=true (ArrayFuse path) is not supported; the "
+                             "reference always passes williamson_condition=false")
+        if stage_limiter is not None or step_limiter is not None:
+            raise ValueError("stage/step limiters are outside the B200 hot path")
+
+    @property
+    def nstages(self):
+        return len(self.B)
+
+
+class ORK256(_LowStorageRK2N):
+    A = (0.0, -1.0, -1.55798, -1.0, -0.45031)
+    B = (0.2, 0.83204, 0.6, 0.35394, 0.2)
+    c = (0.0, 0.2, 0.2, 0.8, 0.8)
+
+
+class CarpenterKennedy2N54(_LowStorageRK2N):
+    A = (0.0, -567301805773 / 1357537059087, -2404267990393 / 2016746695238,
+         -3550918686646 / 2091501179385, -1275806237668 / 842570457699)
+    B = (1432997174477 / 9575080441755, 5161836677717 / 13612068292357,
+         1720146321549 / 2090206949498, 3134564353537 / 4481467310338,
+         2277821191437 / 14882151754819)
+    c = (0.0, 1432997174477 / 9575080441755, 2526269341429 / 6820363962896,
+         2006345519317 / 3224310063776, 2802321613138 / 2924317926251)
+
+
+def _tab(solver):
+    return (np.array(solver.A, dtype=np.float64), np.array(solver.B, dtype=np.float64),
+            np.array(solver.c, dtype=np.float64))
+
+
+def advance(disc, solver, dt, nsteps, t0=0.0):
+    """Device-resident fast path: nsteps RK steps on the uploaded state (asynchronous)."""
+    A, B, c = _tab(solver)
+    L.check(L.lib().flou_b200_lsrk2n_advance(disc.handle, solver.nstages, _ptr(A), _ptr(B), _ptr(c),
+                                             float(dt), float(t0), int(nsteps)))
+
+
+class Solution:
+    """Minimal stand-in for the ODE solution: `u[0]` initial and `u[-1]` final state, `t`."""
+
+    def __init__(self, u0, u1, t0, t1):
+        self.u = [u0, u1]
+        self.t = [t0, t1]
+
+
+def timeintegrate(Q0, disc, equation, solver, tfinal, *, dt, adaptive=False, alias_u0=True,
+                  saveat=None, save_everystep=False, callback=None, t0=0.0, nsteps=None):
+    """Returns (sol, exetime) like the reference; `Q0` is overwritten when alias_u0=True.
+
+    Only fixed-step integration (`adaptive=false`) without callbacks is on the hot path."""
+    if adaptive:
+        raise ValueError("adaptive=true is not supported (the reference always uses adaptive=false)")
+    if callback is not None:
+        raise ValueError("callbacks are outside the B200 hot path")
+    if equation is not disc.equation:
+        raise ValueError("`equation` is not the one the discretisation was built with")
+    Q = _state(Q0, disc.ndofs, disc.nv, writable=alias_u0)
+    u0 = Q.copy(order="F")
+    if not alias_u0:
+        Q = u0.copy(order="F")
+    if nsteps is None:
+        nsteps = int(round((tfinal - t0) / dt))
+    A, B, c = _tab(solver)
+    tic = _time.perf_counter()
+    try:
+        L.check(L.lib().flou_b200_timeintegrate(disc.handle, _ptr(Q), solver.nstages, _ptr(A),
+                                                _ptr(B), _ptr(c), float(dt), float(t0),
+                                                int(nsteps)))
+    except L.DomainError:
+        # FlouTime.jl:39-51: log and return `nothing` for the solution
+        print("ERROR: Simulation crashed!")
+        return None, _time.perf_counter() - tic
+    return Solution(u0, Q, t0, t0 + nsteps * dt), _time.perf_counter() - tic

@@ -1,0 +1,205 @@
+/* flou_b200.h -- C ABI of the B200-native DGSEM right-hand side + low-storage RK library.
+ *
+ * Drop-in boundary for ONE hot path of Andres-MG/Flou.jl (reference paths are relative to
+ * the reference repository root):
+ *
+ *   rhs!(dQ, Q, ::EquationConfig, t)          src/FlouSpatial/Equations/Hyperbolic.jl:31-69
+ *   timeintegrate(Q0, disc, eq, solver, tf)   src/FlouTime/FlouTime.jl:34-54  (the 2N RK loop
+ *                                             itself lives in OrdinaryDiffEq v6.49.1)
+ *   MultielementDisc(mesh, std, eq, op, bcs)  src/FlouSpatial/MultielementDiscontinuous.jl:29-92
+ *
+ * The host (Julia through `ccall`; Python/ctypes in this repository's
+ * tests and benchmark) keeps building meshes, standard regions, operators and boundary
+ * conditions with Flou's own types and hands their plain arrays to `flou_b200_create`.
+ * Everything after that runs in hand-written sm_100a CUDA kernels; there is no CPU
+ * fallback -- every entry point fails with FLOU_B200_ECUDA when no device is usable.
+ *
+ * Conventions
+ *   - all entry points return int32 status (0 = OK) and never abort/exit;
+ *   - ids in connectivity tables are 1-BASED exactly as Flou stores them
+ *     (src/FlouCommon/Mesh.jl:26-150); 0 in `eleminds` means "no element";
+ *   - matrices are column-major (Julia `Matrix`): state Q is (ndofs, nv) so variable v of
+ *     dof i is Q[i + ndofs*v]  (src/FlouSpatial/GlobalContainers.jl:19-29,92-105);
+ *   - host pointers are borrowed for the duration of the call only;
+ *   - one handle = one GPU, one compute stream, one communication stream; calls on a
+ *     handle are stream-ordered and not thread-safe.
+ */
+#ifndef FLOU_B200_H
+#define FLOU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+#define FLOU_B200_OK       0
+#define FLOU_B200_EINVAL   1   /* bad descriptor / argument (Julia: ArgumentError)          */
+#define FLOU_B200_ECUDA    2   /* CUDA failure or no usable device                           */
+#define FLOU_B200_ENCCL    3   /* NCCL failure                                               */
+#define FLOU_B200_EDOMAIN  4   /* rho <= 0, p <= 0 or NaN met on device (Julia: DomainError,
+                                  cf. FlouTime.jl:37-52 "Simulation crashed!")               */
+#define FLOU_B200_EUNSUPPORTED 5 /* combination not compiled into the library               */
+
+/* equations: src/FlouCommon/LinearAdvection.jl:16-18, src/FlouCommon/Euler.jl:16-24 */
+#define FLOU_B200_EQ_LINEAR_ADVECTION 0
+#define FLOU_B200_EQ_EULER            1
+
+/* divergence operators: src/FlouSpatial/Equations/OpDivergence.jl:105 (Strong), :184 (Split) */
+#define FLOU_B200_OP_STRONG 0
+#define FLOU_B200_OP_SPLIT  1
+
+/* numerical-flux structs: src/FlouSpatial/Interfaces.jl:16-23,
+ * src/FlouSpatial/Equations/Euler.jl:167,228-231,303-306 */
+#define FLOU_B200_FLUX_STDAVERAGE        0
+#define FLOU_B200_FLUX_LXF               1
+#define FLOU_B200_FLUX_CHANDRASEKHAR     2
+#define FLOU_B200_FLUX_SCALARDISSIPATION 3
+#define FLOU_B200_FLUX_MATRIXDISSIPATION 4
+
+/* boundary-condition functors: src/FlouSpatial/Equations/Euler.jl:69-94,
+ * src/FlouSpatial/FlouSpatial.jl:85-91 (GenericBC).  A GenericBC whose closure depends only
+ * on the face-node coordinates is passed as a TABLE evaluated by the host at create time. */
+#define FLOU_B200_BC_INFLOW  0   /* EulerInflowBC(Qext): bc_state row                        */
+#define FLOU_B200_BC_OUTFLOW 1   /* EulerOutflowBC                                           */
+#define FLOU_B200_BC_SLIP    2   /* EulerSlipBC                                              */
+#define FLOU_B200_BC_TABLE   3   /* GenericBC(x -> Qext) tabulated per boundary-face node    */
+
+/* geometry kinds */
+#define FLOU_B200_GEOM_CARTESIAN 0  /* CartesianMesh: constant metrics from dx, frames chosen
+                                       by the master's elempos (PhysicalRegions.jl:370-408,
+                                       541-696)                                              */
+#define FLOU_B200_GEOM_GENERAL   1  /* per-node jac/metric, per-face-node frames/jac
+                                       (PhysicalRegions.jl:438-472, 797-971)                 */
+
+typedef struct flou_b200_handle flou_b200_handle;
+
+/* Everything `MultielementDisc` + `EquationConfig` hold that the hot path reads
+ * (SURVEY.md section 8(a) row a15). */
+typedef struct flou_b200_desc {
+    int32_t struct_size;      /* sizeof(flou_b200_desc), ABI check                           */
+    int32_t nd;               /* spatial dimension 1..3                                      */
+    int32_t nv;               /* variables: 1 (advection) or nd+2 (Euler)                    */
+    int32_t np;               /* nodes per direction (p+1), 2..8                             */
+    int32_t equation;         /* FLOU_B200_EQ_*                                              */
+    int32_t divop;            /* FLOU_B200_OP_*        (disc.operators[1])                   */
+    int32_t tpflux;           /* SplitDivOperator.tpflux: STDAVERAGE | CHANDRASEKHAR         */
+    int32_t numflux;          /* operator.numflux kind                                       */
+    int32_t numflux_avg;      /* numflux.avg for LxF / Scalar- / MatrixDissipation           */
+    int32_t geometry;         /* FLOU_B200_GEOM_*                                            */
+    double intensity;         /* numflux.intensity                                           */
+    double gamma;             /* EulerEquation.gamma                                         */
+    double a[3];              /* LinearAdvection.a                                           */
+    double dx[3];             /* CartesianMesh.dx (GEOM_CARTESIAN)                           */
+
+    /* mesh connectivity, GLOBAL tables in the reference's layout and numbering */
+    int64_t ne;               /* nelements(mesh)                                             */
+    int64_t nf;               /* nfaces(mesh)                                                */
+    const int64_t *faceinds;  /* ne*2nd : mesh.elements.faceinds  (Mesh.jl:26-33)            */
+    const int64_t *facepos;   /* ne*2nd : mesh.elements.facepos   1 = master, 2 = slave      */
+    const int64_t *eleminds;  /* nf*2   : mesh.faces.eleminds     (Mesh.jl:91-99)            */
+    const int64_t *elempos;   /* nf*2   : mesh.faces.elempos                                 */
+    const uint8_t *orientation; /* nf   : mesh.faces.orientation                             */
+
+    /* 1-D operators of the standard region (StdSegment.jl:76-89), np x np column-major */
+    const double *D;          /* std.D   (unused by the kernels, kept for completeness)      */
+    const double *Ds;         /* std.Ds  = D - B                                             */
+    const double *Dsharp;     /* std.D♯  = 2D - B                                            */
+    const double *lminus;     /* std.l[1]                                                    */
+    const double *lplus;      /* std.l[2]                                                    */
+    const double *dgminus;    /* std.∂g[1]                                                   */
+    const double *dgplus;     /* std.∂g[2]                                                   */
+
+    /* GEOM_GENERAL only (NULL otherwise); indexed by GLOBAL dof / face-dof */
+    const double *jac;        /* ne*npts            geometry.elements.jac                    */
+    const double *metric;     /* ne*npts*nd*nd      geometry.elements.metric, each SMatrix
+                                                    column-major: [c + nd*d] = Ja^d_c        */
+    const double *fjac;       /* nf*nfp             geometry.faces.jac                       */
+    const double *frames;     /* nf*nfp*3*nd        geometry.faces.frames: n, t, b           */
+
+    /* boundary conditions in mesh.bdfaces order (MultielementDiscontinuous.jl:45-51) */
+    int32_t nbound;
+    const int32_t *bc_kind;   /* nbound                                                      */
+    const int64_t *bc_offsets;/* nbound+1 offsets into bc_faces                              */
+    const int64_t *bc_faces;  /* concatenated mesh.bdfaces (1-based face ids)                */
+    const double *bc_state;   /* nbound*nv  row per boundary (INFLOW)                        */
+    const double *bc_table;   /* (len(bc_faces)*nfp)*nv, row per boundary-face node (TABLE)  */
+
+    /* element partition (new; the reference is shared-memory only): this handle owns the
+     * contiguous range [elem_begin, elem_end) of 0-based global element indices, and
+     * part_offsets[0..nranks] lists every rank's range start (part_offsets[nranks] = ne). */
+    int64_t elem_begin, elem_end;
+    int32_t rank, nranks;
+    const int64_t *part_offsets;  /* NULL when nranks == 1 */
+
+    int32_t device;           /* CUDA device ordinal                                         */
+    int32_t flags;            /* FLOU_B200_FLAG_* */
+} flou_b200_desc;
+
+#define FLOU_B200_FLAG_NO_GRAPH 1  /* launch stages directly instead of replaying a CUDA graph */
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* Replaces MultielementDisc(...) + construct_cache (Hyperbolic.jl:21-29): uploads tables,
+ * allocates u (x2, ping-pong), tmp and k on the device. */
+int32_t flou_b200_create(const flou_b200_desc *desc, flou_b200_handle **out);
+int32_t flou_b200_destroy(flou_b200_handle *h);
+
+/* ---- state ----------------------------------------------------------------------------- */
+/* Q is the (ndofs_local, nv) column-major matrix of the OWNED elements (Q.data of
+ * GlobalStateVector restricted to the rank's rows). */
+int32_t flou_b200_upload_state(flou_b200_handle *h, const double *Q);
+int32_t flou_b200_download_state(flou_b200_handle *h, double *Q);
+
+/* ---- hot path -------------------------------------------------------------------------- */
+/* rhs!(dQ, Q, p, t)  (Hyperbolic.jl:31-69).  Q == NULL: use the device-resident state;
+ * dQ == NULL: leave the result in the device `k` buffer. Synchronises before returning. */
+int32_t flou_b200_rhs(flou_b200_handle *h, const double *Q, double *dQ, double t);
+
+/* OrdinaryDiffEq `LowStorageRK2N` steps on the device-resident state (a14 in SURVEY 8a):
+ *   stage 1: tmp = dt*k;              u += B[0]*tmp
+ *   stage s: tmp = A[s]*tmp + dt*k;   u += B[s]*tmp          (A[0] ignored)
+ * each stage is ONE fused kernel pass (RHS + update).  Asynchronous: returns after
+ * enqueueing; use flou_b200_synchronize / download / status to wait. */
+int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const double *A,
+                                 const double *B, const double *c, double dt, double t0,
+                                 int64_t nsteps);
+
+/* timeintegrate(Q0, disc, eq, solver, tf; adaptive=false, dt, alias_u0=true)
+ * (FlouTime.jl:34-54): upload Q, advance nsteps, download into the same buffer, report
+ * FLOU_B200_EDOMAIN if the state left the admissible set. */
+int32_t flou_b200_timeintegrate(flou_b200_handle *h, double *Q, int32_t nstages,
+                                const double *A, const double *B, const double *c,
+                                double dt, double t0, int64_t nsteps);
+
+int32_t flou_b200_synchronize(flou_b200_handle *h);
+/* sticky device flags: bit 0 = non-positive density/pressure or NaN seen */
+int32_t flou_b200_status(flou_b200_handle *h, int32_t *flags);
+const char *flou_b200_last_error(void);
+
+/* ---- introspection (benchmarks, tests) --------------------------------------------------- */
+int64_t flou_b200_ndofs_local(const flou_b200_handle *h);
+void *flou_b200_stream(flou_b200_handle *h);         /* cudaStream_t of the compute stream   */
+void *flou_b200_device_state(flou_b200_handle *h);   /* device pointer of the current u      */
+int64_t flou_b200_kernel_launches(const flou_b200_handle *h); /* stage/rhs/halo kernels so far */
+/* CUDA-event stopwatch on the compute stream (kernel timing for the roofline figure) */
+int32_t flou_b200_timer_start(flou_b200_handle *h);
+int32_t flou_b200_timer_stop(flou_b200_handle *h, float *ms);
+/* page-lock a host buffer the caller owns (e.g. Julia's Q.data) so uploads/downloads run at
+ * full PCIe rate; optional */
+int32_t flou_b200_pin_host(void *ptr, uint64_t bytes);
+int32_t flou_b200_unpin_host(void *ptr);
+int32_t flou_b200_device_count(void);
+int32_t flou_b200_supported(int32_t nd, int32_t np, int32_t equation, int32_t divop,
+                            int32_t tpflux, int32_t geometry);
+
+/* ---- multi-GPU (one process per GPU) ----------------------------------------------------- */
+/* Halo face traces travel with ncclSend/ncclRecv over NVLink on the communication stream,
+ * overlapped with the interior-element kernel.  `id` is an ncclUniqueId (128 bytes). */
+int32_t flou_b200_nccl_unique_id(char id[128]);
+int32_t flou_b200_comm_init(flou_b200_handle *h, const char id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOU_B200_H */

@@ -1,0 +1,148 @@
+"""Shared builders: the same case assembled twice, once for the oracle (CPU restatement)
+and once for the product (Python host mirror -> C ABI -> CUDA)."""
+import numpy as np
+
+import oracle as O
+from oracle import connectivity as ocn
+
+SEED = 20230917   # reproducible random admissible state
+
+_FLUX_O = {"std": O.FLUX_STDAVG, "lxf": O.FLUX_LXF, "cha": O.FLUX_CHANDRASEKHAR,
+           "sca": O.FLUX_SCALARDISS, "mat": O.FLUX_MATRIXDISS}
+
+
+def box(nd):
+    return [0.0] * nd, [1.0 + 0.5 * d for d in range(nd)]
+
+
+def random_state(ndof, nd, eq, gamma=1.4, seed=SEED):
+    rng = np.random.default_rng(seed)
+    if eq == "adv":
+        return np.asfortranarray(rng.uniform(-1.0, 1.0, size=(ndof, 1)))
+    rho = rng.uniform(0.5, 1.5, ndof)
+    vel = rng.uniform(-0.5, 0.5, (ndof, nd))
+    p = rng.uniform(0.5, 1.5, ndof)
+    Q = np.zeros((ndof, nd + 2), order="F")
+    Q[:, 0] = rho
+    for d in range(nd):
+        Q[:, 1 + d] = rho * vel[:, d]
+    Q[:, nd + 1] = p / (gamma - 1) + 0.5 * rho * np.sum(vel ** 2, axis=1)
+    return Q
+
+
+def smooth_state(coords, nd, eq, gamma=1.4):
+    x = coords
+    s = np.ones(len(x))
+    for d in range(nd):
+        s = s * np.sin(2 * np.pi * x[:, d] / (1.0 + 0.5 * d) + 0.3 * d)
+    if eq == "adv":
+        return np.asfortranarray((1.0 + 0.5 * s)[:, None])
+    rho = 1.0 + 0.2 * s
+    vel = np.stack([0.3 * np.cos(2 * np.pi * x[:, d] / (1.0 + 0.5 * d)) * (1 + 0.1 * s)
+                    for d in range(nd)], axis=1)
+    p = 1.0 + 0.1 * s
+    Q = np.zeros((len(x), nd + 2), order="F")
+    Q[:, 0] = rho
+    for d in range(nd):
+        Q[:, 1 + d] = rho * vel[:, d]
+    Q[:, nd + 1] = p / (gamma - 1) + 0.5 * rho * np.sum(vel ** 2, axis=1)
+    return Q
+
+
+def perturb(nodes, amp, seed=7):
+    rng = np.random.default_rng(seed)
+    return nodes + amp * rng.uniform(-1.0, 1.0, nodes.shape)
+
+
+class Case:
+    """One discretisation described independently of either implementation."""
+
+    def __init__(self, nd, n, npn, nodes="GLL", eq="euler", op="split", tp=None, nf="mat",
+                 avg="cha", intensity=1.0, periodic="all", bcs=None, general=False,
+                 perturb_amp=0.0, gamma=1.4, a=(2.0, -1.0, 0.5)):
+        self.nd, self.n, self.np, self.nodes = nd, tuple(n), npn, nodes
+        self.eq, self.op, self.tp, self.nf, self.avg = eq, op, tp, nf, avg
+        self.intensity, self.gamma, self.a = intensity, gamma, tuple(a[:nd])
+        if periodic == "all":
+            periodic = [(str(2 * d + 1), str(2 * d + 2)) for d in range(nd)]
+        self.periodic = list(periodic or [])
+        self.bcs = bcs or {}
+        self.general = general or perturb_amp > 0
+        self.perturb_amp = perturb_amp
+
+    def __repr__(self):
+        return (f"{self.nd}D n={self.n} np={self.np} {self.nodes} {self.eq} {self.op}"
+                f"{'/' + self.tp if self.tp else ''} {self.nf}({self.avg}) "
+                f"{'general' if self.general else 'cart'} per={len(self.periodic)}")
+
+    # ---------------------------------------------------------------- oracle side
+    def oracle(self):
+        start, finish = box(self.nd)
+        mesh = ocn.cartesian_mesh(start, finish, self.n)
+        if self.perturb_amp > 0:
+            h = min(mesh.dx)
+            mesh.nodes = perturb(mesh.nodes, self.perturb_amp * h)
+        ocn.apply_periodic_bcs(mesh, *self.periodic)
+        g = self.gamma
+        bcs = {}
+        for name, (kind, param) in self.bcs.items():
+            if kind == "inflow":
+                bcs[name] = (O.BC_INFLOW, np.asarray(param, dtype=float))
+            elif kind == "outflow":
+                bcs[name] = (O.BC_OUTFLOW, None)
+            elif kind == "slip":
+                bcs[name] = (O.BC_SLIP, None)
+            else:
+                bcs[name] = (O.BC_TABLE, param)
+        return O.Problem(
+            mesh, self.nodes, self.np,
+            O.EQ_ADVECTION if self.eq == "adv" else O.EQ_EULER,
+            O.OP_STRONG if self.op == "strong" else O.OP_SPLIT,
+            _FLUX_O[self.nf], tpflux=_FLUX_O[self.tp] if self.tp else None,
+            numflux_avg=_FLUX_O[self.avg], intensity=self.intensity, gamma=g, a=self.a,
+            bcs=bcs, cartesian=not self.general)
+
+    # ---------------------------------------------------------------- product side
+    def product(self, rank=0, nranks=1, device=0, use_graph=True):
+        import flou_b200 as F
+        start, finish = box(self.nd)
+        mesh = F.CartesianMesh(self.nd, start, finish, self.n)
+        if self.perturb_amp > 0:
+            h = min(mesh.dx)
+            mesh.nodes = perturb(mesh.nodes, self.perturb_amp * h)
+        mesh.apply_periodicBCs(*self.periodic)
+        eq = F.LinearAdvection(*self.a) if self.eq == "adv" else F.EulerEquation(self.nd, self.gamma)
+        basis = F.LagrangeBasis(self.nodes, self.np)
+        rec = F.DGSEMrec(basis)
+        std = {1: F.StdSegment, 2: F.StdQuad, 3: F.StdHex}[self.nd](basis, rec, eq.nv)
+        avg = {"std": F.StdAverage(), "cha": F.ChandrasekharAverage()}[self.avg]
+        nf = {"std": F.StdAverage(), "cha": F.ChandrasekharAverage(),
+              "lxf": F.LxF(avg, self.intensity), "sca": F.ScalarDissipation(avg, self.intensity),
+              "mat": F.MatrixDissipation(avg, self.intensity)}[self.nf]
+        if self.op == "strong":
+            op = F.StrongDivOperator(nf)
+        elif self.tp:
+            op = F.SplitDivOperator({"std": F.StdAverage(), "cha": F.ChandrasekharAverage()}[self.tp], nf)
+        elif self.nf in ("std", "cha"):
+            op = F.SplitDivOperator(nf, nf)
+        else:
+            op = F.SplitDivOperator(nf)
+        bcs = {}
+        for name, (kind, param) in self.bcs.items():
+            if kind == "inflow":
+                bcs[name] = F.EulerInflowBC(param)
+            elif kind == "outflow":
+                bcs[name] = F.EulerOutflowBC()
+            elif kind == "slip":
+                bcs[name] = F.EulerSlipBC()
+            else:
+                bcs[name] = F.GenericBC(lambda Qin, x, frame, t, eq_, f=param: f(x))
+        disc = F.MultielementDisc(mesh, std, eq, op, bcs, rank=rank, nranks=nranks, device=device,
+                                  geometry="general" if self.general else None,
+                                  use_graph=use_graph)
+        return disc, eq
+
+
+def relerr(a, b):
+    """inf-norm error relative to max|b|."""
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))

@@ -1,0 +1,35 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "flou.jl_b200"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu)")
+
+
+def _has_gpu():
+    try:
+        import flou_b200
+        return flou_b200.device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # `-m gpu` on a box without a GPU must fail loudly, not skip: a silent pass would hide
+    # a missing CUDA path.  `-m "not gpu"` never touches these tests.
+    pass
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    import flou_b200
+    n = flou_b200.device_count()
+    if n <= 0:
+        pytest.fail("no CUDA device visible: the B200 path has no CPU fallback")
+    return n

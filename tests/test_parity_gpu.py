@@ -1,0 +1,187 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+Bar (BASELINE.json north_star): fp64 RHS within 1e-12 relative; connectivity bit-exact."""
+import numpy as np
+import pytest
+
+from common import Case, random_state, relerr, smooth_state
+
+RHS_TOL = 1e-12
+
+CASES = [
+    # config 1 family: linear advection, strong form, LxF, GL and GLL nodes
+    Case(2, (6, 5), 4, nodes="GL", eq="adv", op="strong", nf="lxf", avg="std"),
+    Case(2, (6, 5), 4, nodes="GLL", eq="adv", op="strong", nf="lxf", avg="std"),
+    Case(1, (9,), 5, nodes="GL", eq="adv", op="strong", nf="lxf", avg="std"),
+    Case(3, (3, 4, 2), 3, nodes="GL", eq="adv", op="strong", nf="std", avg="std"),
+    Case(2, (4, 4), 4, nodes="GLL", eq="adv", op="split", nf="lxf", avg="std"),
+    # config 2/3 family: Euler, EC split form + matrix dissipation
+    Case(1, (10,), 4, nodes="GLL", eq="euler", op="split", nf="mat", avg="cha"),
+    Case(2, (5, 4), 5, nodes="GLL", eq="euler", op="split", nf="mat", avg="cha"),
+    Case(3, (3, 3, 4), 4, nodes="GLL", eq="euler", op="split", nf="mat", avg="cha"),
+    Case(3, (2, 3, 2), 5, nodes="GLL", eq="euler", op="split", nf="mat", avg="cha"),
+    # every other flux / operator combination the reference offers
+    Case(2, (4, 3), 4, nodes="GLL", eq="euler", op="strong", nf="lxf", avg="std"),
+    Case(2, (4, 3), 4, nodes="GL", eq="euler", op="strong", nf="lxf", avg="cha"),
+    Case(3, (2, 2, 3), 3, nodes="GL", eq="euler", op="strong", nf="std", avg="std"),
+    Case(2, (4, 3), 4, nodes="GLL", eq="euler", op="split", nf="std", avg="std"),
+    Case(2, (4, 3), 4, nodes="GLL", eq="euler", op="split", nf="cha", avg="cha"),
+    Case(3, (2, 2, 2), 4, nodes="GLL", eq="euler", op="split", nf="cha", avg="cha"),
+    Case(2, (4, 3), 4, nodes="GLL", eq="euler", op="split", nf="sca", avg="cha"),
+    Case(3, (2, 3, 2), 3, nodes="GLL", eq="euler", op="split", nf="sca", avg="std"),
+    Case(1, (8,), 6, nodes="GLL", eq="euler", op="split", nf="sca", avg="cha"),
+    Case(2, (3, 3), 6, nodes="GLL", eq="euler", op="split", tp="std", nf="mat", avg="cha"),
+    Case(3, (2, 2, 2), 4, nodes="GLL", eq="euler", op="split", nf="lxf", avg="cha"),
+    Case(2, (3, 4), 4, nodes="CGL", eq="euler", op="strong", nf="mat", avg="std"),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=repr)
+@pytest.mark.parametrize("state", ["random", "smooth"])
+def test_rhs_matches_oracle(gpu, case, state):
+    import flou_b200 as F
+    orc = case.oracle()
+    disc, eq = case.product()
+    Q = (random_state(orc.ndof, case.nd, case.eq) if state == "random"
+         else smooth_state(orc.coords, case.nd, case.eq))
+    ref = orc.rhs(Q)
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert np.all(np.isfinite(dQ))
+    assert relerr(dQ, ref) <= RHS_TOL
+    disc.close()
+
+
+BC_CASES = [
+    Case(2, (5, 4), 4, eq="euler", op="split", nf="mat", avg="cha", periodic=[("3", "4")],
+         bcs={"1": ("inflow", [1.1, 0.33, 0.02, 2.6]), "2": ("outflow", None)}),
+    Case(2, (4, 4), 4, eq="euler", op="split", nf="mat", avg="cha", periodic=[],
+         bcs={"1": ("slip", None), "2": ("slip", None), "3": ("slip", None), "4": ("slip", None)}),
+    Case(3, (3, 2, 2), 3, eq="euler", op="split", nf="mat", avg="cha", periodic=[("5", "6")],
+         bcs={"1": ("inflow", [1.0, 0.4, 0.0, 0.1, 2.7]), "2": ("outflow", None),
+              "3": ("slip", None), "4": ("slip", None)}),
+    Case(1, (12,), 4, eq="euler", op="split", nf="mat", avg="cha", periodic=[],
+         bcs={"1": ("table", lambda x: np.array([1.0, 0.0, 250.0]) if x[0] < 0.5
+                    else np.array([0.125, 0.0, 25.0])),
+              "2": ("table", lambda x: np.array([1.0, 0.0, 250.0]) if x[0] < 0.5
+                    else np.array([0.125, 0.0, 25.0]))}),
+    Case(2, (4, 3), 3, nodes="GL", eq="adv", op="strong", nf="lxf", avg="std", periodic=[("1", "2")],
+         bcs={"3": ("table", lambda x: np.array([np.sin(3 * x[0])])), "4": ("outflow", None)}),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", BC_CASES, ids=repr)
+def test_rhs_with_boundary_conditions(gpu, case):
+    import flou_b200 as F
+    orc = case.oracle()
+    disc, eq = case.product()
+    Q = random_state(orc.ndof, case.nd, case.eq)
+    ref = orc.rhs(Q)
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert relerr(dQ, ref) <= RHS_TOL
+    disc.close()
+
+
+GENERAL_CASES = [
+    # Cartesian mesh pushed through the per-node metric path must agree with both
+    Case(2, (4, 3), 4, eq="euler", op="split", nf="mat", avg="cha", general=True),
+    Case(3, (2, 3, 2), 3, eq="euler", op="split", nf="mat", avg="cha", general=True),
+    # curved (vertex-perturbed) meshes, wall/inflow/outflow boundaries
+    Case(2, (5, 4), 4, eq="euler", op="split", nf="mat", avg="cha", periodic=[], perturb_amp=0.15,
+         bcs={"1": ("inflow", [1.1, 0.33, 0.02, 2.6]), "2": ("outflow", None),
+              "3": ("slip", None), "4": ("slip", None)}),
+    Case(2, (4, 4), 6, eq="euler", op="split", nf="mat", avg="cha", periodic=[], perturb_amp=0.1,
+         bcs={"1": ("slip", None), "2": ("slip", None), "3": ("slip", None), "4": ("slip", None)}),
+    Case(3, (3, 2, 2), 4, eq="euler", op="split", nf="mat", avg="cha", periodic=[], perturb_amp=0.1,
+         bcs={"1": ("inflow", [1.0, 0.4, 0.0, 0.1, 2.7]), "2": ("outflow", None),
+              "3": ("slip", None), "4": ("slip", None), "5": ("slip", None), "6": ("slip", None)}),
+    Case(2, (4, 3), 4, nodes="GL", eq="euler", op="strong", nf="lxf", avg="std", periodic=[],
+         perturb_amp=0.1,
+         bcs={"1": ("slip", None), "2": ("outflow", None), "3": ("slip", None), "4": ("slip", None)}),
+    Case(2, (4, 3), 3, nodes="GL", eq="adv", op="strong", nf="lxf", avg="std", periodic=[],
+         perturb_amp=0.1, bcs={str(i): ("outflow", None) for i in range(1, 5)}),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GENERAL_CASES, ids=repr)
+def test_rhs_general_geometry(gpu, case):
+    import flou_b200 as F
+    orc = case.oracle()
+    disc, eq = case.product()
+    Q = random_state(orc.ndof, case.nd, case.eq)
+    ref = orc.rhs(Q)
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert relerr(dQ, ref) <= RHS_TOL
+    disc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,dt,nsteps", [
+    (Case(2, (6, 5), 4, nodes="GL", eq="adv", op="strong", nf="lxf", avg="std"), 1e-3, 40),
+    (Case(2, (5, 4), 5, eq="euler", op="split", nf="mat", avg="cha"), 1e-3, 40),
+    (Case(3, (3, 3, 3), 4, eq="euler", op="split", nf="mat", avg="cha"), 1e-3, 25),
+], ids=lambda v: repr(v) if isinstance(v, Case) else None)
+@pytest.mark.parametrize("solver", ["ORK256", "CarpenterKennedy2N54"])
+def test_state_after_n_steps(gpu, case, dt, nsteps, solver):
+    """State after N RK steps: stated tolerance 1e-10 relative."""
+    import flou_b200 as F
+    import oracle as O
+    orc = case.oracle()
+    disc, eq = case.product()
+    Q = smooth_state(orc.coords, case.nd, case.eq)
+    tab = O.ORK256 if solver == "ORK256" else O.CARPENTER_KENNEDY_2N54
+    ref = orc.lsrk2n(Q, tab, dt, nsteps)
+    u = Q.copy(order="F")
+    sol, _ = F.timeintegrate(u, disc, eq, getattr(F, solver)(williamson_condition=False),
+                             nsteps * dt, dt=dt, adaptive=False, alias_u0=True)
+    assert sol is not None
+    assert relerr(sol.u[-1], ref) <= 1e-10
+    assert relerr(sol.u[0], Q) == 0.0
+    # graph replay and direct launches agree bitwise
+    disc2, eq2 = case.product(use_graph=False)
+    u2 = Q.copy(order="F")
+    F.timeintegrate(u2, disc2, eq2, getattr(F, solver)(), nsteps * dt, dt=dt)
+    assert np.array_equal(u2, u)
+    disc.close(); disc2.close()
+
+
+@pytest.mark.gpu
+def test_sod_tube_kat_on_gpu(gpu):
+    """The reference's own KAT (test/runtests.jl:35-39, setup test/tests.jl:90-134) through
+    the CUDA path: minimum/maximum of u(tf) to rtol 1e-7."""
+    import flou_b200 as F
+    eq = F.EulerEquation(1, 1.4)
+    basis = F.LagrangeBasis("GLL", 4)
+    std = F.StdSegment(basis, F.DGSEMrec(basis), eq.nv)
+    mesh = F.CartesianMesh(1, 0, 1, 20)
+
+    def Qext(_, x, __, ___, eq_):
+        P = (1.0, 0.0, 100.0) if x[0] < 0.5 else (0.125, 0.0, 10.0)
+        return F.vars_prim2cons(P, eq_)
+    bcs = {"1": F.GenericBC(Qext), "2": F.GenericBC(Qext)}
+    op = F.SplitDivOperator(F.MatrixDissipation(F.ChandrasekharAverage(), 1.0))
+    dg = F.MultielementDisc(mesh, std, eq, op, bcs)
+    Q = dg.new_state()
+    for i, x in enumerate(dg.coords()):
+        Q[i] = Qext((), x, (), 0.0, eq)
+    sol, _ = F.timeintegrate(Q, dg, eq, F.ORK256(williamson_condition=False), 0.018,
+                             dt=1e-4, adaptive=False, alias_u0=True)
+    assert abs(sol.u[-1].min() / -0.1662939230897596 - 1) <= 1e-7
+    assert abs(sol.u[-1].max() / 254.90504152149907 - 1) <= 1e-7
+    dg.close()
+
+
+@pytest.mark.gpu
+def test_domain_error_is_reported(gpu):
+    import flou_b200 as F
+    case = Case(2, (3, 3), 4, eq="euler", op="split", nf="mat", avg="cha")
+    disc, eq = case.product()
+    Q = random_state(disc.ndofs, 2, "euler")
+    Q[5, 0] = -1.0                      # negative density
+    sol, _ = F.timeintegrate(Q, disc, eq, F.ORK256(), 1e-3, dt=1e-3)
+    assert sol is None                  # FlouTime.jl:39-51 returns nothing after "crashed"
+    disc.close()
