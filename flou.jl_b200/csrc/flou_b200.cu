@@ -103,6 +103,148 @@ struct Peer {
     int64_t nslots;
 };
 
+// Host-only partition / halo plan: element-face records, ghost slots ordered by
+// (peer rank, global face id) -- both sides of an interface sort the same way, so slot s of
+// my send buffer is slot s of the peer's ghost buffer.
+struct Ghost { int peer; int64_t gf; int le, lf; };
+struct Plan {
+    int64_t ne_local = 0;
+    std::vector<Conn> conn;
+    std::vector<Ghost> ghosts;
+    std::vector<Peer> peers;
+    std::vector<int> send_list, interior, boundary, faceid;
+    std::vector<int64_t> slot_face;
+};
+
+int32_t build_plan(const flou_b200_desc *d, bool cart, Plan &pl)
+{
+    const int nd = d->nd, NF = 2 * nd;
+    const int nranks = d->nranks <= 0 ? 1 : d->nranks;
+    pl.ne_local = d->elem_end - d->elem_begin;
+    if (pl.ne_local * (int64_t)NF > INT32_MAX) return fail(FLOU_B200_EINVAL, "too many elements for one handle");
+    // boundary-face lookup: global face -> (boundary index, ordinal in bc_faces)
+    std::map<int64_t, std::pair<int, int64_t>> bdface;
+    for (int ib = 0; ib < d->nbound; ib++)
+        for (int64_t m = d->bc_offsets[ib]; m < d->bc_offsets[ib + 1]; m++)
+            bdface[d->bc_faces[m] - 1] = {ib, m};
+    pl.conn.assign((size_t)pl.ne_local * NF, Conn{0, 0});
+    pl.faceid.assign((size_t)pl.ne_local * NF, 0);
+    std::map<int64_t, int> face_slot;            // global face -> local slot (general geometry)
+    auto owner_of = [&](int64_t ge) {
+        return (int)(std::upper_bound(d->part_offsets, d->part_offsets + nranks + 1, ge) -
+                     d->part_offsets) - 1;
+    };
+    for (int64_t le = 0; le < pl.ne_local; le++) {
+        const int64_t ge = d->elem_begin + le;
+        for (int lf = 0; lf < NF; lf++) {
+            const int64_t gf = d->faceinds[ge * NF + lf] - 1;
+            const int64_t pos = d->facepos[ge * NF + lf];
+            if (gf < 0 || gf >= d->nf || (pos != 1 && pos != 2))
+                return fail(FLOU_B200_EINVAL, "faceinds/facepos out of range");
+            const int master = pos == 1;
+            if (d->eleminds[gf * 2 + (master ? 0 : 1)] - 1 != ge ||
+                d->elempos[gf * 2 + (master ? 0 : 1)] - 1 != lf)
+                return fail(FLOU_B200_EINVAL, "element and face connectivity disagree");
+            const int64_t gn = d->eleminds[gf * 2 + (master ? 1 : 0)] - 1;
+            const int nlf = (int)d->elempos[gf * 2 + (master ? 1 : 0)] - 1;
+            const int orient = d->orientation[gf];
+            Conn c;
+            if (gn < 0) {
+                auto it = bdface.find(gf);
+                if (it == bdface.end())
+                    return fail(FLOU_B200_EINVAL, "boundary face without a boundary condition");
+                c.nbr = (int)it->second.second;
+                c.info = conn_pack(0, 0, 1, FK_BOUNDARY, it->second.first);
+            } else if (gn >= d->elem_begin && gn < d->elem_end) {
+                if (nlf < 0 || nlf >= NF) return fail(FLOU_B200_EINVAL, "elempos out of range");
+                c.nbr = (int)(gn - d->elem_begin);
+                c.info = conn_pack(nlf, orient, master, FK_INTERIOR, 0);
+            } else {
+                if (gn >= d->ne || nranks == 1) return fail(FLOU_B200_EINVAL, "eleminds out of range");
+                c.nbr = -1;   // slot assigned after sorting
+                c.info = conn_pack(nlf, orient, master, FK_GHOST, 0);
+                pl.ghosts.push_back({owner_of(gn), gf, (int)le, lf});
+            }
+            pl.conn[(size_t)le * NF + lf] = c;
+            if (!cart) {
+                auto it = face_slot.find(gf);
+                if (it == face_slot.end()) {
+                    it = face_slot.emplace(gf, (int)pl.slot_face.size()).first;
+                    pl.slot_face.push_back(gf);
+                }
+                pl.faceid[(size_t)le * NF + lf] = it->second;
+            }
+        }
+    }
+    std::sort(pl.ghosts.begin(), pl.ghosts.end(), [](const Ghost &a, const Ghost &b) {
+        return a.peer != b.peer ? a.peer < b.peer : a.gf < b.gf;
+    });
+    pl.send_list.resize(pl.ghosts.size());
+    std::vector<char> is_boundary_elem((size_t)pl.ne_local, 0);
+    for (size_t s = 0; s < pl.ghosts.size(); s++) {
+        const Ghost &g = pl.ghosts[s];
+        pl.conn[(size_t)g.le * NF + g.lf].nbr = (int)s;
+        pl.send_list[s] = g.le * NF + g.lf;
+        is_boundary_elem[g.le] = 1;
+        if (pl.peers.empty() || pl.peers.back().rank != g.peer)
+            pl.peers.push_back({g.peer, (int64_t)s, 0});
+        pl.peers.back().nslots++;
+    }
+    for (int64_t le = 0; le < pl.ne_local; le++)
+        (is_boundary_elem[le] ? pl.boundary : pl.interior).push_back((int)le);
+    return FLOU_B200_OK;
+}
+
+int32_t validate_desc(const flou_b200_desc *d)
+{
+    if (!d) return fail(FLOU_B200_EINVAL, "null argument");
+    if (d->struct_size != (int32_t)sizeof(flou_b200_desc))
+        return fail(FLOU_B200_EINVAL, "flou_b200_desc size mismatch (ABI)");
+    if (d->nd < 1 || d->nd > 3) return fail(FLOU_B200_EINVAL, "nd must be 1, 2 or 3");
+    if (d->np < 2 || d->np > 8) return fail(FLOU_B200_EINVAL, "np must be between 2 and 8");
+    const int nv_expected = d->equation == FLOU_B200_EQ_EULER ? d->nd + 2 : 1;
+    if (d->equation != FLOU_B200_EQ_EULER && d->equation != FLOU_B200_EQ_LINEAR_ADVECTION)
+        return fail(FLOU_B200_EINVAL, "unknown equation");
+    if (d->nv != nv_expected) return fail(FLOU_B200_EINVAL, "nv does not match the equation");
+    if (d->divop != FLOU_B200_OP_STRONG && d->divop != FLOU_B200_OP_SPLIT)
+        return fail(FLOU_B200_EINVAL, "unknown divergence operator");
+    if (d->numflux < 0 || d->numflux > FLOU_B200_FLUX_MATRIXDISSIPATION)
+        return fail(FLOU_B200_EINVAL, "unknown numerical flux");
+    if (d->equation == FLOU_B200_EQ_LINEAR_ADVECTION &&
+        (d->numflux != FLOU_B200_FLUX_STDAVERAGE && d->numflux != FLOU_B200_FLUX_LXF))
+        return fail(FLOU_B200_EINVAL, "linear advection supports StdAverage and LxF fluxes only");
+    if (d->divop == FLOU_B200_OP_SPLIT && d->tpflux != FLOU_B200_FLUX_STDAVERAGE &&
+        d->tpflux != FLOU_B200_FLUX_CHANDRASEKHAR)
+        return fail(FLOU_B200_EINVAL, "the two-point flux must be StdAverage or ChandrasekharAverage");
+    if (d->equation == FLOU_B200_EQ_LINEAR_ADVECTION && d->divop == FLOU_B200_OP_SPLIT &&
+        d->tpflux != FLOU_B200_FLUX_STDAVERAGE)
+        return fail(FLOU_B200_EINVAL, "linear advection split form needs the StdAverage two-point flux");
+    const bool has_avg = d->numflux == FLOU_B200_FLUX_LXF ||
+                         d->numflux == FLOU_B200_FLUX_SCALARDISSIPATION ||
+                         d->numflux == FLOU_B200_FLUX_MATRIXDISSIPATION;
+    if (has_avg && d->numflux_avg != FLOU_B200_FLUX_STDAVERAGE &&
+        d->numflux_avg != FLOU_B200_FLUX_CHANDRASEKHAR)
+        return fail(FLOU_B200_EINVAL, "numflux.avg must be StdAverage or ChandrasekharAverage");
+    if (d->geometry != FLOU_B200_GEOM_CARTESIAN && d->geometry != FLOU_B200_GEOM_GENERAL)
+        return fail(FLOU_B200_EINVAL, "unknown geometry kind");
+    if (d->ne <= 0 || d->nf <= 0 || !d->faceinds || !d->facepos || !d->eleminds || !d->elempos ||
+        !d->orientation)
+        return fail(FLOU_B200_EINVAL, "connectivity tables missing");
+    if (d->nbound < 0 || (d->nbound > 0 && (!d->bc_kind || !d->bc_offsets || !d->bc_faces)))
+        return fail(FLOU_B200_EINVAL, "boundary tables missing");
+    const int nranks = d->nranks <= 0 ? 1 : d->nranks;
+    if (d->elem_begin < 0 || d->elem_end > d->ne || d->elem_begin >= d->elem_end)
+        return fail(FLOU_B200_EINVAL, "bad owned element range");
+    if (nranks > 1 && !d->part_offsets) return fail(FLOU_B200_EINVAL, "part_offsets missing");
+    if (nranks > 1 && (d->rank < 0 || d->rank >= nranks ||
+                       d->part_offsets[d->rank] != d->elem_begin ||
+                       d->part_offsets[d->rank + 1] != d->elem_end))
+        return fail(FLOU_B200_EINVAL, "owned range does not match part_offsets[rank]");
+    if (nranks == 1 && (d->elem_begin != 0 || d->elem_end != d->ne))
+        return fail(FLOU_B200_EINVAL, "single-rank handle must own every element");
+    return FLOU_B200_OK;
+}
+
 }  // namespace
 
 struct flou_b200_handle {
@@ -243,49 +385,50 @@ int32_t flou_b200_supported(int32_t nd, int32_t np, int32_t equation, int32_t di
                               geometry == FLOU_B200_GEOM_CARTESIAN) != nullptr;
 }
 
+int32_t flou_b200_partition_plan(const flou_b200_desc *d, int64_t *nghost, int32_t *npeers,
+                                 int32_t *peer_ranks, int64_t *peer_nslots,
+                                 int64_t *ghost_faces, int32_t *ghost_elemfaces,
+                                 int64_t *n_interior, int64_t *n_boundary)
+{
+    if (int32_t rc = validate_desc(d)) return rc;
+    Plan pl;
+    if (int32_t rc = build_plan(d, d->geometry == FLOU_B200_GEOM_CARTESIAN, pl)) return rc;
+    if (nghost) *nghost = (int64_t)pl.ghosts.size();
+    if (npeers) *npeers = (int32_t)pl.peers.size();
+    for (size_t i = 0; i < pl.peers.size(); i++) {
+        if (peer_ranks) peer_ranks[i] = pl.peers[i].rank;
+        if (peer_nslots) peer_nslots[i] = pl.peers[i].nslots;
+    }
+    for (size_t s = 0; s < pl.ghosts.size(); s++) {
+        if (ghost_faces) ghost_faces[s] = pl.ghosts[s].gf + 1;
+        if (ghost_elemfaces) ghost_elemfaces[s] = pl.send_list[s];
+    }
+    if (n_interior) *n_interior = (int64_t)pl.interior.size();
+    if (n_boundary) *n_boundary = (int64_t)pl.boundary.size();
+    return FLOU_B200_OK;
+}
+
 int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
 {
     if (!d || !out) return fail(FLOU_B200_EINVAL, "null argument");
     *out = nullptr;
-    if (d->struct_size != (int32_t)sizeof(flou_b200_desc))
-        return fail(FLOU_B200_EINVAL, "flou_b200_desc size mismatch (ABI)");
-    if (d->nd < 1 || d->nd > 3) return fail(FLOU_B200_EINVAL, "nd must be 1, 2 or 3");
+    if (int32_t rc = validate_desc(d)) return rc;
     const int nd = d->nd, np = d->np;
-    const int nv_expected = d->equation == FLOU_B200_EQ_EULER ? nd + 2 : 1;
-    if (d->nv != nv_expected) return fail(FLOU_B200_EINVAL, "nv does not match the equation");
-    if (d->equation == FLOU_B200_EQ_LINEAR_ADVECTION &&
-        (d->numflux != FLOU_B200_FLUX_STDAVERAGE && d->numflux != FLOU_B200_FLUX_LXF))
-        return fail(FLOU_B200_EINVAL, "linear advection supports StdAverage and LxF fluxes only");
-    if (d->equation == FLOU_B200_EQ_LINEAR_ADVECTION && d->divop == FLOU_B200_OP_SPLIT &&
-        d->tpflux != FLOU_B200_FLUX_STDAVERAGE)
-        return fail(FLOU_B200_EINVAL, "linear advection split form needs the StdAverage two-point flux");
-    if (d->numflux < 0 || d->numflux > FLOU_B200_FLUX_MATRIXDISSIPATION)
-        return fail(FLOU_B200_EINVAL, "unknown numerical flux");
-    const bool has_avg = d->numflux == FLOU_B200_FLUX_LXF ||
-                         d->numflux == FLOU_B200_FLUX_SCALARDISSIPATION ||
-                         d->numflux == FLOU_B200_FLUX_MATRIXDISSIPATION;
-    if (has_avg && d->numflux_avg != FLOU_B200_FLUX_STDAVERAGE &&
-        d->numflux_avg != FLOU_B200_FLUX_CHANDRASEKHAR)
-        return fail(FLOU_B200_EINVAL, "numflux.avg must be StdAverage or ChandrasekharAverage");
-    if (!flou_b200_supported(nd, np, d->equation, d->divop, d->tpflux, d->geometry))
-        return fail(FLOU_B200_EUNSUPPORTED, "no kernel compiled for this (nd, np, equation, operator)");
-    if (d->ne <= 0 || d->nf <= 0 || !d->faceinds || !d->facepos || !d->eleminds || !d->elempos ||
-        !d->orientation)
-        return fail(FLOU_B200_EINVAL, "connectivity tables missing");
     if (!d->Ds || !d->Dsharp || !d->lminus || !d->lplus || !d->dgminus || !d->dgplus)
         return fail(FLOU_B200_EINVAL, "operator tables missing");
     if (d->geometry == FLOU_B200_GEOM_GENERAL && (!d->jac || !d->metric || !d->fjac || !d->frames))
         return fail(FLOU_B200_EINVAL, "general geometry tables missing");
+    if (!flou_b200_supported(nd, np, d->equation, d->divop, d->tpflux, d->geometry))
+        return fail(FLOU_B200_EUNSUPPORTED, "no kernel compiled for this (nd, np, equation, operator)");
     const int nranks = d->nranks <= 0 ? 1 : d->nranks;
-    if (d->elem_begin < 0 || d->elem_end > d->ne || d->elem_begin >= d->elem_end)
-        return fail(FLOU_B200_EINVAL, "bad owned element range");
-    if (nranks > 1 && !d->part_offsets) return fail(FLOU_B200_EINVAL, "part_offsets missing");
-    if (nranks == 1 && (d->elem_begin != 0 || d->elem_end != d->ne))
-        return fail(FLOU_B200_EINVAL, "single-rank handle must own every element");
+    const bool cart = d->geometry == FLOU_B200_GEOM_CARTESIAN;
 
-    if (flou_b200_device_count() <= d->device)
+    if (flou_b200_device_count() <= d->device || d->device < 0)
         return fail(FLOU_B200_ECUDA, "no usable CUDA device (this library has no CPU path)");
     CUDA_TRY(cudaSetDevice(d->device));
+
+    Plan pl;
+    if (int32_t rc = build_plan(d, cart, pl)) return rc;
 
     flou_b200_handle *h = new flou_b200_handle();
     h->nd = nd; h->nv = d->nv; h->np = np;
@@ -294,93 +437,18 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     h->nfaces = 2 * nd;
     h->device = d->device; h->flags = d->flags;
     h->rank = d->rank; h->nranks = nranks;
-    h->ne_local = d->elem_end - d->elem_begin;
+    h->ne_local = pl.ne_local;
     h->ndof = h->ne_local * h->npts;
-    const bool cart = d->geometry == FLOU_B200_GEOM_CARTESIAN;
     h->stage = get_stage_launcher(nd, np, d->equation, vol_kind(d->divop, d->tpflux), cart);
     h->emit = get_emit_launcher(nd, np, d->nv);
-    if (h->ne_local * (int64_t)h->nfaces > INT32_MAX)
-        { delete h; return fail(FLOU_B200_EINVAL, "too many elements for one handle"); }
-
-    // ---- boundary-face lookup: global face -> (boundary index, ordinal in bc_faces)
-    std::map<int64_t, std::pair<int, int64_t>> bdface;
-    for (int ib = 0; ib < d->nbound; ib++)
-        for (int64_t m = d->bc_offsets[ib]; m < d->bc_offsets[ib + 1]; m++)
-            bdface[d->bc_faces[m] - 1] = {ib, m};
-
-    // ---- element-face records, ghosts
-    const int NF = h->nfaces;
-    std::vector<Conn> conn((size_t)h->ne_local * NF);
-    struct Ghost { int peer; int64_t gf; int le, lf; };
-    std::vector<Ghost> ghosts;
-    std::map<int64_t, int> face_slot;            // global face -> local slot (general geometry)
-    std::vector<int64_t> slot_face;
-    std::vector<int> faceid((size_t)h->ne_local * NF, 0);
-    auto owner_of = [&](int64_t ge) {
-        int r = (int)(std::upper_bound(d->part_offsets, d->part_offsets + nranks + 1, ge) -
-                      d->part_offsets) - 1;
-        return r;
-    };
-    for (int64_t le = 0; le < h->ne_local; le++) {
-        const int64_t ge = d->elem_begin + le;
-        for (int lf = 0; lf < NF; lf++) {
-            const int64_t gf = d->faceinds[ge * NF + lf] - 1;
-            const int64_t pos = d->facepos[ge * NF + lf];
-            if (gf < 0 || gf >= d->nf || (pos != 1 && pos != 2))
-                { delete h; return fail(FLOU_B200_EINVAL, "faceinds/facepos out of range"); }
-            const int master = pos == 1;
-            if (d->eleminds[gf * 2 + (master ? 0 : 1)] - 1 != ge ||
-                d->elempos[gf * 2 + (master ? 0 : 1)] - 1 != lf)
-                { delete h; return fail(FLOU_B200_EINVAL, "element and face connectivity disagree"); }
-            const int64_t gn = d->eleminds[gf * 2 + (master ? 1 : 0)] - 1;
-            const int nlf = (int)d->elempos[gf * 2 + (master ? 1 : 0)] - 1;
-            const int orient = d->orientation[gf];
-            Conn c;
-            if (gn < 0) {
-                auto it = bdface.find(gf);
-                if (it == bdface.end())
-                    { delete h; return fail(FLOU_B200_EINVAL, "boundary face without a boundary condition"); }
-                c.nbr = (int)it->second.second;
-                c.info = conn_pack(0, 0, 1, FK_BOUNDARY, it->second.first);
-            } else if (gn >= d->elem_begin && gn < d->elem_end) {
-                c.nbr = (int)(gn - d->elem_begin);
-                c.info = conn_pack(nlf, orient, master, FK_INTERIOR, 0);
-            } else {
-                c.nbr = -1;   // slot assigned after sorting
-                c.info = conn_pack(nlf, orient, master, FK_GHOST, 0);
-                ghosts.push_back({owner_of(gn), gf, (int)le, lf});
-            }
-            conn[(size_t)le * NF + lf] = c;
-            if (!cart) {
-                auto it = face_slot.find(gf);
-                if (it == face_slot.end()) {
-                    it = face_slot.emplace(gf, (int)slot_face.size()).first;
-                    slot_face.push_back(gf);
-                }
-                faceid[(size_t)le * NF + lf] = it->second;
-            }
-        }
-    }
-    std::sort(ghosts.begin(), ghosts.end(), [](const Ghost &a, const Ghost &b) {
-        return a.peer != b.peer ? a.peer < b.peer : a.gf < b.gf;
-    });
-    std::vector<int> send_list(ghosts.size());
-    std::vector<char> is_boundary_elem((size_t)h->ne_local, 0);
-    for (size_t s = 0; s < ghosts.size(); s++) {
-        const Ghost &g = ghosts[s];
-        conn[(size_t)g.le * NF + g.lf].nbr = (int)s;
-        send_list[s] = g.le * NF + g.lf;
-        is_boundary_elem[g.le] = 1;
-        if (h->peers.empty() || h->peers.back().rank != g.peer)
-            h->peers.push_back({g.peer, (int64_t)s, 0});
-        h->peers.back().nslots++;
-    }
-    h->nghost = (int64_t)ghosts.size();
-    std::vector<int> interior, boundary;
-    for (int64_t le = 0; le < h->ne_local; le++)
-        (is_boundary_elem[le] ? boundary : interior).push_back((int)le);
-    h->n_interior = (int)interior.size();
-    h->n_boundary = (int)boundary.size();
+    h->peers = pl.peers;
+    h->nghost = (int64_t)pl.ghosts.size();
+    h->n_interior = (int)pl.interior.size();
+    h->n_boundary = (int)pl.boundary.size();
+    const std::vector<Conn> &conn = pl.conn;
+    const std::vector<int> &send_list = pl.send_list, &interior = pl.interior,
+                           &boundary = pl.boundary, &faceid = pl.faceid;
+    const std::vector<int64_t> &slot_face = pl.slot_face;
 
     // ---- kernel parameters
     KParams &P = h->base;

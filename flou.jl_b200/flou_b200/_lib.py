@@ -75,6 +75,10 @@ SYMBOLS = {
     "flou_b200_unpin_host": (C.c_int32, [C.c_void_p]),
     "flou_b200_device_count": (C.c_int32, []),
     "flou_b200_supported": (C.c_int32, [C.c_int32] * 6),
+    "flou_b200_partition_plan": (C.c_int32, [C.POINTER(Desc), C.POINTER(C.c_int64),
+                                             C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
+                                             C.POINTER(C.c_int64)]),
     "flou_b200_nccl_unique_id": (C.c_int32, [C.c_char_p]),
     "flou_b200_comm_init": (C.c_int32, [C.c_void_p, C.c_char_p]),
 }

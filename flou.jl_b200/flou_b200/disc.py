@@ -29,7 +29,7 @@ class EquationConfig:
 
 class MultielementDisc:
     def __init__(self, mesh, std, equation, operators, bcs, source=None, *,
-                 rank=0, nranks=1, device=None, geometry=None, use_graph=True):
+                 rank=0, nranks=1, device=None, geometry=None, use_graph=True, create=True):
         if source is not None:
             raise ValueError("source terms are not part of the B200 hot path (default no-op only)")
         if std.nd != mesh.nd or equation.nd != mesh.nd:
@@ -134,10 +134,30 @@ class MultielementDisc:
         d.device = int(device if device is not None else 0)
         d.flags = 0 if use_graph else L.FLAG_NO_GRAPH
         self._h = C.c_void_p()
-        L.check(L.lib().flou_b200_create(C.byref(d), C.byref(self._h)))
-        # the library copied everything it needs; drop the big host tables
-        for name in ("jac", "metric", "fjac", "frames"):
-            keep.pop(name, None)
+        if create:
+            L.check(L.lib().flou_b200_create(C.byref(d), C.byref(self._h)))
+            # the library copied everything it needs; drop the big host tables
+            for name in ("jac", "metric", "fjac", "frames"):
+                keep.pop(name, None)
+
+    def partition_plan(self):
+        """Host-only halo plan (no GPU needed): dict with peers, per-peer slot counts, the
+        global face id and (local element, local face) of every ghost slot."""
+        lib = L.lib()
+        ng, npeer = C.c_int64(0), C.c_int32(0)
+        ni, nb = C.c_int64(0), C.c_int64(0)
+        L.check(lib.flou_b200_partition_plan(C.byref(self._desc), C.byref(ng), C.byref(npeer),
+                                             None, None, None, None, C.byref(ni), C.byref(nb)))
+        peers = np.zeros(max(npeer.value, 1), dtype=np.int32)
+        counts = np.zeros(max(npeer.value, 1), dtype=np.int64)
+        faces = np.zeros(max(ng.value, 1), dtype=np.int64)
+        elemfaces = np.zeros(max(ng.value, 1), dtype=np.int32)
+        L.check(lib.flou_b200_partition_plan(C.byref(self._desc), C.byref(ng), C.byref(npeer),
+                                             _ptr(peers), _ptr(counts), _ptr(faces),
+                                             _ptr(elemfaces), C.byref(ni), C.byref(nb)))
+        return dict(nghost=ng.value, peers=peers[:npeer.value].tolist(),
+                    counts=counts[:npeer.value].tolist(), faces=faces[:ng.value],
+                    elemfaces=elemfaces[:ng.value], n_interior=ni.value, n_boundary=nb.value)
 
     # ------------------------------------------------------------------ geometry access
     def _face_geometry(self):

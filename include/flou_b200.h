@@ -196,6 +196,16 @@ int32_t flou_b200_supported(int32_t nd, int32_t np, int32_t equation, int32_t di
 /* ---- multi-GPU (one process per GPU) ----------------------------------------------------- */
 /* Halo face traces travel with ncclSend/ncclRecv over NVLink on the communication stream,
  * overlapped with the interior-element kernel.  `id` is an ncclUniqueId (128 bytes). */
+/* Host-only (no GPU needed): the halo plan flou_b200_create would build for this descriptor.
+ * Ghost slots are ordered by (peer rank, global face id), so slot s of this rank's send
+ * buffer towards a peer is slot s of that peer's ghost buffer.  Output arrays may be NULL;
+ * call once for the counts, then with buffers: peer_* need *npeers entries (<= nranks-1),
+ * ghost_faces (1-based global face ids) and ghost_elemfaces (local element*2nd + local face)
+ * need *nghost entries. */
+int32_t flou_b200_partition_plan(const flou_b200_desc *desc, int64_t *nghost, int32_t *npeers,
+                                 int32_t *peer_ranks, int64_t *peer_nslots,
+                                 int64_t *ghost_faces, int32_t *ghost_elemfaces,
+                                 int64_t *n_interior, int64_t *n_boundary);
 int32_t flou_b200_nccl_unique_id(char id[128]);
 int32_t flou_b200_comm_init(flou_b200_handle *h, const char id[128]);
 

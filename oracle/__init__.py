@@ -115,8 +115,11 @@ class Problem:
         self.ndof = self.ne * self.npts
         self.coords, self.jac, self.metric = geometry.element_geometry(
             mesh, self.ops["xi"], cartesian)
+        # face coordinates are only needed to tabulate GenericBC closures
+        want = any(isinstance(b, tuple) and b[0] == BC_TABLE
+                   for b in (bcs.values() if isinstance(bcs, dict) else bcs))
         self.fcoords, self.fjac, self.frames = geometry.face_geometry(
-            mesh, self.ops["xi"], cartesian)
+            mesh, self.ops["xi"], cartesian, want_coords=want or not cartesian)
         self.weights = geometry.tensor_weights(self.ops["w"], nd)
         if tpflux is None:   # SplitDivOperator(numflux) -> tpflux = numflux.avg
             tpflux = numflux_avg if numflux in (FLUX_LXF, FLUX_SCALARDISS, FLUX_MATRIXDISS) \

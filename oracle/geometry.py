@@ -100,10 +100,19 @@ def element_geometry(mesh, xi1d, cartesian=True):
     coords = np.zeros((ne * npts, nd))
     jac = np.zeros(ne * npts)
     metric = np.zeros((ne * npts, nd, nd))
+    # shape-function weights of every reference node (same formula as phys_coords)
+    nvert = 2 ** nd
+    shape = np.zeros((npts, nvert))
+    for i in range(npts):
+        for v in range(nvert):
+            unit = [np.zeros(1) for _ in range(nvert)]
+            unit[v] = np.ones(1)
+            shape[i, v] = phys_coords(xi[i], unit)[0]
+    enodes = np.asarray(mesh.enodes, dtype=np.int64) - 1
+    verts = np.asarray(mesh.nodes)[enodes]                    # (ne, nvert, nd)
+    coords[:] = np.einsum("pv,evd->epd", shape, verts).reshape(ne * npts, nd)
     for e in range(ne):
-        nodes = [mesh.nodes[i - 1] for i in mesh.enodes[e]]
-        for i in range(npts):
-            coords[e * npts + i] = phys_coords(xi[i], nodes)
+        nodes = [mesh.nodes[i - 1] for i in mesh.enodes[e]] if not cartesian else None
         if cartesian:
             dx = mesh.dx
             jac[e * npts:(e + 1) * npts] = np.prod(dx) / 2 ** nd
@@ -157,7 +166,7 @@ def _face_ref_point(pos, xif, nd):
     return out
 
 
-def face_geometry(mesh, xi1d, cartesian=True, face_nodes=None):
+def face_geometry(mesh, xi1d, cartesian=True, want_coords=True):
     nd = mesh.nd
     xif = tensor_nodes(xi1d, nd - 1) if nd > 1 else np.zeros((1, 1))
     nfp = len(xif) if nd > 1 else 1
@@ -185,9 +194,10 @@ def face_geometry(mesh, xi1d, cartesian=True, face_nodes=None):
                             dx[0] * dx[2] / 4 if pos <= 4 else dx[0] * dx[1] / 4)
             # face coordinates through the face's own vertex list (Mesh.jl:338-343);
             # on a Cartesian mesh they coincide with the master element's face nodes
-            nodes = [mesh.nodes[i - 1] for i in mesh.enodes[ielem - 1]]
-            for i in range(nfp):
-                fcoords[f * nfp + i] = phys_coords(_face_ref_point(pos, xif[i], nd), nodes)
+            if want_coords:
+                nodes = [mesh.nodes[i - 1] for i in mesh.enodes[ielem - 1]]
+                for i in range(nfp):
+                    fcoords[f * nfp + i] = phys_coords(_face_ref_point(pos, xif[i], nd), nodes)
         else:
             nodes = [mesh.nodes[i - 1] for i in mesh.enodes[ielem - 1]]
             d = (pos - 1) // 2

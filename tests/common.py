@@ -15,13 +15,15 @@ def box(nd):
     return [0.0] * nd, [1.0 + 0.5 * d for d in range(nd)]
 
 
-def random_state(ndof, nd, eq, gamma=1.4, seed=SEED):
+def random_state(ndof, nd, eq, gamma=1.4, seed=SEED, amp=0.5):
+    """rho, p in U[1-amp, 1+amp], velocities in U[-amp, amp] (amp = 0.5: SURVEY.md 8(d); use a
+    smaller amp with Gauss nodes, whose face extrapolation of white noise overshoots)."""
     rng = np.random.default_rng(seed)
     if eq == "adv":
         return np.asfortranarray(rng.uniform(-1.0, 1.0, size=(ndof, 1)))
-    rho = rng.uniform(0.5, 1.5, ndof)
-    vel = rng.uniform(-0.5, 0.5, (ndof, nd))
-    p = rng.uniform(0.5, 1.5, ndof)
+    rho = rng.uniform(1 - amp, 1 + amp, ndof)
+    vel = rng.uniform(-amp, amp, (ndof, nd))
+    p = rng.uniform(1 - amp, 1 + amp, ndof)
     Q = np.zeros((ndof, nd + 2), order="F")
     Q[:, 0] = rho
     for d in range(nd):
@@ -69,6 +71,10 @@ class Case:
         self.bcs = bcs or {}
         self.general = general or perturb_amp > 0
         self.perturb_amp = perturb_amp
+
+    @property
+    def amp(self):
+        return 0.5 if self.nodes == "GLL" else 0.15
 
     def __repr__(self):
         return (f"{self.nd}D n={self.n} np={self.np} {self.nodes} {self.eq} {self.op}"

@@ -42,7 +42,7 @@ def test_rhs_matches_oracle(gpu, case, state):
     import flou_b200 as F
     orc = case.oracle()
     disc, eq = case.product()
-    Q = (random_state(orc.ndof, case.nd, case.eq) if state == "random"
+    Q = (random_state(orc.ndof, case.nd, case.eq, amp=case.amp) if state == "random"
          else smooth_state(orc.coords, case.nd, case.eq))
     ref = orc.rhs(Q)
     dQ = disc.new_state()
@@ -76,7 +76,7 @@ def test_rhs_with_boundary_conditions(gpu, case):
     import flou_b200 as F
     orc = case.oracle()
     disc, eq = case.product()
-    Q = random_state(orc.ndof, case.nd, case.eq)
+    Q = random_state(orc.ndof, case.nd, case.eq, amp=case.amp)
     ref = orc.rhs(Q)
     dQ = disc.new_state()
     F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
@@ -111,7 +111,7 @@ def test_rhs_general_geometry(gpu, case):
     import flou_b200 as F
     orc = case.oracle()
     disc, eq = case.product()
-    Q = random_state(orc.ndof, case.nd, case.eq)
+    Q = random_state(orc.ndof, case.nd, case.eq, amp=case.amp)
     ref = orc.rhs(Q)
     dQ = disc.new_state()
     F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
