@@ -464,6 +464,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     }
     P.colloc = colloc ? 1 : 0;
     P.fp.gamma = d->gamma; P.fp.intensity = d->intensity;
+    P.fp.gm1 = d->gamma - 1.0; P.fp.inv_gm1 = 1.0 / (d->gamma - 1.0); P.fp.inv_gamma = 1.0 / d->gamma;
     for (int c = 0; c < 3; c++) P.fp.a[c] = d->a[c];
     P.fp.numflux = d->numflux; P.fp.numflux_avg = d->numflux_avg;
     if (cart) {
@@ -471,6 +472,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         double prod = 1.0;
         for (int c = 0; c < nd; c++) prod *= d->dx[c];
         P.cjac = prod / (double)(1 << nd);
+        P.crjac = 1.0 / P.cjac;
         if (nd == 1) { P.cmet[0] = 1.0; P.cfjac[0] = 1.0; }
         else if (nd == 2) {
             P.cmet[0] = d->dx[1] / 2; P.cmet[1] = d->dx[0] / 2;

@@ -12,8 +12,12 @@ namespace flou {
 template <class C>
 static cudaError_t do_prepare()
 {
-    return cudaFuncSetAttribute(stage_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(stage_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    // ask for the largest shared-memory carve-out so several CTAs fit per SM
+    return cudaFuncSetAttribute(stage_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared);
 }
 
 template <class C>

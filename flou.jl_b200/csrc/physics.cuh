@@ -27,30 +27,50 @@ enum : int { FX_STD = FLOU_B200_FLUX_STDAVERAGE, FX_LXF = FLOU_B200_FLUX_LXF,
              FX_CHA = FLOU_B200_FLUX_CHANDRASEKHAR, FX_SCA = FLOU_B200_FLUX_SCALARDISSIPATION,
              FX_MAT = FLOU_B200_FLUX_MATRIXDISSIPATION };
 
-struct LogMean {       // logarithmic mean plus the series factor F it was built from
-    double mean;       // (al+ar)/(2F)
-    double F;          // F = log(xi)/(2f), xi = al/ar, f = (xi-1)/(xi+1)
-};
+// 1/x for normal, finite x (states are O(1)): MUFU.RCP64H seed + two Newton steps, no
+// special-case slow path.  Within 1 ulp of the correctly rounded quotient.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
 
-// f = (al-ar)/(al+ar) is algebraically the reference's (xi-1)/(xi+1).
+// rare branch of the logarithmic mean (|f| >= 0.1, i.e. a jump ratio above ~1.22): kept out
+// of line so its log/division code is not replicated at every flux site
+static __device__ __noinline__ double logmean_F_slow(double al, double ar, double f)
+{
+    return log(al / ar) / (2.0 * f);
+}
+
+// F = log(xi)/(2f) with xi = al/ar and f = (al-ar)/(al+ar), which is algebraically the
+// reference's (xi-1)/(xi+1); same u < 0.01 threshold and 3-term series (Utilities.jl:34-44).
 __device__ __forceinline__ double logmean_F(double al, double ar, double rsum)
 {
     const double f = (al - ar) * rsum;
     const double u = f * f;
-    double F;
-    if (u < 0.01) {
-        F = 1.0 + u * (1.0 / 3.0 + u * (1.0 / 5.0 + u * (1.0 / 7.0)));
-    } else {
-        F = log(al / ar) / (2.0 * f);
-    }
+    double F = 1.0 + u * (1.0 / 3.0 + u * (1.0 / 5.0 + u * (1.0 / 7.0)));
+    if (u >= 0.01) F = logmean_F_slow(al, ar, f);
     return F;
 }
 
-__device__ __forceinline__ double logarithmic_mean(double al, double ar)
+static __device__ __noinline__ double log_ratio_slow(double al, double ar) { return log(al / ar); }
+
+// log(al/ar) = 2 atanh(f) from f = (al-ar)/(al+ar): 8-term series below u = f^2 < 0.01
+// (truncation < 1e-17 relative), library log otherwise.
+__device__ __forceinline__ double log_ratio(double al, double ar, double rsum)
 {
-    const double s = al + ar;
-    const double F = logmean_F(al, ar, 1.0 / s);
-    return s / (2.0 * F);
+    const double f = (al - ar) * rsum;
+    const double u = f * f;
+    double G = 1.0 + u * (1.0 / 3.0 + u * (1.0 / 5.0 + u * (1.0 / 7.0 + u * (1.0 / 9.0
+             + u * (1.0 / 11.0 + u * (1.0 / 13.0 + u * (1.0 / 15.0)))))));
+    double r = 2.0 * f * G;
+    if (u >= 0.01) r = log_ratio_slow(al, ar);
+    return r;
 }
 
 template <int ND>
@@ -73,7 +93,7 @@ struct NodeAux {
 template <int ND>
 __device__ __forceinline__ void node_aux(const double *Q, double gamma, NodeAux<ND> &A)
 {
-    const double ir = 1.0 / Q[0];
+    const double ir = fast_rcp(Q[0]);
     double m2 = 0.0;
 #pragma unroll
     for (int d = 0; d < ND; d++) {
@@ -81,7 +101,7 @@ __device__ __forceinline__ void node_aux(const double *Q, double gamma, NodeAux<
         m2 += Q[1 + d] * Q[1 + d];
     }
     A.p = (gamma - 1.0) * (Q[ND + 1] - m2 * (0.5 * ir));
-    A.beta = Q[0] / (2.0 * A.p);
+    A.beta = 0.5 * Q[0] * fast_rcp(A.p);
 }
 
 // Physical flux in direction c of a node (Euler): F_c = (m_c, m_c*vel + p e_c, (E+p) vel_c)
@@ -97,31 +117,30 @@ __device__ __forceinline__ void euler_flux_dir(const double *Q, const double *ve
 }
 
 // Two-point Chandrasekhar flux contracted with the averaged metric vector n[ND].
-// (rho1, vel1, p1, beta1) and (rho2, ...) are node primitives.
+// (rho, vel, beta = rho/(2p)) are node primitives; inv_gm1 = 1/(gamma-1).
+// Identities used (beta_ln = bs/(2 Fb), rho_ln = rs/(2 Fr), p_hat = rs/(2 bs)):
+//   1/(2 beta_ln (g-1)) = Fb/(bs (g-1)),      p_hat/rho_ln = Fr/bs.
 template <int ND>
-__device__ __forceinline__ void tp_chandrasekhar(double r1, const double *v1, double p1,
-                                                 double b1, double r2, const double *v2,
-                                                 double p2, double b2, double gamma,
-                                                 const double *n, double *F)
+__device__ __forceinline__ void tp_chandrasekhar(double r1, const double *v1, double b1,
+                                                 double r2, const double *v2, double b2,
+                                                 double inv_gm1, const double *n, double *F)
 {
-    (void)p1; (void)p2;
     const double rs = r1 + r2, bs = b1 + b2;
-    const double irs = 1.0 / rs, ibs = 1.0 / bs;
+    const double irb = fast_rcp(rs * bs);        // one reciprocal for both sums
+    const double irs = irb * bs, ibs = irb * rs;
     const double Fr = logmean_F(r1, r2, irs);
     const double Fb = logmean_F(b1, b2, ibs);
-    const double rho = rs / (2.0 * Fr);          // logarithmic_mean(rho1, rho2)
+    const double rho = 0.5 * rs * fast_rcp(Fr);  // logarithmic_mean(rho1, rho2)
     const double p = rs * ibs * 0.5;             // (rho1+rho2)/(2(beta1+beta2))
-    // 1/(2 beta_ln (g-1)) with beta_ln = bs/(2Fb);  p/rho_ln = Fr/bs
-    double vavg[ND], q1 = 0.0, q2 = 0.0, qa = 0.0, vn = 0.0;
+    double vavg[ND], q12 = 0.0, qa = 0.0, vn = 0.0;
 #pragma unroll
     for (int d = 0; d < ND; d++) {
         vavg[d] = 0.5 * (v1[d] + v2[d]);
-        q1 += v1[d] * v1[d];
-        q2 += v2[d] * v2[d];
+        q12 += v1[d] * v1[d] + v2[d] * v2[d];
         qa += vavg[d] * vavg[d];
         vn += vavg[d] * n[d];
     }
-    const double h = Fb * ibs / (gamma - 1.0) - 0.25 * (q1 + q2) + Fr * ibs + qa;
+    const double h = (Fb * inv_gm1 + Fr) * ibs - 0.25 * q12 + qa;
     const double mdot = rho * vn;                 // rho * (v . n)
     F[0] = mdot;
 #pragma unroll
@@ -158,6 +177,8 @@ __device__ __forceinline__ void tp_stdavg(const double *Q1, const double *v1, do
 // ------------------------------------------------------------------ surface fluxes
 struct FluxParams {
     double gamma, intensity;
+    double gm1, inv_gm1;      // gamma-1, 1/(gamma-1)
+    double inv_gamma;         // 1/gamma
     double a[3];
     int numflux, numflux_avg;
 };
@@ -171,7 +192,7 @@ struct SidePrim {
 template <int ND>
 __device__ __forceinline__ void side_prim(const double *Q, double gamma, SidePrim<ND> &S)
 {
-    const double ir = 1.0 / Q[0];
+    const double ir = fast_rcp(Q[0]);
     double m2 = 0.0;
     S.rho = Q[0];
 #pragma unroll
@@ -200,6 +221,7 @@ template <int ND>
 struct ChaAvg {
     double rho, p, beta_inv2;   // rho_ln, p_hat, 1/(2 beta_ln)
     double p_over_rho;          // p_hat / rho_ln
+    double irs;                 // 1/(rho_l + rho_r)
     double v[ND];
 };
 
@@ -208,10 +230,12 @@ __device__ __forceinline__ void cha_avg(const SidePrim<ND> &L, const SidePrim<ND
                                         double bl, double br, ChaAvg<ND> &A)
 {
     const double rs = L.rho + R.rho, bs = bl + br;
-    const double irs = 1.0 / rs, ibs = 1.0 / bs;
+    const double irb = fast_rcp(rs * bs);
+    const double irs = irb * bs, ibs = irb * rs;
     const double Fr = logmean_F(L.rho, R.rho, irs);
     const double Fb = logmean_F(bl, br, ibs);
-    A.rho = rs / (2.0 * Fr);
+    A.irs = irs;
+    A.rho = 0.5 * rs * fast_rcp(Fr);
     A.p = rs * ibs * 0.5;
     A.beta_inv2 = Fb * ibs;          // 1/(2 beta_ln) = Fb/(bl+br)
     A.p_over_rho = Fr * ibs;
@@ -221,7 +245,7 @@ __device__ __forceinline__ void cha_avg(const SidePrim<ND> &L, const SidePrim<ND
 
 template <int ND>
 __device__ __forceinline__ void nf_chandrasekhar(const SidePrim<ND> &L, const SidePrim<ND> &R,
-                                                 const ChaAvg<ND> &A, double gamma, double *F)
+                                                 const ChaAvg<ND> &A, double inv_gm1, double *F)
 {
     double ql = 0.0, qr = 0.0, qa = 0.0;
 #pragma unroll
@@ -233,7 +257,7 @@ __device__ __forceinline__ void nf_chandrasekhar(const SidePrim<ND> &L, const Si
     if (ND == 3) {   // reference quirk, Euler.jl:216: (... + ur^2 + vr^2 + wl^2)
         qr = R.vel[0] * R.vel[0] + R.vel[1] * R.vel[1] + L.vel[ND - 1] * L.vel[ND - 1];
     }
-    const double h = A.beta_inv2 / (gamma - 1.0) - 0.25 * (ql + qr) + A.p_over_rho + qa;
+    const double h = A.beta_inv2 * inv_gm1 - 0.25 * (ql + qr) + A.p_over_rho + qa;
     const double mdot = A.rho * A.v[0];
     F[0] = mdot;
     F[1] = mdot * A.v[0] + A.p;
@@ -254,11 +278,12 @@ __device__ __forceinline__ void euler_numflux(const FluxParams &fp, const double
     side_prim<ND>(Qr, g, R);
     const int kind = fp.numflux;
     const int avg = (kind == FX_STD || kind == FX_CHA) ? kind : fp.numflux_avg;
-    const double bl = L.rho / (2.0 * L.p), br = R.rho / (2.0 * R.p);
+    const double ipl = fast_rcp(L.p), ipr = fast_rcp(R.p);
+    const double bl = 0.5 * L.rho * ipl, br = 0.5 * R.rho * ipr;
     ChaAvg<ND> A;
     const bool need_cha = (avg == FX_CHA) || kind == FX_SCA || kind == FX_MAT;
     if (need_cha) cha_avg<ND>(L, R, bl, br, A);
-    if (avg == FX_CHA) nf_chandrasekhar<ND>(L, R, A, g, F);
+    if (avg == FX_CHA) nf_chandrasekhar<ND>(L, R, A, fp.inv_gm1, F);
     else nf_stdavg<ND>(Ql, Qr, L, R, F);
     if (kind == FX_STD || kind == FX_CHA) return;
 
@@ -267,7 +292,7 @@ __device__ __forceinline__ void euler_numflux(const FluxParams &fp, const double
         const double lam = fmax(fabs(L.vel[0]) + al, fabs(R.vel[0]) + ar);
         const double c = 0.5 * lam * fp.intensity;
 #pragma unroll
-        for (int v = 0; v < NV; v++) F[v] += c * (Ql[v] - Qr[v]);
+        for (int v = 0; v < NV; v++) F[v] = fma(c, Ql[v] - Qr[v], F[v]);
         return;
     }
     if (kind == FX_SCA) {
@@ -275,7 +300,7 @@ __device__ __forceinline__ void euler_numflux(const FluxParams &fp, const double
         const double lam = fmax(fabs(L.vel[0]) + al, fabs(R.vel[0]) + ar);
         const double rho = 0.5 * (L.rho + R.rho);
         const double dr = R.rho - L.rho;
-        const double gm1 = g - 1.0;
+        const double gm1 = fp.gm1;
         double dot_lr = 0.0, jump = 0.0;
 #pragma unroll
         for (int d = 0; d < ND; d++) {
@@ -308,14 +333,15 @@ __device__ __forceinline__ void euler_numflux(const FluxParams &fp, const double
             qa += A.v[d] * A.v[d];
         }
         const double v2 = 2.0 * qa - 0.5 * (ql + qr);
-        const double a = sqrt(g * A.p / A.rho);
-        const double h = g * A.beta_inv2 / (g - 1.0) + 0.5 * v2;
+        // a^2 = g p_hat / rho_ln = g * (p_hat/rho_ln)
+        const double a = sqrt(g * A.p_over_rho);
+        const double h = g * A.beta_inv2 * fp.inv_gm1 + 0.5 * v2;
         const double u = A.v[0];
-        // entropy-variable jump  W = ((g-s)/(g-1) - rho|v|^2/(2p), rho v/p, -rho/p)
-        const double sl = log(L.p) - g * log(L.rho);
-        const double sr = log(R.p) - g * log(R.rho);
+        // entropy-variable jump  W = ((g-s)/(g-1) - rho|v|^2/(2p), rho v/p, -rho/p) with
+        // s_l - s_r = log(p_l/p_r) - g log(rho_l/rho_r) evaluated as log-ratios
+        const double ds = log_ratio(L.p, R.p, fast_rcp(L.p + R.p)) - g * log_ratio(L.rho, R.rho, A.irs);
         double dW[NV];
-        dW[0] = ((g - sl) / (g - 1.0) - bl * ql) - ((g - sr) / (g - 1.0) - br * qr);
+        dW[0] = -ds * fp.inv_gm1 - (bl * ql - br * qr);
 #pragma unroll
         for (int d = 0; d < ND; d++) dW[1 + d] = 2.0 * (bl * L.vel[d] - br * R.vel[d]);
         dW[ND + 1] = -2.0 * (bl - br);
@@ -329,7 +355,7 @@ __device__ __forceinline__ void euler_numflux(const FluxParams &fp, const double
                 dm += A.v[d] * dW[1 + d];
                 dp += A.v[d] * dW[1 + d];
             }
-            const double t = A.rho / (2.0 * g);
+            const double t = 0.5 * A.rho * fp.inv_gamma;
             dm *= fabs(u - a) * t * c;
             dp *= fabs(u + a) * t * c;
             F[0] += dm + dp;
@@ -343,7 +369,7 @@ __device__ __forceinline__ void euler_numflux(const FluxParams &fp, const double
             double de = dW[0] + u * dW[1] + 0.5 * v2 * dW[ND + 1];
 #pragma unroll
             for (int d = 1; d < ND; d++) de += A.v[d] * dW[1 + d];
-            de *= fabs(u) * ((g - 1.0) * A.rho / g) * c;
+            de *= fabs(u) * (fp.gm1 * A.rho * fp.inv_gamma) * c;
             F[0] += de;
 #pragma unroll
             for (int d = 0; d < ND; d++) F[1 + d] += de * A.v[d];

@@ -51,6 +51,7 @@ struct KParams {
     FluxParams fp;
     // Cartesian geometry (PhysicalRegions.jl:370-408, 541-696)
     double cjac;                // prod(dx)/2^nd
+    double crjac;               // 1/cjac
     double cmet[3];             // metric diagonal  Ja^d_d
     double cfjac[3];            // face jac by direction
     // general geometry, device SoA
@@ -157,16 +158,23 @@ __device__ __forceinline__ void cart_frame(int pm, double *fr)
 {
     const int dm = pm >> 1;
     const double s = (pm & 1) ? 1.0 : -1.0;
+    // selects instead of dynamic indexing keep `fr` in registers
 #pragma unroll
-    for (int c = 0; c < 3 * ND; c++) fr[c] = 0.0;
-    fr[dm] = s;
+    for (int c = 0; c < ND; c++) fr[c] = (c == dm) ? s : 0.0;
     if (ND == 2) {
         // pos1: t=(0,-1)  pos2: t=(0,1)  pos3: t=(1,0)  pos4: t=(-1,0)
-        fr[ND + (1 - dm)] = (dm == 0) ? s : -s;
+#pragma unroll
+        for (int c = 0; c < ND; c++) fr[ND + c] = (c == 1 - dm) ? ((dm == 0) ? s : -s) : 0.0;
+#pragma unroll
+        for (int c = 0; c < ND; c++) fr[2 * ND + c] = 0.0;
     } else if (ND == 3) {
-        const int tm = (dm + 1) % 3, bm = (dm + 2) % 3;
-        fr[ND + tm] = s;
-        fr[2 * ND + bm] = 1.0;
+        const int tm = (dm == 2) ? 0 : dm + 1, bm = (dm == 0) ? 2 : dm - 1;
+#pragma unroll
+        for (int c = 0; c < ND; c++) fr[ND + c] = (c == tm) ? s : 0.0;
+#pragma unroll
+        for (int c = 0; c < ND; c++) fr[2 * ND + c] = (c == bm) ? 1.0 : 0.0;
+    } else {
+        fr[1] = 0.0; fr[2] = 0.0;
     }
 }
 
@@ -218,22 +226,32 @@ struct KCfg {
     static constexpr int NFT = NFACES * NFP;           // face tasks per element
     static constexpr int EPB = (NPTS >= 256) ? 1 : 256 / NPTS;
     static constexpr int THREADS = ((EPB * NPTS + 31) / 32) * 32;
+    static constexpr bool SPLIT = (VOL != VOL_STRONG);
+    // split form: node pair (i, i+s) is evaluated once, by node i, for s = 1..NP/2; pairs
+    // with s <= (NP-1)/2 are handed to the partner through the exchange buffer
+    static constexpr int ROUNDS = NP / 2;
+    static constexpr int XROUNDS = (NP - 1) / 2;
     // shared-memory layout (doubles), per element
-    static constexpr int NAUX = (EQ == EQ_EULER && VOL != VOL_STRONG) ? ND + 2 : 0;
-    static constexpr int NFT_VOL = (VOL == VOL_STRONG) ? ND * NV : 0;   // contravariant fluxes
-    static constexpr int NMET = CART ? 0 : ND * ND;
-    static constexpr int PER_ELEM = (NV + NAUX + NFT_VOL + NMET) * NPTS + NFACES * NV * NFP;
+    static constexpr int NAUX = (EQ == EQ_EULER && SPLIT) ? ND + 2 : 0;     // vel, p, beta
+    static constexpr int NFT_VOL = SPLIT ? 0 : ND * NV;                      // contravariant fluxes
+    static constexpr int NMET = (CART || !SPLIT) ? 0 : ND * ND;
+    static constexpr int NXCH = SPLIT ? 2 * XROUNDS * NV : 0;               // two exchange buffers
+    static constexpr int FOFF = (NV + NAUX + NFT_VOL + NMET + NXCH) * NPTS;
+    static constexpr int PER_ELEM = FOFF + NFACES * NV * NFP;
     static constexpr int OPS = NP * NP + 4 * NP;
     static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OPS + EPB * PER_ELEM);
+    // at least two CTAs per SM whenever the CTA is small enough (<= 128 registers/thread)
+    static constexpr int MIN_BLOCKS = (THREADS <= 256 && SMEM_BYTES <= 100 * 1024) ? 2 : 1;
 };
 
 template <class C>
-__global__ void __launch_bounds__(C::THREADS)
+__global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS)
 stage_kernel(const __grid_constant__ KParams P)
 {
     constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
     constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NFT = C::NFT, EPB = C::EPB;
-    constexpr bool CART = C::CART;
+    constexpr bool CART = C::CART, SPLIT = C::SPLIT;
+    constexpr int FOFF = C::FOFF;
 
     extern __shared__ double smem[];
     double *sD = smem;                       // [ii + NP*jj]
@@ -255,8 +273,7 @@ stage_kernel(const __grid_constant__ KParams P)
     double *sA = sQ + NV * NPTS;                                       // aux [a][node]
     double *sFt = sA + C::NAUX * NPTS;                                 // [d][v][node]
     double *sM = sFt + C::NFT_VOL * NPTS;                              // [c + ND*d][node]
-    // face fluxes of element `x`: sElem + x*PER_ELEM + FOFF : [lf][v][k]
-    constexpr int FOFF = (NV + C::NAUX + C::NFT_VOL + C::NMET) * NPTS;
+    double *sX = sM + C::NMET * NPTS;                                  // [buf][s][v][node]
 
     const int64_t ndof = P.ndof;
     const int64_t dof = (int64_t)e * NPTS + node;
@@ -264,18 +281,25 @@ stage_kernel(const __grid_constant__ KParams P)
     // ---------------- phase 1: load the element, node primitives, contravariant fluxes
     double Q[NV];
     double met[CART ? 1 : ND * ND];
+    double vi[ND], pi = 0.0, bi = 0.0;
     if (active) {
 #pragma unroll
-        for (int v = 0; v < NV; v++) { Q[v] = P.u_in[dof + ndof * v]; sQ[v * NPTS + node] = Q[v]; }
+        for (int v = 0; v < NV; v++) { Q[v] = __ldg(P.u_in + dof + ndof * v); sQ[v * NPTS + node] = Q[v]; }
         if (!CART) {
 #pragma unroll
-            for (int m = 0; m < ND * ND; m++) { met[m] = P.metric[dof + ndof * m]; sM[m * NPTS + node] = met[m]; }
+            for (int m = 0; m < ND * ND; m++) {
+                met[m] = __ldg(P.metric + dof + ndof * m);
+                if (SPLIT) sM[m * NPTS + node] = met[m];
+            }
         }
         if (EQ == EQ_EULER) {
             NodeAux<ND> A;
             node_aux<ND>(Q, P.fp.gamma, A);
             if (!(Q[0] > 0.0) || !(A.p > 0.0)) atomicOr(P.status, 1);
-            if (VOL != VOL_STRONG) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) vi[d] = A.vel[d];
+            pi = A.p; bi = A.beta;
+            if (SPLIT) {
 #pragma unroll
                 for (int d = 0; d < ND; d++) sA[d * NPTS + node] = A.vel[d];
                 sA[ND * NPTS + node] = A.p;
@@ -288,8 +312,8 @@ stage_kernel(const __grid_constant__ KParams P)
                     for (int v = 0; v < NV; v++) Ft[v] = 0.0;
 #pragma unroll
                     for (int c = 0; c < ND; c++) {
-                        const double m = CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d];
                         if (CART && c != d) continue;
+                        const double m = CART ? P.cmet[d] : met[c + ND * d];
                         euler_flux_dir<ND>(Q, A.vel, A.p, c, Fc);
 #pragma unroll
                         for (int v = 0; v < NV; v++) Ft[v] += Fc[v] * m;
@@ -298,7 +322,7 @@ stage_kernel(const __grid_constant__ KParams P)
                     for (int v = 0; v < NV; v++) sFt[(d * NV + v) * NPTS + node] = Ft[v];
                 }
             }
-        } else if (VOL == VOL_STRONG) {
+        } else if (!SPLIT) {
 #pragma unroll
             for (int d = 0; d < ND; d++) {
                 double an = 0.0;
@@ -315,13 +339,13 @@ stage_kernel(const __grid_constant__ KParams P)
     double acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; v++) acc[v] = 0.0;
-    if (active) {
+    if (!SPLIT) {
+        if (active) {
 #pragma unroll
-        for (int d = 0; d < ND; d++) {
-            int k, ii, base, stride;
-            node_line<ND, NP>(node, d, k, ii);
-            line_of<ND, NP>(d, k, base, stride);
-            if (VOL == VOL_STRONG) {
+            for (int d = 0; d < ND; d++) {
+                int k, ii, base, stride;
+                node_line<ND, NP>(node, d, k, ii);
+                line_of<ND, NP>(d, k, base, stride);
 #pragma unroll
                 for (int jj = 0; jj < NP; jj++) {
                     const double dij = sD[ii + NP * jj];
@@ -329,71 +353,95 @@ stage_kernel(const __grid_constant__ KParams P)
 #pragma unroll
                     for (int v = 0; v < NV; v++) acc[v] -= dij * sFt[(d * NV + v) * NPTS + l];
                 }
-            } else {
-                // own metric column Ja^d (and primitives) of this node
+            }
+        }
+    } else {
+        // split form  dQ_i -= sum_j D#[i,j] F#(i,j)   (OpDivergence.jl:248-282).  F# is
+        // symmetric: node i evaluates the pairs (i, i+s mod NP), s = 1..NP/2, keeps them
+        // for itself and leaves those with s <= (NP-1)/2 in shared memory for node i+s.
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+            int k, ii, base, stride;
+            node_line<ND, NP>(node, d, k, ii);
+            line_of<ND, NP>(d, k, base, stride);
+            double *xb = sX + (size_t)(d & 1) * (C::XROUNDS * NV * NPTS);
+            if (active) {
                 double ni[ND];
 #pragma unroll
                 for (int c = 0; c < ND; c++) ni[c] = CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d];
-                double vi[ND > 0 ? ND : 1], pi = 0.0, bi = 0.0;
-                if (EQ == EQ_EULER) {
-#pragma unroll
-                    for (int c = 0; c < ND; c++) vi[c] = sA[c * NPTS + node];
-                    pi = sA[ND * NPTS + node];
-                    bi = sA[(ND + 1) * NPTS + node];
-                }
-#pragma unroll
-                for (int jj = 0; jj < NP; jj++) {
-                    const double dij = sD[ii + NP * jj];
-                    const int l = base + jj * stride;
+                // diagonal entry: the node's own contravariant flux (OpDivergence.jl:252)
+                {
                     double F[NV];
-                    if (jj == ii) {
-                        // diagonal entry: the node's own contravariant flux (OpDivergence.jl:252)
-                        if (EQ == EQ_EULER) {
+                    if (EQ == EQ_EULER) {
 #pragma unroll
-                            for (int v = 0; v < NV; v++) F[v] = 0.0;
+                        for (int v = 0; v < NV; v++) F[v] = 0.0;
 #pragma unroll
-                            for (int c = 0; c < ND; c++) {
-                                if (CART && c != d) continue;
-                                double Fc[NV];
-                                euler_flux_dir<ND>(Q, vi, pi, c, Fc);
+                        for (int c = 0; c < ND; c++) {
+                            if (CART && c != d) continue;
+                            double Fc[NV];
+                            euler_flux_dir<ND>(Q, vi, pi, c, Fc);
 #pragma unroll
-                                for (int v = 0; v < NV; v++) F[v] += Fc[v] * ni[c];
-                            }
-                        } else {
-                            double an = 0.0;
-#pragma unroll
-                            for (int c = 0; c < ND; c++) an += P.fp.a[c] * ni[c];
-                            F[0] = an * Q[0];
+                            for (int v = 0; v < NV; v++) F[v] += Fc[v] * ni[c];
                         }
                     } else {
-                        double n[ND];
+                        double an = 0.0;
 #pragma unroll
-                        for (int c = 0; c < ND; c++)
-                            n[c] = CART ? ni[c] : 0.5 * (ni[c] + sM[(c + ND * d) * NPTS + l]);
-                        if (EQ == EQ_EULER) {
-                            double vl[ND];
+                        for (int c = 0; c < ND; c++) an += P.fp.a[c] * ni[c];
+                        F[0] = an * Q[0];
+                    }
+                    const double dii = sD[ii + NP * ii];
 #pragma unroll
-                            for (int c = 0; c < ND; c++) vl[c] = sA[c * NPTS + l];
-                            const double pl = sA[ND * NPTS + l];
-                            if (VOL == VOL_SPLIT_CHA) {
-                                const double bl = sA[(ND + 1) * NPTS + l];
-                                tp_chandrasekhar<ND>(Q[0], vi, pi, bi, sQ[l], vl, pl, bl,
-                                                     P.fp.gamma, n, F);
-                            } else {
-                                double Ql[NV];
+                    for (int v = 0; v < NV; v++) acc[v] -= dii * F[v];
+                }
 #pragma unroll
-                                for (int v = 0; v < NV; v++) Ql[v] = sQ[v * NPTS + l];
-                                tp_stdavg<ND>(Q, vi, pi, Ql, vl, pl, n, F);
-                            }
+                for (int s = 1; s <= C::ROUNDS; s++) {
+                    int jj = ii + s;
+                    if (jj >= NP) jj -= NP;
+                    const int l = base + jj * stride;
+                    const double dij = sD[ii + NP * jj];
+                    double n[ND], F[NV];
+#pragma unroll
+                    for (int c = 0; c < ND; c++)
+                        n[c] = CART ? ni[c] : 0.5 * (ni[c] + sM[(c + ND * d) * NPTS + l]);
+                    if (EQ == EQ_EULER) {
+                        double vl[ND];
+#pragma unroll
+                        for (int c = 0; c < ND; c++) vl[c] = sA[c * NPTS + l];
+                        if (VOL == VOL_SPLIT_CHA) {
+                            tp_chandrasekhar<ND>(Q[0], vi, bi, sQ[l], vl, sA[(ND + 1) * NPTS + l],
+                                                 P.fp.inv_gm1, n, F);
                         } else {
-                            double an = 0.0;
+                            double Ql[NV];
 #pragma unroll
-                            for (int c = 0; c < ND; c++) an += P.fp.a[c] * n[c];
-                            F[0] = an * (Q[0] + sQ[l]) * 0.5;
+                            for (int v = 0; v < NV; v++) Ql[v] = sQ[v * NPTS + l];
+                            tp_stdavg<ND>(Q, vi, pi, Ql, vl, sA[ND * NPTS + l], n, F);
                         }
+                    } else {
+                        double an = 0.0;
+#pragma unroll
+                        for (int c = 0; c < ND; c++) an += P.fp.a[c] * n[c];
+                        F[0] = an * (Q[0] + sQ[l]) * 0.5;
                     }
 #pragma unroll
                     for (int v = 0; v < NV; v++) acc[v] -= dij * F[v];
+                    if (s <= C::XROUNDS) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++) xb[((s - 1) * NV + v) * NPTS + node] = F[v];
+                    }
+                }
+            }
+            if (C::XROUNDS > 0) {
+                __syncthreads();
+                if (active) {
+#pragma unroll
+                    for (int s = 1; s <= C::XROUNDS; s++) {
+                        int jp = ii - s;
+                        if (jp < 0) jp += NP;
+                        const int lp = base + jp * stride;
+                        const double dij = sD[ii + NP * jp];
+#pragma unroll
+                        for (int v = 0; v < NV; v++) acc[v] -= dij * xb[((s - 1) * NV + v) * NPTS + lp];
+                    }
                 }
             }
         }
@@ -442,12 +490,13 @@ stage_kernel(const __grid_constant__ KParams P)
             if (CART) {
                 const int pm = master ? lf : nlf;
                 cart_frame<ND>(pm, fr);
-                fj = P.cfjac[pm >> 1];
+                fj = (pm >> 1) == 0 ? P.cfjac[0] : ((pm >> 1) == 1 ? P.cfjac[1] : P.cfjac[2]);
             } else {
                 const int64_t fi = (int64_t)P.faceid[(int64_t)te * NFACES + lf] * NFP + im;
 #pragma unroll
-                for (int c = 0; c < 3 * ND; c++) fr[c] = (c < ND * ND || ND == 3) ? P.frames[fi + P.nfacedofs * c] : 0.0;
-                fj = P.fjac[fi];
+                for (int c = 0; c < 3 * ND; c++)
+                    fr[c] = (c < ND * ND || ND == 3) ? __ldg(P.frames + fi + P.nfacedofs * c) : 0.0;
+                fj = __ldg(P.fjac + fi);
             }
 
             double Qnb[NV];
@@ -459,14 +508,14 @@ stage_kernel(const __grid_constant__ KParams P)
                 if (P.colloc) {
                     const int64_t n0 = nbase + (sn ? (NP - 1) * ns : 0);
 #pragma unroll
-                    for (int v = 0; v < NV; v++) Qnb[v] = P.u_in[n0 + ndof * v];
+                    for (int v = 0; v < NV; v++) Qnb[v] = __ldg(P.u_in + n0 + ndof * v);
                 } else {
                     const double *lv = sn ? sLp : sLm;
 #pragma unroll
                     for (int v = 0; v < NV; v++) {
                         double s = 0.0;
 #pragma unroll
-                        for (int ii = 0; ii < NP; ii++) s += lv[ii] * P.u_in[nbase + ii * ns + ndof * v];
+                        for (int ii = 0; ii < NP; ii++) s += lv[ii] * __ldg(P.u_in + nbase + ii * ns + ndof * v);
                         Qnb[v] = s;
                     }
                 }
@@ -532,14 +581,15 @@ stage_kernel(const __grid_constant__ KParams P)
             for (int v = 0; v < NV; v++)
                 acc[v] -= gl * sF[((2 * d) * NV + v) * NFP + k] + gr * sF[((2 * d + 1) * NV + v) * NFP + k];
         }
-        const double jac = CART ? P.cjac : P.jac[dof];
+        // mass matrix: dQ / jac (Diagonal ldiv!, MultielementDiscontinuous.jl:132-137)
+        const double rjac = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof));
         if (P.mode == MODE_RHS) {
 #pragma unroll
-            for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[v] / jac;
+            for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[v] * rjac;
         } else {
 #pragma unroll
             for (int v = 0; v < NV; v++) {
-                const double kv = acc[v] / jac;
+                const double kv = acc[v] * rjac;
                 double t;
                 if (P.mode == MODE_STAGE_FIRST) t = P.dt * kv;
                 else t = fma(P.dt, kv, P.rkA * P.tmp[dof + ndof * v]);
