@@ -257,6 +257,9 @@ struct flou_b200_handle {
     KParams base;
     // device memory
     double *u[2] = {nullptr, nullptr}, *tmp = nullptr, *k = nullptr;
+    double *tr[2] = {nullptr, nullptr};   // face traces of u[0], u[1]
+    bool traces_valid = false;            // tr[cur] matches u[cur]
+    bool colloc = false;
     int cur = 0;
     Conn *conn = nullptr;
     int *faceid = nullptr;
@@ -280,6 +283,7 @@ struct flou_b200_handle {
     cudaGraphExec_t graph = nullptr;
     std::vector<double> graph_key;
     int64_t launches = 0;
+    int64_t graph_launches_per_replay = 0;
 };
 
 namespace {
@@ -289,6 +293,16 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
                  const double *u_in, double *u_out)
 {
     KParams P = h->base;
+    const int iin = (u_in == h->u[0]) ? 0 : 1;
+    if (!h->traces_valid) {
+        // traces of u_in (first pass after an upload, and every pass with Gauss nodes)
+        CUDA_TRY(h->emit->launch(u_in, h->ndof, nullptr, (int)(h->ne_local * h->nfaces),
+                                 h->base.colloc, h->d_lm, h->d_lp, h->tr[iin], h->stream));
+        h->launches += 1;
+        h->traces_valid = true;
+    }
+    P.tr_in = h->tr[iin];
+    P.tr_out = h->tr[iin ^ 1];
     P.u_in = u_in;
     P.u_out = u_out;
     P.tmp = h->tmp;
@@ -297,12 +311,15 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
     P.rkA = A;
     P.rkB = B;
     P.dt = dt;
+    // after a stage pass the kernel has written the traces of u_out (collocated nodes only)
+    const bool out_traces = (mode != MODE_RHS) && h->colloc;
     if (h->nranks == 1 || h->nghost == 0) {
         P.elem_first = 0;
         P.elem_count = (int)h->ne_local;
         P.elem_list = nullptr;
         CUDA_TRY(h->stage->launch(P, h->stream));
         h->launches += 1;
+        if (mode != MODE_RHS) h->traces_valid = out_traces;
         return FLOU_B200_OK;
     }
     if (!h->comm) return fail(FLOU_B200_EINVAL, "partitioned handle used before flou_b200_comm_init");
@@ -332,6 +349,7 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
     P.elem_count = h->n_boundary;
     CUDA_TRY(h->stage->launch(P, h->stream));
     h->launches += 2;
+    if (mode != MODE_RHS) h->traces_valid = out_traces;
     return FLOU_B200_OK;
 }
 
@@ -463,6 +481,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         if (std::fabs(d->lminus[i] - em) > 1e-13 || std::fabs(d->lplus[i] - ep) > 1e-13) colloc = false;
     }
     P.colloc = colloc ? 1 : 0;
+    h->colloc = colloc;
     P.fp.gamma = d->gamma; P.fp.intensity = d->intensity;
     P.fp.gm1 = d->gamma - 1.0; P.fp.inv_gm1 = 1.0 / (d->gamma - 1.0); P.fp.inv_gamma = 1.0 / d->gamma;
     for (int c = 0; c < 3; c++) P.fp.a[c] = d->a[c];
@@ -546,6 +565,11 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     H_TRY(cudaMalloc((void **)&h->u[1], state_bytes));
     H_TRY(cudaMalloc((void **)&h->tmp, state_bytes));
     H_TRY(cudaMalloc((void **)&h->k, state_bytes));
+    const size_t trace_bytes = sizeof(double) * (size_t)h->ne_local * h->nfaces * h->nfp * h->nv;
+    H_TRY(cudaMalloc((void **)&h->tr[0], trace_bytes));
+    H_TRY(cudaMalloc((void **)&h->tr[1], trace_bytes));
+    H_TRY(cudaMemset(h->tr[0], 0, trace_bytes));
+    H_TRY(cudaMemset(h->tr[1], 0, trace_bytes));
     H_TRY(cudaMemset(h->u[0], 0, state_bytes));
     H_TRY(cudaMemset(h->u[1], 0, state_bytes));
     H_TRY(cudaMemset(h->tmp, 0, state_bytes));
@@ -581,7 +605,7 @@ int32_t flou_b200_destroy(flou_b200_handle *h)
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     destroy_graph(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    void *ptrs[] = {h->u[0], h->u[1], h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
+    void *ptrs[] = {h->u[0], h->u[1], h->tr[0], h->tr[1], h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
                     h->frames, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
                     h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -602,6 +626,7 @@ int32_t flou_b200_upload_state(flou_b200_handle *h, const double *Q)
     CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, sizeof(double) * (size_t)h->ndof * h->nv,
                              cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->traces_valid = false;
     return FLOU_B200_OK;
 }
 
@@ -641,7 +666,10 @@ int32_t flou_b200_rhs(flou_b200_handle *h, const double *Q, double *dQ, double t
     if (!h) return fail(FLOU_B200_EINVAL, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t bytes = sizeof(double) * (size_t)h->ndof * h->nv;
-    if (Q) CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (Q) {
+        CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, bytes, cudaMemcpyHostToDevice, h->stream));
+        h->traces_valid = false;
+    }
     const int32_t rc = run_pass(h, MODE_RHS, 0.0, 0.0, 0.0, h->u[h->cur], h->u[h->cur ^ 1]);
     if (rc) return rc;
     if (dQ) CUDA_TRY(cudaMemcpyAsync(dQ, h->k, bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -661,6 +689,13 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
     // only for single-rank handles: NCCL calls are issued directly.
     const bool use_graph = !(h->flags & FLOU_B200_FLAG_NO_GRAPH) && h->nranks == 1 && nsteps >= 4;
     int64_t done = 0;
+    if (use_graph && !h->traces_valid) {
+        // bring the traces of the current state up to date outside the captured region
+        CUDA_TRY(h->emit->launch(h->u[h->cur], h->ndof, nullptr, (int)(h->ne_local * h->nfaces),
+                                 h->base.colloc, h->d_lm, h->d_lp, h->tr[h->cur], h->stream));
+        h->launches += 1;
+        h->traces_valid = true;
+    }
     if (use_graph) {
         std::vector<double> key;
         key.push_back((double)nstages); key.push_back(dt); key.push_back((double)h->cur);
@@ -671,10 +706,13 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
             cudaGraph_t g = nullptr;
             const int cur0 = h->cur;
             const int64_t l0 = h->launches;
+            // Gauss nodes: every captured pass starts with its own trace emit
+            if (!h->colloc) h->traces_valid = false;
             CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             const int32_t rc = run_steps_direct(h, nstages, A, B, dt, 2);
             cudaError_t e = cudaStreamEndCapture(h->stream, &g);
             h->cur = cur0;
+            h->graph_launches_per_replay = h->launches - l0;
             h->launches = l0;
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             CUDA_TRY(e);
@@ -685,8 +723,9 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
         }
         while (nsteps - done >= 2) {
             CUDA_TRY(cudaGraphLaunch(h->graph, h->stream));
-            h->launches += 2 * nstages;
+            h->launches += h->graph_launches_per_replay;
             done += 2;
+            h->traces_valid = h->colloc;
         }
     }
     return run_steps_direct(h, nstages, A, B, dt, nsteps - done);
@@ -701,6 +740,7 @@ int32_t flou_b200_timeintegrate(flou_b200_handle *h, double *Q, int32_t nstages,
     const size_t bytes = sizeof(double) * (size_t)h->ndof * h->nv;
     CUDA_TRY(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, bytes, cudaMemcpyHostToDevice, h->stream));
+    h->traces_valid = false;
     const int32_t rc = flou_b200_lsrk2n_advance(h, nstages, A, B, c, dt, t0, nsteps);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(Q, h->u[h->cur], bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -715,6 +755,18 @@ int64_t flou_b200_ndofs_local(const flou_b200_handle *h) { return h ? h->ndof : 
 void *flou_b200_stream(flou_b200_handle *h) { return h ? (void *)h->stream : nullptr; }
 void *flou_b200_device_state(flou_b200_handle *h) { return h ? (void *)h->u[h->cur] : nullptr; }
 int64_t flou_b200_kernel_launches(const flou_b200_handle *h) { return h ? h->launches : 0; }
+
+int32_t flou_b200_kernel_info(flou_b200_handle *h, int32_t *grid_ctas, int32_t *threads,
+                              int32_t *smem_bytes, int32_t *elems_per_cta_iter)
+{
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (grid_ctas) *grid_ctas = h->stage->resident();
+    if (threads) *threads = h->stage->threads;
+    if (smem_bytes) *smem_bytes = (int32_t)h->stage->smem;
+    if (elems_per_cta_iter) *elems_per_cta_iter = h->stage->epb;
+    return FLOU_B200_OK;
+}
 
 int32_t flou_b200_timer_start(flou_b200_handle *h)
 {

@@ -1,7 +1,12 @@
 // Kernel instances for one (ND, NP) pair; compiled once per pair with
 //   -DFLOU_ND=<1|2|3> -DFLOU_NP=<2..8>
 // so the instances build in parallel.  dispatch.cu stitches the per-pair tables together.
+#include <cstdlib>
 #include "launch.h"
+
+#ifndef FLOU_GRID_MULT_DEFAULT
+#define FLOU_GRID_MULT_DEFAULT 1
+#endif
 
 #ifndef FLOU_ND
 #error "compile with -DFLOU_ND=.. -DFLOU_NP=.."
@@ -10,21 +15,43 @@
 namespace flou {
 
 template <class C>
+static int resident_ctas();
+
+template <class C>
 static cudaError_t do_prepare()
 {
     cudaError_t e = cudaFuncSetAttribute(stage_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     // ask for the largest shared-memory carve-out so several CTAs fit per SM
-    return cudaFuncSetAttribute(stage_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(stage_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    resident_ctas<C>();      // occupancy query outside any stream capture
+    return cudaSuccess;
+}
+
+// persistent grid: (CTAs that fit per SM) x (SM count), queried once per kernel instance
+template <class C>
+static int resident_ctas()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_kernel<C>, C::THREADS, C::SMEM_BYTES);
+        n = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    }
+    return n;
 }
 
 template <class C>
 static cudaError_t do_launch(const KParams &P, cudaStream_t s)
 {
     if (P.elem_count <= 0) return cudaSuccess;
-    const int grid = (P.elem_count + C::EPB - 1) / C::EPB;
+    const int ngroups = (P.elem_count + C::EPB - 1) / C::EPB;
+    const int grid = ngroups;      // one CTA per group of EPB consecutive elements
     stage_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(P);
     return cudaGetLastError();
 }
@@ -32,7 +59,7 @@ static cudaError_t do_launch(const KParams &P, cudaStream_t s)
 template <class C>
 static constexpr StageLauncher make()
 {
-    return StageLauncher{&do_launch<C>, &do_prepare<C>, C::EPB, C::THREADS, C::SMEM_BYTES};
+    return StageLauncher{&do_launch<C>, &do_prepare<C>, &resident_ctas<C>, C::EPB, C::THREADS, C::SMEM_BYTES};
 }
 
 #define ND FLOU_ND
@@ -43,7 +70,7 @@ static const StageLauncher table[2][3][2] = {
     {   // linear advection: strong, split (StdAverage two-point flux); no Chandrasekhar
         {make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, true>>()},
-        {StageLauncher{nullptr, nullptr, 0, 0, 0}, StageLauncher{nullptr, nullptr, 0, 0, 0}},
+        {StageLauncher{nullptr, nullptr, nullptr, 0, 0, 0}, StageLauncher{nullptr, nullptr, nullptr, 0, 0, 0}},
     },
     {   // Euler
         {make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, true>>()},

@@ -8,6 +8,7 @@ namespace flou {
 struct StageLauncher {
     cudaError_t (*launch)(const KParams &, cudaStream_t);
     cudaError_t (*prepare)();
+    int (*resident)();          // persistent grid size (CTAs per SM x SMs)
     int epb, threads;
     size_t smem;
 };

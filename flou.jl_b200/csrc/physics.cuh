@@ -27,17 +27,16 @@ enum : int { FX_STD = FLOU_B200_FLUX_STDAVERAGE, FX_LXF = FLOU_B200_FLUX_LXF,
              FX_CHA = FLOU_B200_FLUX_CHANDRASEKHAR, FX_SCA = FLOU_B200_FLUX_SCALARDISSIPATION,
              FX_MAT = FLOU_B200_FLUX_MATRIXDISSIPATION };
 
-// 1/x for normal, finite x (states are O(1)): MUFU.RCP64H seed + two Newton steps, no
-// special-case slow path.  Within 1 ulp of the correctly rounded quotient.
+// 1/x for normal, finite x (states are O(1)): MUFU.RCP64H seed + one cubic (Halley) step, no
+// special-case slow path.  Relative error ~1e-16 (checked in tests/test_parity_gpu.py).
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    // third-order step: r (1 + e + e^2), e = 1 - x r; a 2^-20 seed gives 2^-60
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 
 // rare branch of the logarithmic mean (|f| >= 0.1, i.e. a jump ratio above ~1.22): kept out
@@ -56,6 +55,20 @@ __device__ __forceinline__ double logmean_F(double al, double ar, double rsum)
     double F = 1.0 + u * (1.0 / 3.0 + u * (1.0 / 5.0 + u * (1.0 / 7.0)));
     if (u >= 0.01) F = logmean_F_slow(al, ar, f);
     return F;
+}
+
+static // Both log-mean factors of a flux with ONE branch on the common (smooth) path.
+__device__ __forceinline__ void logmean_F2(double a1, double a2, double ia, double b1, double b2,
+                                           double ib, double &Fa, double &Fb)
+{
+    const double fa = (a1 - a2) * ia, fb = (b1 - b2) * ib;
+    const double ua = fa * fa, ub = fb * fb;
+    Fa = 1.0 + ua * (1.0 / 3.0 + ua * (1.0 / 5.0 + ua * (1.0 / 7.0)));
+    Fb = 1.0 + ub * (1.0 / 3.0 + ub * (1.0 / 5.0 + ub * (1.0 / 7.0)));
+    if (fmax(ua, ub) >= 0.01) {
+        if (ua >= 0.01) Fa = logmean_F_slow(a1, a2, fa);
+        if (ub >= 0.01) Fb = logmean_F_slow(b1, b2, fb);
+    }
 }
 
 static __device__ __noinline__ double log_ratio_slow(double al, double ar) { return log(al / ar); }
@@ -82,7 +95,7 @@ __device__ __forceinline__ double pressure(const double *Q, double gamma)
     return (gamma - 1.0) * (Q[ND + 1] - m2 / (2.0 * Q[0]));
 }
 
-// Node primitives kept in shared memory for the split form: vel[ND], p, beta = rho/(2p).
+// Node primitives: vel[ND], p, beta = rho/(2p).
 template <int ND>
 struct NodeAux {
     double vel[ND];
@@ -117,34 +130,33 @@ __device__ __forceinline__ void euler_flux_dir(const double *Q, const double *ve
 }
 
 // Two-point Chandrasekhar flux contracted with the averaged metric vector n[ND].
-// (rho, vel, beta = rho/(2p)) are node primitives; inv_gm1 = 1/(gamma-1).
+// Node data: rho, half velocities hv = v/2, q = |v|^2, beta = rho/(2p); inv_gm1 = 1/(gamma-1).
 // Identities used (beta_ln = bs/(2 Fb), rho_ln = rs/(2 Fr), p_hat = rs/(2 bs)):
 //   1/(2 beta_ln (g-1)) = Fb/(bs (g-1)),      p_hat/rho_ln = Fr/bs.
 template <int ND>
-__device__ __forceinline__ void tp_chandrasekhar(double r1, const double *v1, double b1,
-                                                 double r2, const double *v2, double b2,
+__device__ __forceinline__ void tp_chandrasekhar(double r1, const double *hv1, double q1, double b1,
+                                                 double r2, const double *hv2, double q2, double b2,
                                                  double inv_gm1, const double *n, double *F)
 {
     const double rs = r1 + r2, bs = b1 + b2;
     const double irb = fast_rcp(rs * bs);        // one reciprocal for both sums
     const double irs = irb * bs, ibs = irb * rs;
-    const double Fr = logmean_F(r1, r2, irs);
-    const double Fb = logmean_F(b1, b2, ibs);
+    double Fr, Fb;
+    logmean_F2(r1, r2, irs, b1, b2, ibs, Fr, Fb);
     const double rho = 0.5 * rs * fast_rcp(Fr);  // logarithmic_mean(rho1, rho2)
     const double p = rs * ibs * 0.5;             // (rho1+rho2)/(2(beta1+beta2))
-    double vavg[ND], q12 = 0.0, qa = 0.0, vn = 0.0;
+    double vavg[ND], qa = 0.0, vn = 0.0;
 #pragma unroll
     for (int d = 0; d < ND; d++) {
-        vavg[d] = 0.5 * (v1[d] + v2[d]);
-        q12 += v1[d] * v1[d] + v2[d] * v2[d];
-        qa += vavg[d] * vavg[d];
-        vn += vavg[d] * n[d];
+        vavg[d] = hv1[d] + hv2[d];
+        qa = fma(vavg[d], vavg[d], qa);
+        vn = fma(vavg[d], n[d], vn);
     }
-    const double h = (Fb * inv_gm1 + Fr) * ibs - 0.25 * q12 + qa;
+    const double h = fma(fma(Fb, inv_gm1, Fr), ibs, fma(-0.25, q1 + q2, qa));
     const double mdot = rho * vn;                 // rho * (v . n)
     F[0] = mdot;
 #pragma unroll
-    for (int d = 0; d < ND; d++) F[1 + d] = mdot * vavg[d] + p * n[d];
+    for (int d = 0; d < ND; d++) F[1 + d] = fma(mdot, vavg[d], p * n[d]);
     F[ND + 1] = mdot * h;
 }
 
@@ -232,8 +244,8 @@ __device__ __forceinline__ void cha_avg(const SidePrim<ND> &L, const SidePrim<ND
     const double rs = L.rho + R.rho, bs = bl + br;
     const double irb = fast_rcp(rs * bs);
     const double irs = irb * bs, ibs = irb * rs;
-    const double Fr = logmean_F(L.rho, R.rho, irs);
-    const double Fb = logmean_F(bl, br, ibs);
+    double Fr, Fb;
+    logmean_F2(L.rho, R.rho, irs, bl, br, ibs, Fr, Fb);
     A.irs = irs;
     A.rho = 0.5 * rs * fast_rcp(Fr);
     A.p = rs * ibs * 0.5;

@@ -22,7 +22,21 @@
 #include <stdint.h>
 #include "physics.cuh"
 
+#ifndef FLOU_TPB
+#define FLOU_TPB 128      // target threads per CTA (measured: 128 beats 256 on B200)
+#endif
+
 namespace flou {
+
+// 8-byte asynchronous global -> shared copy (LDGSTS); completion via cp_async_wait_all()
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __host__ __device__ constexpr int ipow_c(int b, int e) { return e <= 0 ? 1 : b * ipow_c(b, e - 1); }
 
@@ -67,6 +81,9 @@ struct KParams {
     const int *bc_kind;
     const double *bc_state;     // [ib*nv + v]
     const double *bc_table;     // [(m*NFP + i)*nv + v]
+    // face traces of the state, one block per (element, local face): [(e*2nd + lf)*nv + v]*NFP + k
+    const double *tr_in;        // traces of u_in  (read by the neighbours)
+    double *tr_out;             // traces of u_out (written together with u_out)
     // halo
     const double *ghost;        // [(slot*nv + v)*NFP + k] in the sender's face-dof order
     // state
@@ -214,6 +231,52 @@ __device__ __forceinline__ void rotate2phys(const double *R, const double *fr, d
     Q[ND + 1] = R[ND + 1];
 }
 
+// Cartesian frames are signed axis permutations (PhysicalRegions.jl:541-696): rotating is
+// a component select and a sign, which reproduces the reference's dot products with
+// (+-1, 0, 0)-type vectors exactly.
+template <int ND>
+__device__ __forceinline__ double pick(const double *m, int c)
+{   // m[c] without dynamic register indexing
+    if (ND == 1) return m[0];
+    if (ND == 2) return c == 0 ? m[0] : m[1];
+    return c == 0 ? m[0] : (c == 1 ? m[1] : m[2]);
+}
+
+template <int ND, int EQ>
+__device__ __forceinline__ void rotate2face_cart(const double *Q, int dm, double s, double *R)
+{
+    R[0] = Q[0];
+    if (EQ == EQ_ADV) return;
+    R[1] = s * pick<ND>(Q + 1, dm);
+    if (ND == 2) R[2] = ((dm == 0) ? s : -s) * pick<ND>(Q + 1, 1 - dm);
+    if (ND == 3) {
+        const int tm = (dm == 2) ? 0 : dm + 1, bm = (dm == 0) ? 2 : dm - 1;
+        R[2] = s * pick<ND>(Q + 1, tm);
+        R[3] = pick<ND>(Q + 1, bm);
+    }
+    R[ND + 1] = Q[ND + 1];
+}
+
+template <int ND, int EQ>
+__device__ __forceinline__ void rotate2phys_cart(const double *R, int dm, double s, double *Q)
+{
+    Q[0] = R[0];
+    if (EQ == EQ_ADV) return;
+    if (ND == 1) Q[1] = s * R[1];
+    if (ND == 2) {
+        const double n = s * R[1], t = ((dm == 0) ? s : -s) * R[2];
+        Q[1] = dm == 0 ? n : t;
+        Q[2] = dm == 0 ? t : n;
+    }
+    if (ND == 3) {
+        const int tm = (dm == 2) ? 0 : dm + 1;
+        const double n = s * R[1], t = s * R[2], b = R[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) Q[1 + c] = (c == dm) ? n : (c == tm ? t : b);
+    }
+    Q[ND + 1] = R[ND + 1];
+}
+
 // ------------------------------------------------------------------ kernel configuration
 template <int ND_, int NP_, int EQ_, int VOL_, bool CART_>
 struct KCfg {
@@ -224,34 +287,69 @@ struct KCfg {
     static constexpr int NFP = ipow_c(NP, ND - 1);
     static constexpr int NFACES = 2 * ND;
     static constexpr int NFT = NFACES * NFP;           // face tasks per element
-    static constexpr int EPB = (NPTS >= 256) ? 1 : 256 / NPTS;
+    static constexpr int EPB = (NPTS >= FLOU_TPB) ? 1 : FLOU_TPB / NPTS;   // elements per group
     static constexpr int THREADS = ((EPB * NPTS + 31) / 32) * 32;
+    static constexpr int TPT = (EPB * NFT + THREADS - 1) / THREADS;         // face tasks per thread
     static constexpr bool SPLIT = (VOL != VOL_STRONG);
     // split form: node pair (i, i+s) is evaluated once, by node i, for s = 1..NP/2; pairs
     // with s <= (NP-1)/2 are handed to the partner through the exchange buffer
     static constexpr int ROUNDS = NP / 2;
     static constexpr int XROUNDS = (NP - 1) / 2;
-    // shared-memory layout (doubles), per element
-    static constexpr int NAUX = (EQ == EQ_EULER && SPLIT) ? ND + 2 : 0;     // vel, p, beta
+    // shared-memory layout (doubles), per element slot
+    static constexpr int QOFF = 0;                                           // sQ[NV][NPTS]
+    static constexpr int TOFF = QOFF + NV * NPTS;                            // sT[NV][NPTS]
+    static constexpr int AOFF = TOFF + NV * NPTS;
+    // Euler split form: Chandrasekhar keeps (v/2, |v|^2, beta) per node, StdAverage (v, p)
+    static constexpr int NAUX = (EQ == EQ_EULER && SPLIT) ? (VOL == VOL_SPLIT_CHA ? ND + 2 : ND + 1) : 0;
     static constexpr int NFT_VOL = SPLIT ? 0 : ND * NV;                      // contravariant fluxes
     static constexpr int NMET = (CART || !SPLIT) ? 0 : ND * ND;
     static constexpr int NXCH = SPLIT ? 2 * XROUNDS * NV : 0;               // two exchange buffers
-    static constexpr int FOFF = (NV + NAUX + NFT_VOL + NMET + NXCH) * NPTS;
+    // parked volume accumulators reuse the exchange buffer that is idle after the last
+    // direction (buffer ND&1) when there is one
+    static constexpr bool ACC_ALIAS = SPLIT && XROUNDS >= 1;
+    static constexpr int NACC = ACC_ALIAS ? 0 : NV;
+    static constexpr int FTOFF = AOFF + NAUX * NPTS;
+    static constexpr int MOFF = FTOFF + NFT_VOL * NPTS;
+    static constexpr int XOFF = MOFF + NMET * NPTS;
+    static constexpr int ACCOFF = ACC_ALIAS ? XOFF + (ND & 1) * (XROUNDS * NV * NPTS)
+                                            : XOFF + NXCH * NPTS;
+    // neighbour traces are prefetched into the slots the face fluxes later overwrite
+    static constexpr int FOFF = XOFF + (NXCH + NACC) * NPTS;
     static constexpr int PER_ELEM = FOFF + NFACES * NV * NFP;
     static constexpr int OPS = NP * NP + 4 * NP;
     static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OPS + EPB * PER_ELEM);
-    // at least two CTAs per SM whenever the CTA is small enough (<= 128 registers/thread)
-    static constexpr int MIN_BLOCKS = (THREADS <= 256 && SMEM_BYTES <= 100 * 1024) ? 2 : 1;
+    static constexpr int MIN_BLOCKS_WANTED =
+#ifdef FLOU_MIN_BLOCKS
+        FLOU_MIN_BLOCKS;
+#else
+        (THREADS > 256) ? 1 : (THREADS > 128 ? 2 : 4);
+#endif
+    static constexpr int SMEM_BLOCKS = (int)((227 * 1024) / (SMEM_BYTES + 1024));
+    static constexpr int MIN_BLOCKS =
+        SMEM_BLOCKS < 1 ? 1 : (SMEM_BLOCKS < MIN_BLOCKS_WANTED ? SMEM_BLOCKS : MIN_BLOCKS_WANTED);
 };
 
+template <int N>
+__device__ __forceinline__ Conn pick_conn(const Conn *cn, int j)
+{   // cn[j] for a register array (no dynamic indexing)
+    Conn c = cn[0];
+#pragma unroll
+    for (int q = 1; q < N; q++) if (j == q) c = cn[q];
+    return c;
+}
+
+// One CTA = one group of EPB consecutive elements.  Phase 0 starts the asynchronous copies
+// (cp.async) of `tmp` and of the neighbours' face traces -- contiguous blocks of the trace
+// array, so they coalesce -- and they are only waited for right before the face / update
+// phases, i.e. behind the volume work.
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS)
 stage_kernel(const __grid_constant__ KParams P)
 {
     constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
     constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NFT = C::NFT, EPB = C::EPB;
+    constexpr int TPT = C::TPT;
     constexpr bool CART = C::CART, SPLIT = C::SPLIT;
-    constexpr int FOFF = C::FOFF;
 
     extern __shared__ double smem[];
     double *sD = smem;                       // [ii + NP*jj]
@@ -263,201 +361,262 @@ stage_kernel(const __grid_constant__ KParams P)
     if (tid < NP) { sLm[tid] = P.lm[tid]; sLp[tid] = P.lp[tid]; sGl[tid] = P.dgl[tid]; sGr[tid] = P.dgr[tid]; }
 
     const int el = tid / NPTS, node = tid - el * NPTS;
-    const int eidx = blockIdx.x * EPB + el;
-    const bool active = (el < EPB) && (eidx < P.elem_count);
-    int e = 0;
-    if (active) e = P.elem_list ? P.elem_list[eidx] : P.elem_first + eidx;
-
-    // per-element shared arrays
-    double *sQ = sElem + (size_t)(el < EPB ? el : 0) * C::PER_ELEM;   // [v][node]
-    double *sA = sQ + NV * NPTS;                                       // aux [a][node]
-    double *sFt = sA + C::NAUX * NPTS;                                 // [d][v][node]
-    double *sM = sFt + C::NFT_VOL * NPTS;                              // [c + ND*d][node]
-    double *sX = sM + C::NMET * NPTS;                                  // [buf][s][v][node]
-
+    const bool node_thread = el < EPB;
+    double *sMine = sElem + (size_t)(node_thread ? el : 0) * C::PER_ELEM;
+    double *sQ = sMine + C::QOFF;
+    double *sT = sMine + C::TOFF;
+    double *sA = sMine + C::AOFF;
+    double *sFt = sMine + C::FTOFF;
+    double *sM = sMine + C::MOFF;
+    double *sX = sMine + C::XOFF;
+    double *sAcc = sMine + C::ACCOFF;
     const int64_t ndof = P.ndof;
+    const bool need_tmp = (P.mode == MODE_STAGE);
+
+    const int g = blockIdx.x;
+    const int nact = min(EPB, P.elem_count - g * EPB);
+    const bool active = node_thread && el < nact;
+    auto elem_of = [&](int idx) { return P.elem_list ? P.elem_list[idx] : P.elem_first + idx; };
+    const int e = active ? elem_of(g * EPB + el) : 0;
     const int64_t dof = (int64_t)e * NPTS + node;
 
-    // ---------------- phase 1: load the element, node primitives, contravariant fluxes
-    double Q[NV];
-    double met[CART ? 1 : ND * ND];
-    double vi[ND], pi = 0.0, bi = 0.0;
-    if (active) {
+    // ---------------- phase 0: connectivity of this thread's face tasks; start the copies
+    Conn cn_cur[TPT];
 #pragma unroll
-        for (int v = 0; v < NV; v++) { Q[v] = __ldg(P.u_in + dof + ndof * v); sQ[v * NPTS + node] = Q[v]; }
-        if (!CART) {
+    for (int j = 0; j < TPT; j++) {
+        const int task = tid + j * C::THREADS;
+        cn_cur[j].nbr = 0; cn_cur[j].info = conn_pack(0, 0, 1, FK_BOUNDARY, 0);
+        if (task < nact * NFT) {
+            const int tel = task / NFT, r = task - tel * NFT;
+            const int lf = r / NFP, k = r - lf * NFP;
+            const int te = elem_of(g * EPB + tel);
+            const int2 c = __ldg(reinterpret_cast<const int2 *>(P.conn) + ((int64_t)te * NFACES + lf));
+            cn_cur[j].nbr = c.x; cn_cur[j].info = c.y;
+            const int kind = (c.y >> 7) & 3;
+            if (kind != FK_BOUNDARY) {
+                const int nlf = c.y & 7, orient = (c.y >> 3) & 7;
+                const bool master = (c.y >> 6) & 1;
+                const int kn = master ? master2slave<ND, NP>(k, orient) : slave2master<ND, NP>(k, orient);
+                double *dst = sElem + (size_t)tel * C::PER_ELEM + C::FOFF + lf * NV * NFP + k;
+                const double *src = (kind == FK_INTERIOR)
+                    ? P.tr_in + ((int64_t)c.x * NFACES + nlf) * (NV * NFP) + kn
+                    : P.ghost + (int64_t)c.x * (NV * NFP) + kn;
 #pragma unroll
-            for (int m = 0; m < ND * ND; m++) {
-                met[m] = __ldg(P.metric + dof + ndof * m);
-                if (SPLIT) sM[m * NPTS + node] = met[m];
-            }
-        }
-        if (EQ == EQ_EULER) {
-            NodeAux<ND> A;
-            node_aux<ND>(Q, P.fp.gamma, A);
-            if (!(Q[0] > 0.0) || !(A.p > 0.0)) atomicOr(P.status, 1);
-#pragma unroll
-            for (int d = 0; d < ND; d++) vi[d] = A.vel[d];
-            pi = A.p; bi = A.beta;
-            if (SPLIT) {
-#pragma unroll
-                for (int d = 0; d < ND; d++) sA[d * NPTS + node] = A.vel[d];
-                sA[ND * NPTS + node] = A.p;
-                sA[(ND + 1) * NPTS + node] = A.beta;
-            } else {
-#pragma unroll
-                for (int d = 0; d < ND; d++) {
-                    double Fc[NV], Ft[NV];
-#pragma unroll
-                    for (int v = 0; v < NV; v++) Ft[v] = 0.0;
-#pragma unroll
-                    for (int c = 0; c < ND; c++) {
-                        if (CART && c != d) continue;
-                        const double m = CART ? P.cmet[d] : met[c + ND * d];
-                        euler_flux_dir<ND>(Q, A.vel, A.p, c, Fc);
-#pragma unroll
-                        for (int v = 0; v < NV; v++) Ft[v] += Fc[v] * m;
-                    }
-#pragma unroll
-                    for (int v = 0; v < NV; v++) sFt[(d * NV + v) * NPTS + node] = Ft[v];
-                }
-            }
-        } else if (!SPLIT) {
-#pragma unroll
-            for (int d = 0; d < ND; d++) {
-                double an = 0.0;
-#pragma unroll
-                for (int c = 0; c < ND; c++)
-                    an += P.fp.a[c] * (CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d]);
-                sFt[d * NPTS + node] = an * Q[0];
+                for (int v = 0; v < NV; v++) cp_async8(dst + v * NFP, src + v * NFP);
             }
         }
     }
-    __syncthreads();
-
-    // ---------------- phase 2: volume term
-    double acc[NV];
+    if (need_tmp && active) {
 #pragma unroll
-    for (int v = 0; v < NV; v++) acc[v] = 0.0;
-    if (!SPLIT) {
+        for (int v = 0; v < NV; v++) cp_async8(sT + v * NPTS + node, P.tmp + dof + ndof * v);
+    }
+    cp_async_commit();
+
+    {
+        // ---------------- phase 1: node primitives, contravariant fluxes
+        double Q[NV];
+        double met[CART ? 1 : ND * ND];
+        double vi[ND], hvi[ND], pi = 0.0, bi = 0.0, qi = 0.0;
         if (active) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) { Q[v] = __ldg(P.u_in + dof + ndof * v); sQ[v * NPTS + node] = Q[v]; }
+            if (!CART) {
+#pragma unroll
+                for (int m = 0; m < ND * ND; m++) {
+                    met[m] = __ldg(P.metric + dof + ndof * m);
+                    if (SPLIT) sM[m * NPTS + node] = met[m];
+                }
+            }
+            if (EQ == EQ_EULER) {
+                NodeAux<ND> A;
+                node_aux<ND>(Q, P.fp.gamma, A);
+                if (!(Q[0] > 0.0) || !(A.p > 0.0)) atomicOr(P.status, 1);
+#pragma unroll
+                for (int d = 0; d < ND; d++) vi[d] = A.vel[d];
+                pi = A.p; bi = A.beta;
+                if (VOL == VOL_SPLIT_CHA) {
+                    double q = 0.0;
+#pragma unroll
+                    for (int d = 0; d < ND; d++) {
+                        q = fma(A.vel[d], A.vel[d], q);
+                        hvi[d] = 0.5 * A.vel[d];
+                        sA[d * NPTS + node] = hvi[d];
+                    }
+                    qi = q;
+                    sA[ND * NPTS + node] = q;
+                    sA[(ND + 1) * NPTS + node] = A.beta;
+                } else if (VOL == VOL_SPLIT_STD) {
+#pragma unroll
+                    for (int d = 0; d < ND; d++) sA[d * NPTS + node] = A.vel[d];
+                    sA[ND * NPTS + node] = A.p;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < ND; d++) {
+                        double Fc[NV], Ft[NV];
+#pragma unroll
+                        for (int v = 0; v < NV; v++) Ft[v] = 0.0;
+#pragma unroll
+                        for (int c = 0; c < ND; c++) {
+                            if (CART && c != d) continue;
+                            const double m = CART ? P.cmet[d] : met[c + ND * d];
+                            euler_flux_dir<ND>(Q, A.vel, A.p, c, Fc);
+#pragma unroll
+                            for (int v = 0; v < NV; v++) Ft[v] += Fc[v] * m;
+                        }
+#pragma unroll
+                        for (int v = 0; v < NV; v++) sFt[(d * NV + v) * NPTS + node] = Ft[v];
+                    }
+                }
+            } else if (!SPLIT) {
+#pragma unroll
+                for (int d = 0; d < ND; d++) {
+                    double an = 0.0;
+#pragma unroll
+                    for (int c = 0; c < ND; c++)
+                        an += P.fp.a[c] * (CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d]);
+                    sFt[d * NPTS + node] = an * Q[0];
+                }
+            }
+        }
+        __syncthreads();     // every node's state and primitives are now visible
+
+        // ---------------- phase 2: volume term
+        double acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[v] = 0.0;
+        if (!SPLIT) {
+            if (active) {
+#pragma unroll
+                for (int d = 0; d < ND; d++) {
+                    int k, ii, base, stride;
+                    node_line<ND, NP>(node, d, k, ii);
+                    line_of<ND, NP>(d, k, base, stride);
+#pragma unroll
+                    for (int jj = 0; jj < NP; jj++) {
+                        const double dij = sD[ii + NP * jj];
+                        const int l = base + jj * stride;
+#pragma unroll
+                        for (int v = 0; v < NV; v++) acc[v] -= dij * sFt[(d * NV + v) * NPTS + l];
+                    }
+                }
+            }
+        }
+#ifdef FLOU_EXPERIMENT_SKIP_VOLUME
+        else if (P.elem_count < 0) {
+#else
+        else {
+#endif
+            // split form  dQ_i -= sum_j D#[i,j] F#(i,j)   (OpDivergence.jl:248-282).  F# is
+            // symmetric: node i evaluates the pairs (i, i+s mod NP), s = 1..NP/2, keeps them
+            // for itself and leaves those with s <= (NP-1)/2 in shared memory for node i+s.
 #pragma unroll
             for (int d = 0; d < ND; d++) {
                 int k, ii, base, stride;
                 node_line<ND, NP>(node, d, k, ii);
                 line_of<ND, NP>(d, k, base, stride);
-#pragma unroll
-                for (int jj = 0; jj < NP; jj++) {
-                    const double dij = sD[ii + NP * jj];
-                    const int l = base + jj * stride;
-#pragma unroll
-                    for (int v = 0; v < NV; v++) acc[v] -= dij * sFt[(d * NV + v) * NPTS + l];
-                }
-            }
-        }
-    } else {
-        // split form  dQ_i -= sum_j D#[i,j] F#(i,j)   (OpDivergence.jl:248-282).  F# is
-        // symmetric: node i evaluates the pairs (i, i+s mod NP), s = 1..NP/2, keeps them
-        // for itself and leaves those with s <= (NP-1)/2 in shared memory for node i+s.
-#pragma unroll
-        for (int d = 0; d < ND; d++) {
-            int k, ii, base, stride;
-            node_line<ND, NP>(node, d, k, ii);
-            line_of<ND, NP>(d, k, base, stride);
-            double *xb = sX + (size_t)(d & 1) * (C::XROUNDS * NV * NPTS);
-            if (active) {
-                double ni[ND];
-#pragma unroll
-                for (int c = 0; c < ND; c++) ni[c] = CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d];
-                // diagonal entry: the node's own contravariant flux (OpDivergence.jl:252)
-                {
-                    double F[NV];
-                    if (EQ == EQ_EULER) {
-#pragma unroll
-                        for (int v = 0; v < NV; v++) F[v] = 0.0;
-#pragma unroll
-                        for (int c = 0; c < ND; c++) {
-                            if (CART && c != d) continue;
-                            double Fc[NV];
-                            euler_flux_dir<ND>(Q, vi, pi, c, Fc);
-#pragma unroll
-                            for (int v = 0; v < NV; v++) F[v] += Fc[v] * ni[c];
-                        }
-                    } else {
-                        double an = 0.0;
-#pragma unroll
-                        for (int c = 0; c < ND; c++) an += P.fp.a[c] * ni[c];
-                        F[0] = an * Q[0];
-                    }
-                    const double dii = sD[ii + NP * ii];
-#pragma unroll
-                    for (int v = 0; v < NV; v++) acc[v] -= dii * F[v];
-                }
-#pragma unroll
-                for (int s = 1; s <= C::ROUNDS; s++) {
-                    int jj = ii + s;
-                    if (jj >= NP) jj -= NP;
-                    const int l = base + jj * stride;
-                    const double dij = sD[ii + NP * jj];
-                    double n[ND], F[NV];
-#pragma unroll
-                    for (int c = 0; c < ND; c++)
-                        n[c] = CART ? ni[c] : 0.5 * (ni[c] + sM[(c + ND * d) * NPTS + l]);
-                    if (EQ == EQ_EULER) {
-                        double vl[ND];
-#pragma unroll
-                        for (int c = 0; c < ND; c++) vl[c] = sA[c * NPTS + l];
-                        if (VOL == VOL_SPLIT_CHA) {
-                            tp_chandrasekhar<ND>(Q[0], vi, bi, sQ[l], vl, sA[(ND + 1) * NPTS + l],
-                                                 P.fp.inv_gm1, n, F);
-                        } else {
-                            double Ql[NV];
-#pragma unroll
-                            for (int v = 0; v < NV; v++) Ql[v] = sQ[v * NPTS + l];
-                            tp_stdavg<ND>(Q, vi, pi, Ql, vl, sA[ND * NPTS + l], n, F);
-                        }
-                    } else {
-                        double an = 0.0;
-#pragma unroll
-                        for (int c = 0; c < ND; c++) an += P.fp.a[c] * n[c];
-                        F[0] = an * (Q[0] + sQ[l]) * 0.5;
-                    }
-#pragma unroll
-                    for (int v = 0; v < NV; v++) acc[v] -= dij * F[v];
-                    if (s <= C::XROUNDS) {
-#pragma unroll
-                        for (int v = 0; v < NV; v++) xb[((s - 1) * NV + v) * NPTS + node] = F[v];
-                    }
-                }
-            }
-            if (C::XROUNDS > 0) {
-                __syncthreads();
+                double *xb = sX + (size_t)(d & 1) * (C::XROUNDS * NV * NPTS);
                 if (active) {
+                    double ni[ND];
 #pragma unroll
-                    for (int s = 1; s <= C::XROUNDS; s++) {
-                        int jp = ii - s;
-                        if (jp < 0) jp += NP;
-                        const int lp = base + jp * stride;
-                        const double dij = sD[ii + NP * jp];
+                    for (int c = 0; c < ND; c++) ni[c] = CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d];
+                    // diagonal entry: the node's own contravariant flux (OpDivergence.jl:252)
+                    {
+                        double F[NV];
+                        if (EQ == EQ_EULER) {
 #pragma unroll
-                        for (int v = 0; v < NV; v++) acc[v] -= dij * xb[((s - 1) * NV + v) * NPTS + lp];
+                            for (int v = 0; v < NV; v++) F[v] = 0.0;
+#pragma unroll
+                            for (int c = 0; c < ND; c++) {
+                                if (CART && c != d) continue;
+                                double Fc[NV];
+                                euler_flux_dir<ND>(Q, vi, pi, c, Fc);
+#pragma unroll
+                                for (int v = 0; v < NV; v++) F[v] += Fc[v] * ni[c];
+                            }
+                        } else {
+                            double an = 0.0;
+#pragma unroll
+                            for (int c = 0; c < ND; c++) an += P.fp.a[c] * ni[c];
+                            F[0] = an * Q[0];
+                        }
+                        const double dii = sD[ii + NP * ii];
+#pragma unroll
+                        for (int v = 0; v < NV; v++) acc[v] -= dii * F[v];
+                    }
+#pragma unroll
+                    for (int s = 1; s <= C::ROUNDS; s++) {
+                        int jj = ii + s;
+                        if (jj >= NP) jj -= NP;
+                        const int l = base + jj * stride;
+                        const double dij = sD[ii + NP * jj];
+                        double n[ND], F[NV];
+#pragma unroll
+                        for (int c = 0; c < ND; c++)
+                            n[c] = CART ? ni[c] : 0.5 * (ni[c] + sM[(c + ND * d) * NPTS + l]);
+                        if (EQ == EQ_EULER) {
+                            double vl[ND];
+#pragma unroll
+                            for (int c = 0; c < ND; c++) vl[c] = sA[c * NPTS + l];
+                            if (VOL == VOL_SPLIT_CHA) {
+                                tp_chandrasekhar<ND>(Q[0], hvi, qi, bi, sQ[l], vl, sA[ND * NPTS + l],
+                                                     sA[(ND + 1) * NPTS + l], P.fp.inv_gm1, n, F);
+                            } else {
+                                double Ql[NV];
+#pragma unroll
+                                for (int v = 0; v < NV; v++) Ql[v] = sQ[v * NPTS + l];
+                                tp_stdavg<ND>(Q, vi, pi, Ql, vl, sA[ND * NPTS + l], n, F);
+                            }
+                        } else {
+                            double an = 0.0;
+#pragma unroll
+                            for (int c = 0; c < ND; c++) an += P.fp.a[c] * n[c];
+                            F[0] = an * (Q[0] + sQ[l]) * 0.5;
+                        }
+#pragma unroll
+                        for (int v = 0; v < NV; v++) acc[v] -= dij * F[v];
+                        if (s <= C::XROUNDS) {
+#pragma unroll
+                            for (int v = 0; v < NV; v++) xb[((s - 1) * NV + v) * NPTS + node] = F[v];
+                        }
+                    }
+                }
+                if (C::XROUNDS > 0) {
+                    __syncthreads();
+                    if (active) {
+#pragma unroll
+                        for (int s = 1; s <= C::XROUNDS; s++) {
+                            int jp = ii - s;
+                            if (jp < 0) jp += NP;
+                            const int lp = base + jp * stride;
+                            const double dij = sD[ii + NP * jp];
+#pragma unroll
+                            for (int v = 0; v < NV; v++) acc[v] -= dij * xb[((s - 1) * NV + v) * NPTS + lp];
+                        }
                     }
                 }
             }
         }
-    }
+        // park the volume accumulators: the face phase needs the registers
+        if (active) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) sAcc[v * NPTS + node] = acc[v];
+        }
 
-    // ---------------- phase 3: face tasks (traces, BCs, Riemann flux) -> shared memory
-    {
-        const int nact = min(EPB, P.elem_count - blockIdx.x * EPB);
-        for (int task = tid; task < nact * NFT; task += C::THREADS) {
+        // ---------------- phase 3: face tasks (traces, BCs, Riemann flux) -> shared memory
+        cp_async_wait<0>();                 // tmp and the neighbours' traces have landed
+#ifdef FLOU_EXPERIMENT_SKIP_FACES
+        if (P.elem_count < 0)
+#endif
+#pragma unroll 1
+        for (int j = 0; j < TPT; j++) {
+            const int task = tid + j * C::THREADS;
+            if (task >= nact * NFT) break;
             const int tel = task / NFT, r = task - tel * NFT;
             const int lf = r / NFP, k = r - lf * NFP;
             const int d = lf >> 1, side = lf & 1;
-            const int teidx = blockIdx.x * EPB + tel;
-            const int te = P.elem_list ? P.elem_list[teidx] : P.elem_first + teidx;
-            const double *tQ = sElem + (size_t)tel * C::PER_ELEM;
-            double *tF = sElem + (size_t)tel * C::PER_ELEM + FOFF;
+            const double *tQ = sElem + (size_t)tel * C::PER_ELEM + C::QOFF;
+            double *tF = sElem + (size_t)tel * C::PER_ELEM + C::FOFF;
+            const Conn cn = pick_conn<TPT>(cn_cur, j);
 
             // own trace
             double Qown[NV];
@@ -478,7 +637,6 @@ stage_kernel(const __grid_constant__ KParams P)
                 }
             }
 
-            const Conn cn = P.conn[(int64_t)te * NFACES + lf];
             const int kind = (cn.info >> 7) & 3;
             const int nlf = cn.info & 7, orient = (cn.info >> 3) & 7;
             const bool master = (cn.info >> 6) & 1;
@@ -486,12 +644,16 @@ stage_kernel(const __grid_constant__ KParams P)
             const int kn = master ? master2slave<ND, NP>(k, orient) : slave2master<ND, NP>(k, orient);
             const int im = master ? k : kn;          // master face dof: frame and jac index
 
-            double fr[3 * ND], fj;
+            double fr[CART ? 1 : 3 * ND], fj;
+            int dm = 0;
+            double sn_ = 1.0;                      // Cartesian: normal = sn_ * e_dm
             if (CART) {
                 const int pm = master ? lf : nlf;
-                cart_frame<ND>(pm, fr);
-                fj = (pm >> 1) == 0 ? P.cfjac[0] : ((pm >> 1) == 1 ? P.cfjac[1] : P.cfjac[2]);
+                dm = pm >> 1;
+                sn_ = (pm & 1) ? 1.0 : -1.0;
+                fj = dm == 0 ? P.cfjac[0] : (dm == 1 ? P.cfjac[1] : P.cfjac[2]);
             } else {
+                const int te = elem_of(g * EPB + tel);
                 const int64_t fi = (int64_t)P.faceid[(int64_t)te * NFACES + lf] * NFP + im;
 #pragma unroll
                 for (int c = 0; c < 3 * ND; c++)
@@ -500,28 +662,9 @@ stage_kernel(const __grid_constant__ KParams P)
             }
 
             double Qnb[NV];
-            if (kind == FK_INTERIOR) {
-                const int dn = nlf >> 1, sn = nlf & 1;
-                int nb, ns;
-                line_of<ND, NP>(dn, kn, nb, ns);
-                const int64_t nbase = (int64_t)cn.nbr * NPTS + nb;
-                if (P.colloc) {
-                    const int64_t n0 = nbase + (sn ? (NP - 1) * ns : 0);
+            if (kind != FK_BOUNDARY) {
 #pragma unroll
-                    for (int v = 0; v < NV; v++) Qnb[v] = __ldg(P.u_in + n0 + ndof * v);
-                } else {
-                    const double *lv = sn ? sLp : sLm;
-#pragma unroll
-                    for (int v = 0; v < NV; v++) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int ii = 0; ii < NP; ii++) s += lv[ii] * __ldg(P.u_in + nbase + ii * ns + ndof * v);
-                        Qnb[v] = s;
-                    }
-                }
-            } else if (kind == FK_GHOST) {
-#pragma unroll
-                for (int v = 0; v < NV; v++) Qnb[v] = P.ghost[((int64_t)cn.nbr * NV + v) * NFP + kn];
+                for (int v = 0; v < NV; v++) Qnb[v] = tF[(lf * NV + v) * NFP + k];
             } else {
                 // boundary face: exterior state from the BC functor (Interfaces.jl:44-48)
                 const int ib = cn.info >> 9;
@@ -534,9 +677,11 @@ stage_kernel(const __grid_constant__ KParams P)
                     for (int v = 0; v < NV; v++) Qnb[v] = Qown[v];
                 } else if (bk == FLOU_B200_BC_SLIP) {
                     double R[NV];
-                    rotate2face<ND, EQ>(Qown, fr, R);
+                    if (CART) rotate2face_cart<ND, EQ>(Qown, dm, sn_, R);
+                    else rotate2face<ND, EQ>(Qown, fr, R);
                     if (NV > 1) R[NV > 1 ? 1 : 0] = -R[NV > 1 ? 1 : 0];
-                    rotate2phys<ND, EQ>(R, fr, Qnb);
+                    if (CART) rotate2phys_cart<ND, EQ>(R, dm, sn_, Qnb);
+                    else rotate2phys<ND, EQ>(R, fr, Qnb);
                 } else {
 #pragma unroll
                     for (int v = 0; v < NV; v++) Qnb[v] = P.bc_table[((int64_t)cn.nbr * NFP + k) * NV + v];
@@ -547,8 +692,13 @@ stage_kernel(const __grid_constant__ KParams P)
             double Ql[NV], Qr[NV], Fn[NV], Fp[NV];
             {
                 double Ro[NV], Rn[NV];
-                rotate2face<ND, EQ>(Qown, fr, Ro);
-                rotate2face<ND, EQ>(Qnb, fr, Rn);
+                if (CART) {
+                    rotate2face_cart<ND, EQ>(Qown, dm, sn_, Ro);
+                    rotate2face_cart<ND, EQ>(Qnb, dm, sn_, Rn);
+                } else {
+                    rotate2face<ND, EQ>(Qown, fr, Ro);
+                    rotate2face<ND, EQ>(Qnb, fr, Rn);
+                }
 #pragma unroll
                 for (int v = 0; v < NV; v++) { Ql[v] = master ? Ro[v] : Rn[v]; Qr[v] = master ? Rn[v] : Ro[v]; }
             }
@@ -556,53 +706,80 @@ stage_kernel(const __grid_constant__ KParams P)
                 euler_numflux<ND>(P.fp, Ql, Qr, Fn);
             } else {
                 double an = 0.0;
+                if (CART) an = sn_ * pick<ND>(P.fp.a, dm);
+                else {
 #pragma unroll
-                for (int c = 0; c < ND; c++) an += P.fp.a[c] * fr[c];
+                    for (int c = 0; c < ND; c++) an += P.fp.a[c] * fr[c];
+                }
                 Fn[0] = an * (Ql[0] + Qr[0]) * 0.5;
                 if (P.fp.numflux == FX_LXF) Fn[0] += fabs(an) * (Ql[0] - Qr[0]) * 0.5 * P.fp.intensity;
             }
-            rotate2phys<ND, EQ>(Fn, fr, Fp);
+            if (CART) rotate2phys_cart<ND, EQ>(Fn, dm, sn_, Fp);
+            else rotate2phys<ND, EQ>(Fn, fr, Fp);
             const double sgn = master ? fj : -fj;
 #pragma unroll
             for (int v = 0; v < NV; v++) tF[(lf * NV + v) * NFP + k] = Fp[v] * sgn;
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---------------- phase 4: lift, mass matrix, RK stage update
-    if (active) {
-        const double *sF = sElem + (size_t)el * C::PER_ELEM + FOFF;
+        // ---------------- phase 4: lift, mass matrix, RK stage update
+        if (active) {
+            const double *sF = sMine + C::FOFF;
 #pragma unroll
-        for (int d = 0; d < ND; d++) {
-            int k, ii;
-            node_line<ND, NP>(node, d, k, ii);
-            const double gl = sGl[ii], gr = sGr[ii];
+            for (int v = 0; v < NV; v++) acc[v] = sAcc[v * NPTS + node];
+#ifdef FLOU_EXPERIMENT_SKIP_LIFT
+            if (P.elem_count < 0)
+#endif
 #pragma unroll
-            for (int v = 0; v < NV; v++)
-                acc[v] -= gl * sF[((2 * d) * NV + v) * NFP + k] + gr * sF[((2 * d + 1) * NV + v) * NFP + k];
-        }
-        // mass matrix: dQ / jac (Diagonal ldiv!, MultielementDiscontinuous.jl:132-137)
-        const double rjac = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof));
-        if (P.mode == MODE_RHS) {
+            for (int d = 0; d < ND; d++) {
+                int k, ii;
+                node_line<ND, NP>(node, d, k, ii);
+                const double gl = sGl[ii], gr = sGr[ii];
 #pragma unroll
-            for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[v] * rjac;
-        } else {
+                for (int v = 0; v < NV; v++)
+                    acc[v] -= gl * sF[((2 * d) * NV + v) * NFP + k] + gr * sF[((2 * d + 1) * NV + v) * NFP + k];
+            }
+            // mass matrix: dQ / jac (Diagonal ldiv!, MultielementDiscontinuous.jl:132-137)
+            const double rjac = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof));
+            if (P.mode == MODE_RHS) {
 #pragma unroll
-            for (int v = 0; v < NV; v++) {
-                const double kv = acc[v] * rjac;
-                double t;
-                if (P.mode == MODE_STAGE_FIRST) t = P.dt * kv;
-                else t = fma(P.dt, kv, P.rkA * P.tmp[dof + ndof * v]);
-                P.tmp[dof + ndof * v] = t;
-                P.u_out[dof + ndof * v] = fma(P.rkB, t, Q[v]);
+                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[v] * rjac;
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const double kv = acc[v] * rjac;
+                    double t;
+                    if (P.mode == MODE_STAGE_FIRST) t = P.dt * kv;
+                    else t = fma(P.dt, kv, P.rkA * sT[v * NPTS + node]);
+                    P.tmp[dof + ndof * v] = t;
+                    const double un = fma(P.rkB, t, sQ[v * NPTS + node]);
+                    P.u_out[dof + ndof * v] = un;
+                    acc[v] = un;
+                }
+                // traces of the new state for the next stage (collocated nodes: the boundary
+                // node values; Gauss nodes are handled by emit_traces_kernel)
+                if (P.colloc) {
+#pragma unroll
+                    for (int d = 0; d < ND; d++) {
+                        int k, ii;
+                        node_line<ND, NP>(node, d, k, ii);
+                        if (ii == 0 || ii == NP - 1) {
+                            const int lf = 2 * d + (ii == 0 ? 0 : 1);
+                            double *dst = P.tr_out + ((int64_t)e * NFACES + lf) * (NV * NFP) + k;
+#pragma unroll
+                            for (int v = 0; v < NV; v++) dst[v * NFP] = acc[v];
+                        }
+                    }
+                }
             }
         }
     }
 }
 
 // ------------------------------------------------------------------ halo trace emit
-// Traces of the partition-boundary faces, in this side's face-dof order, packed for
-// ncclSend:  out[(slot*NV + v)*NFP + k].   list[slot] = local element * 2nd + local face.
+// Face traces of a state, in the owning side's face-dof order: out[(slot*NV + v)*NFP + k].
+// list[slot] = local element * 2nd + local face (partition-boundary faces packed for
+// ncclSend), or list == nullptr for every (element, face): the full trace array.
 template <int ND, int NP, int NV>
 __global__ void emit_traces_kernel(const double *__restrict__ u, int64_t ndof,
                                    const int *__restrict__ list, int nslots, int colloc,
@@ -613,7 +790,7 @@ __global__ void emit_traces_kernel(const double *__restrict__ u, int64_t ndof,
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)nslots * NFP) return;
     const int slot = (int)(t / NFP), k = (int)(t - (int64_t)slot * NFP);
-    const int ef = list[slot];
+    const int ef = list ? list[slot] : slot;
     const int e = ef / NFACES, lf = ef - e * NFACES;
     const int d = lf >> 1, side = lf & 1;
     int base, stride;

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflou_b200.so")
+# FLOU_B200_LIB: alternative build of the same library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("FLOU_B200_LIB") or os.path.join(_HERE, "libflou_b200.so")
 
 OK, EINVAL, ECUDA, ENCCL, EDOMAIN, EUNSUPPORTED = range(6)
 
@@ -69,6 +70,7 @@ SYMBOLS = {
     "flou_b200_stream": (C.c_void_p, [C.c_void_p]),
     "flou_b200_device_state": (C.c_void_p, [C.c_void_p]),
     "flou_b200_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "flou_b200_kernel_info": (C.c_int32, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),
     "flou_b200_timer_start": (C.c_int32, [C.c_void_p]),
     "flou_b200_timer_stop": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
     "flou_b200_pin_host": (C.c_int32, [C.c_void_p, C.c_uint64]),

@@ -209,6 +209,12 @@ class MultielementDisc:
     def kernel_launches(self):
         return int(L.lib().flou_b200_kernel_launches(self.handle))
 
+    def kernel_info(self):
+        v = [C.c_int32(0) for _ in range(4)]
+        L.check(L.lib().flou_b200_kernel_info(self.handle, *[C.byref(x) for x in v]))
+        return dict(grid_ctas=v[0].value, threads=v[1].value, smem_bytes=v[2].value,
+                    elems_per_cta_iter=v[3].value)
+
     def timer_start(self):
         L.check(L.lib().flou_b200_timer_start(self.handle))
 

@@ -182,6 +182,10 @@ int64_t flou_b200_ndofs_local(const flou_b200_handle *h);
 void *flou_b200_stream(flou_b200_handle *h);         /* cudaStream_t of the compute stream   */
 void *flou_b200_device_state(flou_b200_handle *h);   /* device pointer of the current u      */
 int64_t flou_b200_kernel_launches(const flou_b200_handle *h); /* stage/rhs/halo kernels so far */
+/* launch geometry of the fused stage kernel: persistent grid size (resident CTAs), threads
+ * per CTA, dynamic shared memory per CTA, elements a CTA processes per loop iteration */
+int32_t flou_b200_kernel_info(flou_b200_handle *h, int32_t *grid_ctas, int32_t *threads,
+                              int32_t *smem_bytes, int32_t *elems_per_cta_iter);
 /* CUDA-event stopwatch on the compute stream (kernel timing for the roofline figure) */
 int32_t flou_b200_timer_start(flou_b200_handle *h);
 int32_t flou_b200_timer_stop(flou_b200_handle *h, float *ms);
