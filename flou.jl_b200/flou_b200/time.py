@@ -69,7 +69,8 @@ class Solution:
 
 
 def timeintegrate(Q0, disc, equation, solver, tfinal, *, dt, adaptive=False, alias_u0=True,
-                  saveat=None, save_everystep=False, callback=None, t0=0.0, nsteps=None):
+                  saveat=None, save_everystep=False, callback=None, t0=0.0, nsteps=None,
+                  save_start=True):
     """Returns (sol, exetime) like the reference; `Q0` is overwritten when alias_u0=True.
 
     Only fixed-step integration (`adaptive=false`) without callbacks is on the hot path."""
@@ -80,7 +81,8 @@ def timeintegrate(Q0, disc, equation, solver, tfinal, *, dt, adaptive=False, ali
     if equation is not disc.equation:
         raise ValueError("`equation` is not the one the discretisation was built with")
     Q = _state(Q0, disc.ndofs, disc.nv, writable=alias_u0)
-    u0 = Q.copy(order="F")
+    # sol.u[1] like `saveat=(0, tf)` in the reference's tests; skipped with save_start=False
+    u0 = Q.copy(order="F") if (save_start or not alias_u0) else None
     if not alias_u0:
         Q = u0.copy(order="F")
     if nsteps is None:
