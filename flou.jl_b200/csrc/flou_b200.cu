@@ -257,7 +257,8 @@ struct flou_b200_handle {
     KParams base;
     // device memory
     double *u[2] = {nullptr, nullptr}, *tmp = nullptr, *k = nullptr;
-    double *tr[2] = {nullptr, nullptr};   // face traces of u[0], u[1]
+    double *tr[2] = {nullptr, nullptr};   // x-face traces of u[0], u[1]
+    double *tr_all = nullptr;             // Gauss nodes: interpolated traces of every face
     bool traces_valid = false;            // tr[cur] matches u[cur]
     bool colloc = false;
     int cur = 0;
@@ -296,11 +297,17 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
     const int iin = (u_in == h->u[0]) ? 0 : 1;
     if (!h->traces_valid) {
         // traces of u_in (first pass after an upload, and every pass with Gauss nodes)
-        CUDA_TRY(h->emit->launch(u_in, h->ndof, nullptr, (int)(h->ne_local * h->nfaces),
+        CUDA_TRY(h->emit->launch(u_in, h->ndof, nullptr, (int)(h->ne_local * 2), 2,
                                  h->base.colloc, h->d_lm, h->d_lp, h->tr[iin], h->stream));
         h->launches += 1;
+        if (!h->colloc) {
+            CUDA_TRY(h->emit->launch(u_in, h->ndof, nullptr, (int)(h->ne_local * h->nfaces), h->nfaces,
+                                     0, h->d_lm, h->d_lp, h->tr_all, h->stream));
+            h->launches += 1;
+        }
         h->traces_valid = true;
     }
+    P.tr_hi = h->tr_all;
     P.tr_in = h->tr[iin];
     P.tr_out = h->tr[iin ^ 1];
     P.u_in = u_in;
@@ -325,7 +332,7 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
     if (!h->comm) return fail(FLOU_B200_EINVAL, "partitioned handle used before flou_b200_comm_init");
     // 1. pack the traces the neighbours need, 2. exchange on the comm stream,
     // 3. interior elements meanwhile, 4. partition-boundary elements after the receive
-    CUDA_TRY(h->emit->launch(u_in, h->ndof, h->send_list, (int)h->nghost, h->base.colloc,
+    CUDA_TRY(h->emit->launch(u_in, h->ndof, h->send_list, (int)h->nghost, h->nfaces, h->base.colloc,
                              h->d_lm, h->d_lp, h->sendbuf, h->stream));
     h->launches += 1;
     CUDA_TRY(cudaEventRecord(h->ev_emit, h->stream));
@@ -482,6 +489,14 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     }
     P.colloc = colloc ? 1 : 0;
     h->colloc = colloc;
+    if (colloc) {
+        // GLL: l(-1) = e_1 and l(+1) = e_np up to the reference's monomial round-off
+        // (O(1e-16) off-entries); the lifting weights away from the end nodes are dropped
+        for (int i = 0; i < np; i++) {
+            if (i != 0) P.dgl[i] = 0.0;
+            if (i != np - 1) P.dgr[i] = 0.0;
+        }
+    }
     P.fp.gamma = d->gamma; P.fp.intensity = d->intensity;
     P.fp.gm1 = d->gamma - 1.0; P.fp.inv_gm1 = 1.0 / (d->gamma - 1.0); P.fp.inv_gamma = 1.0 / d->gamma;
     for (int c = 0; c < 3; c++) P.fp.a[c] = d->a[c];
@@ -565,7 +580,12 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     H_TRY(cudaMalloc((void **)&h->u[1], state_bytes));
     H_TRY(cudaMalloc((void **)&h->tmp, state_bytes));
     H_TRY(cudaMalloc((void **)&h->k, state_bytes));
-    const size_t trace_bytes = sizeof(double) * (size_t)h->ne_local * h->nfaces * h->nfp * h->nv;
+    const size_t trace_bytes = sizeof(double) * (size_t)h->ne_local * 2 * h->nfp * h->nv;
+    if (!h->colloc) {
+        const size_t all_bytes = sizeof(double) * (size_t)h->ne_local * h->nfaces * h->nfp * h->nv;
+        H_TRY(cudaMalloc((void **)&h->tr_all, all_bytes));
+        H_TRY(cudaMemset(h->tr_all, 0, all_bytes));
+    }
     H_TRY(cudaMalloc((void **)&h->tr[0], trace_bytes));
     H_TRY(cudaMalloc((void **)&h->tr[1], trace_bytes));
     H_TRY(cudaMemset(h->tr[0], 0, trace_bytes));
@@ -605,7 +625,7 @@ int32_t flou_b200_destroy(flou_b200_handle *h)
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     destroy_graph(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    void *ptrs[] = {h->u[0], h->u[1], h->tr[0], h->tr[1], h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
+    void *ptrs[] = {h->u[0], h->u[1], h->tr[0], h->tr[1], h->tr_all, h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
                     h->frames, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
                     h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -691,10 +711,10 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
     int64_t done = 0;
     if (use_graph && !h->traces_valid) {
         // bring the traces of the current state up to date outside the captured region
-        CUDA_TRY(h->emit->launch(h->u[h->cur], h->ndof, nullptr, (int)(h->ne_local * h->nfaces),
+        CUDA_TRY(h->emit->launch(h->u[h->cur], h->ndof, nullptr, (int)(h->ne_local * 2), 2,
                                  h->base.colloc, h->d_lm, h->d_lp, h->tr[h->cur], h->stream));
         h->launches += 1;
-        h->traces_valid = true;
+        h->traces_valid = h->colloc;     // Gauss nodes: the captured passes emit their own
     }
     if (use_graph) {
         std::vector<double> key;

@@ -81,15 +81,15 @@ static const StageLauncher table[2][3][2] = {
 
 template <int NV>
 static cudaError_t emit_launch(const double *u, int64_t ndof, const int *list, int nslots,
-                               int colloc, const double *lm, const double *lp, double *out,
-                               cudaStream_t s)
+                               int faces_per_elem, int colloc, const double *lm, const double *lp,
+                               double *out, cudaStream_t s)
 {
     if (nslots <= 0) return cudaSuccess;
     constexpr int NFP = ipow_c(NP, ND - 1);
     const int64_t n = (int64_t)nslots * NFP;
     const int threads = 128;
     const int grid = (int)((n + threads - 1) / threads);
-    emit_traces_kernel<ND, NP, NV><<<grid, threads, 0, s>>>(u, ndof, list, nslots, colloc, lm, lp, out);
+    emit_traces_kernel<ND, NP, NV><<<grid, threads, 0, s>>>(u, ndof, list, nslots, faces_per_elem, colloc, lm, lp, out);
     return cudaGetLastError();
 }
 

@@ -14,7 +14,8 @@ struct StageLauncher {
 };
 
 struct EmitLauncher {
-    cudaError_t (*launch)(const double *u, int64_t ndof, const int *list, int nslots, int colloc,
+    cudaError_t (*launch)(const double *u, int64_t ndof, const int *list, int nslots,
+                          int faces_per_elem, int colloc,
                           const double *lm, const double *lp, double *out, cudaStream_t);
 };
 

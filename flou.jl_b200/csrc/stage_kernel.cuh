@@ -81,9 +81,12 @@ struct KParams {
     const int *bc_kind;
     const double *bc_state;     // [ib*nv + v]
     const double *bc_table;     // [(m*NFP + i)*nv + v]
-    // face traces of the state, one block per (element, local face): [(e*2nd + lf)*nv + v]*NFP + k
+    // traces of the two x-faces of every element (the only faces whose nodes are strided in
+    // u), one contiguous block per (element, side): [(e*2 + side)*nv + v]*NFP + k
     const double *tr_in;        // traces of u_in  (read by the neighbours)
     double *tr_out;             // traces of u_out (written together with u_out)
+    // Gauss nodes only: interpolated traces of the remaining faces, [(e*2nd + lf)*nv + v]*NFP + k
+    const double *tr_hi;
     // halo
     const double *ghost;        // [(slot*nv + v)*NFP + k] in the sender's face-dof order
     // state
@@ -393,16 +396,36 @@ stage_kernel(const __grid_constant__ KParams P)
             const int2 c = __ldg(reinterpret_cast<const int2 *>(P.conn) + ((int64_t)te * NFACES + lf));
             cn_cur[j].nbr = c.x; cn_cur[j].info = c.y;
             const int kind = (c.y >> 7) & 3;
+#ifdef FLOU_EXPERIMENT_SKIP_TRACE_READ
+            if (kind != FK_BOUNDARY && P.elem_count < 0) {
+#else
             if (kind != FK_BOUNDARY) {
+#endif
                 const int nlf = c.y & 7, orient = (c.y >> 3) & 7;
                 const bool master = (c.y >> 6) & 1;
                 const int kn = master ? master2slave<ND, NP>(k, orient) : slave2master<ND, NP>(k, orient);
                 double *dst = sElem + (size_t)tel * C::PER_ELEM + C::FOFF + lf * NV * NFP + k;
-                const double *src = (kind == FK_INTERIOR)
-                    ? P.tr_in + ((int64_t)c.x * NFACES + nlf) * (NV * NFP) + kn
-                    : P.ghost + (int64_t)c.x * (NV * NFP) + kn;
+                if (kind == FK_GHOST) {
+                    const double *src = P.ghost + (int64_t)c.x * (NV * NFP) + kn;
 #pragma unroll
-                for (int v = 0; v < NV; v++) cp_async8(dst + v * NFP, src + v * NFP);
+                    for (int v = 0; v < NV; v++) cp_async8(dst + v * NFP, src + v * NFP);
+                } else if (nlf < 2) {
+                    // the neighbour's x-faces are strided in u: read its trace block instead
+                    const double *src = P.tr_in + ((int64_t)c.x * 2 + nlf) * (NV * NFP) + kn;
+#pragma unroll
+                    for (int v = 0; v < NV; v++) cp_async8(dst + v * NFP, src + v * NFP);
+                } else if (P.colloc) {
+                    // y-/z-faces of the neighbour are (runs of) contiguous nodes of u
+                    int nb, ns;
+                    line_of<ND, NP>(nlf >> 1, kn, nb, ns);
+                    const double *src = P.u_in + (int64_t)c.x * NPTS + nb + ((nlf & 1) ? (NP - 1) * ns : 0);
+#pragma unroll
+                    for (int v = 0; v < NV; v++) cp_async8(dst + v * NFP, src + ndof * v);
+                } else {
+                    const double *src = P.tr_hi + ((int64_t)c.x * NFACES + nlf) * (NV * NFP) + kn;
+#pragma unroll
+                    for (int v = 0; v < NV; v++) cp_async8(dst + v * NFP, src + v * NFP);
+                }
             }
         }
     }
@@ -735,9 +758,15 @@ stage_kernel(const __grid_constant__ KParams P)
                 int k, ii;
                 node_line<ND, NP>(node, d, k, ii);
                 const double gl = sGl[ii], gr = sGr[ii];
+                // collocated nodes: the lifting weights vanish away from the two end nodes
+                if (gl != 0.0) {
 #pragma unroll
-                for (int v = 0; v < NV; v++)
-                    acc[v] -= gl * sF[((2 * d) * NV + v) * NFP + k] + gr * sF[((2 * d + 1) * NV + v) * NFP + k];
+                    for (int v = 0; v < NV; v++) acc[v] -= gl * sF[((2 * d) * NV + v) * NFP + k];
+                }
+                if (gr != 0.0) {
+#pragma unroll
+                    for (int v = 0; v < NV; v++) acc[v] -= gr * sF[((2 * d + 1) * NV + v) * NFP + k];
+                }
             }
             // mass matrix: dQ / jac (Diagonal ldiv!, MultielementDiscontinuous.jl:132-137)
             const double rjac = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof));
@@ -758,14 +787,16 @@ stage_kernel(const __grid_constant__ KParams P)
                 }
                 // traces of the new state for the next stage (collocated nodes: the boundary
                 // node values; Gauss nodes are handled by emit_traces_kernel)
+#ifdef FLOU_EXPERIMENT_SKIP_TRACE_WRITE
+                if (P.colloc && P.elem_count < 0) {
+#else
                 if (P.colloc) {
-#pragma unroll
-                    for (int d = 0; d < ND; d++) {
+#endif
+                    {
                         int k, ii;
-                        node_line<ND, NP>(node, d, k, ii);
+                        node_line<ND, NP>(node, 0, k, ii);
                         if (ii == 0 || ii == NP - 1) {
-                            const int lf = 2 * d + (ii == 0 ? 0 : 1);
-                            double *dst = P.tr_out + ((int64_t)e * NFACES + lf) * (NV * NFP) + k;
+                            double *dst = P.tr_out + ((int64_t)e * 2 + (ii == 0 ? 0 : 1)) * (NV * NFP) + k;
 #pragma unroll
                             for (int v = 0; v < NV; v++) dst[v * NFP] = acc[v];
                         }
@@ -779,10 +810,10 @@ stage_kernel(const __grid_constant__ KParams P)
 // ------------------------------------------------------------------ halo trace emit
 // Face traces of a state, in the owning side's face-dof order: out[(slot*NV + v)*NFP + k].
 // list[slot] = local element * 2nd + local face (partition-boundary faces packed for
-// ncclSend), or list == nullptr for every (element, face): the full trace array.
+// ncclSend), or list == nullptr for the first `faces_per_elem` faces of every element.
 template <int ND, int NP, int NV>
 __global__ void emit_traces_kernel(const double *__restrict__ u, int64_t ndof,
-                                   const int *__restrict__ list, int nslots, int colloc,
+                                   const int *__restrict__ list, int nslots, int faces_per_elem, int colloc,
                                    const double *__restrict__ lm, const double *__restrict__ lp,
                                    double *__restrict__ out)
 {
@@ -790,7 +821,8 @@ __global__ void emit_traces_kernel(const double *__restrict__ u, int64_t ndof,
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)nslots * NFP) return;
     const int slot = (int)(t / NFP), k = (int)(t - (int64_t)slot * NFP);
-    const int ef = list ? list[slot] : slot;
+    // no list: the first `faces_per_elem` local faces of every element (2 = the x-faces)
+    const int ef = list ? list[slot] : (slot / faces_per_elem) * NFACES + (slot % faces_per_elem);
     const int e = ef / NFACES, lf = ef - e * NFACES;
     const int d = lf >> 1, side = lf & 1;
     int base, stride;

@@ -1,0 +1,181 @@
+# FlouB200.jl -- drop-in shim: Flou.jl's own objects in, B200 kernels underneath.
+#
+# NOT runnable in the build container (no `julia` there); it is the binding a Flou
+# maintainer adds next to the package (see INTEGRATION.md).  Everything above the `ccall`s is
+# plain Flou API: the mesh, standard region, operators and boundary conditions are built by
+# Flou's own constructors and only their arrays cross the C ABI (include/flou_b200.h).
+#
+#   rhs!(dQ, Q, p::EquationConfig{<:B200Disc}, t)      replaces Hyperbolic.jl:31-69
+#   timeintegrate(Q0, ::B200Disc, eq, solver, tf; dt)  replaces FlouTime.jl:34-54 for the
+#                                                      LowStorageRK2N solvers (ORK256,
+#                                                      CarpenterKennedy2N54)
+module FlouB200
+
+using Flou
+using Flou.FlouCommon: AbstractSpatialDiscretization, EquationConfig, CartesianMesh,
+    LinearAdvection, EulerEquation, nvariables, spatialdim, nelements, nfaces
+using Flou.FlouSpatial: MultielementDisc, StrongDivOperator, SplitDivOperator, StdAverage, LxF,
+    ChandrasekharAverage, ScalarDissipation, MatrixDissipation, EulerInflowBC, EulerOutflowBC,
+    EulerSlipBC, GenericBC, ndofs
+import Flou.FlouCommon: rhs!
+import Flou.FlouTime: timeintegrate
+using OrdinaryDiffEq: ORK256, CarpenterKennedy2N54
+
+const lib = get(ENV, "FLOU_B200_LIB", "libflou_b200.so")
+
+# mirrors `flou_b200_desc` field by field (include/flou_b200.h)
+struct Desc
+    struct_size::Int32; nd::Int32; nv::Int32; np::Int32
+    equation::Int32; divop::Int32; tpflux::Int32; numflux::Int32; numflux_avg::Int32
+    geometry::Int32
+    intensity::Float64; gamma::Float64
+    a::NTuple{3,Float64}; dx::NTuple{3,Float64}
+    ne::Int64; nf::Int64
+    faceinds::Ptr{Int64}; facepos::Ptr{Int64}; eleminds::Ptr{Int64}; elempos::Ptr{Int64}
+    orientation::Ptr{UInt8}
+    D::Ptr{Float64}; Ds::Ptr{Float64}; Dsharp::Ptr{Float64}
+    lminus::Ptr{Float64}; lplus::Ptr{Float64}; dgminus::Ptr{Float64}; dgplus::Ptr{Float64}
+    jac::Ptr{Float64}; metric::Ptr{Float64}; fjac::Ptr{Float64}; frames::Ptr{Float64}
+    nbound::Int32
+    bc_kind::Ptr{Int32}; bc_offsets::Ptr{Int64}; bc_faces::Ptr{Int64}
+    bc_state::Ptr{Float64}; bc_table::Ptr{Float64}
+    elem_begin::Int64; elem_end::Int64
+    rank::Int32; nranks::Int32; part_offsets::Ptr{Int64}
+    device::Int32; flags::Int32
+end
+
+fluxkind(::StdAverage) = Int32(0)
+fluxkind(::LxF) = Int32(1)
+fluxkind(::ChandrasekharAverage) = Int32(2)
+fluxkind(::ScalarDissipation) = Int32(3)
+fluxkind(::MatrixDissipation) = Int32(4)
+avgkind(f) = hasproperty(f, :avg) ? fluxkind(f.avg) : Int32(0)
+intensity(f) = hasproperty(f, :intensity) ? Float64(f.intensity) : 0.0
+
+bckind(::EulerInflowBC) = Int32(0)
+bckind(::EulerOutflowBC) = Int32(1)
+bckind(::EulerSlipBC) = Int32(2)
+bckind(::GenericBC) = Int32(3)      # tabulated at the boundary-face nodes below
+
+function check(rc)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:flou_b200_last_error, lib), Cstring, ()))
+    rc == 1 || rc == 5 ? throw(ArgumentError(msg)) :
+    rc == 4 ? throw(DomainError(NaN, msg)) : error("flou_b200 error $rc: $msg")
+end
+
+"""
+    B200Disc(disc::MultielementDisc, equation; device=0)
+
+Wraps a discretisation built by Flou itself and uploads its tables to the GPU.
+"""
+mutable struct B200Disc{ND,RT,D<:MultielementDisc{ND,RT}} <: AbstractSpatialDiscretization{ND,RT}
+    disc::D
+    handle::Ptr{Cvoid}
+end
+
+function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,RT}
+    RT === Float64 || throw(ArgumentError("the B200 path is fp64 only"))
+    (; mesh, std, geometry, bcs) = disc
+    op = disc.operators[1]
+    nv = nvariables(equation)
+    cart = mesh isa CartesianMesh
+    # connectivity exactly as Flou stores it (1-based, Mesh.jl:26-150)
+    faceinds = Int64.(mesh.elements.faceinds); facepos = Int64.(mesh.elements.facepos)
+    eleminds = Int64.(mesh.faces.eleminds);    elempos = Int64.(mesh.faces.elempos)
+    orientation = mesh.faces.orientation
+    # operators: Julia matrices are column-major, which is what the ABI expects
+    D, Ds, Dsharp = std.D, std.Ds, std.D♯
+    lm, lp = std.l; dgm, dgp = std.∂g
+    # general geometry tables (unused for CartesianMesh)
+    jac = cart ? Float64[] : geometry.elements.jac
+    metric = cart ? Float64[] : collect(reinterpret(Float64, geometry.elements.metric))
+    fjac = cart ? Float64[] : geometry.faces.jac
+    frames = cart ? Float64[] : collect(reinterpret(Float64, geometry.faces.frames))
+    # boundary conditions in mesh.bdfaces order (disc.bcs is already ordered by bdmap)
+    kinds = Int32[bckind(bc) for bc in bcs]
+    offsets = Int64[0; cumsum(length.(mesh.bdfaces))]
+    bcfaces = Int64.(reduce(vcat, mesh.bdfaces; init=Int[]))
+    nfp = Flou.FlouSpatial.ndofs(std.face)
+    state = zeros(Float64, nv, max(length(bcs), 1))          # row per boundary (C order)
+    table = zeros(Float64, nv, max(length(bcfaces), 1) * nfp)
+    for (ib, bc) in enumerate(bcs)
+        if bc isa EulerInflowBC
+            state[:, ib] .= bc.Qext
+        elseif bc isa GenericBC
+            for m in (offsets[ib] + 1):offsets[ib + 1], i in 1:nfp
+                f = bcfaces[m]
+                x = geometry.faces[f].coords[i]
+                # only position-dependent closures are supported on the device
+                table[:, (m - 1) * nfp + i] .= bc.Qext(nothing, x, nothing, 0.0, equation)
+            end
+        end
+    end
+    a = equation isa LinearAdvection ? ntuple(i -> i <= ND ? Float64(equation.a[i]) : 0.0, 3) : (0.0, 0.0, 0.0)
+    dx = cart ? ntuple(i -> i <= ND ? Float64(mesh.Δx[i]) : 0.0, 3) : (0.0, 0.0, 0.0)
+    ne = nelements(mesh)
+    handle = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve faceinds facepos eleminds elempos orientation D Ds Dsharp lm lp dgm dgp jac metric fjac frames kinds offsets bcfaces state table begin
+        desc = Desc(
+            Int32(sizeof(Desc)), Int32(ND), Int32(nv), Int32(size(D, 1)),
+            equation isa EulerEquation ? Int32(1) : Int32(0),
+            op isa SplitDivOperator ? Int32(1) : Int32(0),
+            op isa SplitDivOperator ? fluxkind(op.tpflux) : Int32(0),
+            fluxkind(op.numflux), avgkind(op.numflux), cart ? Int32(0) : Int32(1),
+            intensity(op.numflux), equation isa EulerEquation ? Float64(equation.γ) : 0.0, a, dx,
+            Int64(ne), Int64(nfaces(mesh)),
+            pointer(faceinds), pointer(facepos), pointer(eleminds), pointer(elempos), pointer(orientation),
+            pointer(D), pointer(Ds), pointer(Dsharp), pointer(lm), pointer(lp), pointer(dgm), pointer(dgp),
+            cart ? C_NULL : pointer(jac), cart ? C_NULL : pointer(metric),
+            cart ? C_NULL : pointer(fjac), cart ? C_NULL : pointer(frames),
+            Int32(length(bcs)), pointer(kinds), pointer(offsets), pointer(bcfaces),
+            pointer(state), pointer(table),
+            Int64(0), Int64(ne), Int32(0), Int32(1), C_NULL, Int32(device), Int32(0))
+        check(ccall((:flou_b200_create, lib), Int32, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle))
+    end
+    b = B200Disc{ND,RT,typeof(disc)}(disc, handle[])
+    finalizer(x -> ccall((:flou_b200_destroy, lib), Int32, (Ptr{Cvoid},), x.handle), b)
+    return b
+end
+
+# rhs!(dQ, Q, p, t): host in, host out -- what OrdinaryDiffEq calls as f(du, u, p, t)
+function rhs!(dQ::Matrix{Float64}, Q::Matrix{Float64}, p::EquationConfig{<:B200Disc}, time::Real)
+    check(ccall((:flou_b200_rhs, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
+                p.disc.handle, Q, dQ, Float64(time)))
+    return nothing
+end
+
+# 2N tableaus straight from the OrdinaryDiffEq solver objects' caches
+function tableau(solver::Union{ORK256,CarpenterKennedy2N54})
+    tab = OrdinaryDiffEq.alg_cache(solver, zeros(1), zeros(1), Float64, Float64, Float64,
+                                   zeros(1), zeros(1), nothing, 0.0, 0.0, 0.0, nothing, false,
+                                   Val(true)).tab
+    A = Float64[0.0; collect(tab.A2end)]
+    B = Float64[tab.B1; collect(tab.B2end)]
+    c = Float64[0.0; collect(tab.c2end)]
+    return A, B, c
+end
+
+# timeintegrate(Q0, disc, equation, solver, tfinal; adaptive=false, dt, alias_u0=true)
+function timeintegrate(Q0::Matrix{Float64}, disc::B200Disc, equation,
+                       solver::Union{ORK256,CarpenterKennedy2N54}, tfinal;
+                       dt, adaptive=false, alias_u0=true, kwargs...)
+    adaptive && throw(ArgumentError("adaptive=true is not supported on the B200 path"))
+    A, B, c = tableau(solver)
+    Q = alias_u0 ? Q0 : copy(Q0)
+    nsteps = round(Int64, tfinal / dt)
+    exetime = @elapsed begin
+        rc = ccall((:flou_b200_timeintegrate, lib), Int32,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                    Float64, Float64, Int64),
+                   disc.handle, Q, Int32(length(B)), A, B, c, Float64(dt), 0.0, nsteps)
+    end
+    if rc == 4                       # FLOU_B200_EDOMAIN, cf. FlouTime.jl:39-51
+        @error "Simulation crashed!"
+        return (nothing, exetime)
+    end
+    check(rc)
+    return ((u=[Q], t=[nsteps * dt]), exetime)
+end
+
+end # module
