@@ -44,6 +44,9 @@ WORKLOADS = {
                  desc="3D Euler Taylor-Green vortex 128^3 p=4 GLL SplitDiv(Chandrasekhar)+MatrixDissipation ORK256"),
     "cfg4s": dict(nd=3, n=(64, 64, 64), np=5, eq="euler", dt=2e-4,
                   desc="3D Euler Taylor-Green vortex 64^3 p=4 GLL SplitDiv(Chandrasekhar)+MatrixDissipation ORK256"),
+    "cfg5": dict(nd=2, n=(73 * 64,), np=6, eq="euler", dt=2e-5, unstructured=8,
+                 desc="2D Euler on the reference's 2D_cylinder quad mesh (73 quads) refined 8x8, p=5 GLL, "
+                      "SplitDiv(Chandrasekhar)+MatrixDissipation, slip walls + inflow/outflow, ORK256"),
 }
 GAMMA = 1.4
 
@@ -168,6 +171,7 @@ def cpu_sample_case(w):
     from common import Case
     nd = w["nd"]
     n = {2: (48, 48), 3: (16, 16, 16)}[nd] if w["eq"] == "euler" else (32, 32)
+    # (config 5: the CPU sample is the same operator/order on a Cartesian quad mesh)
     if w["eq"] == "adv":
         return Case(nd, n, w["np"], nodes="GLL", eq="adv", op="strong", nf="lxf", avg="std",
                     a=(2.0, -1.0, 0.0)), n
@@ -265,9 +269,21 @@ def main():
         gloo = dist.new_group(backend="gloo")
 
     nd = w["nd"]
-    start, finish = domain(w)
-    mesh = F.CartesianMesh(nd, start, finish, w["n"])
-    mesh.apply_periodicBCs(*[(str(2 * d + 1), str(2 * d + 2)) for d in range(nd)])
+    bcs = {}
+    if w.get("unstructured"):
+        g = np.load(os.path.join(ROOT, "tests", "golden", "cylinder_p5.npz"))
+        groups = [(str(n), [int(v) for v in str(e).split(",")])
+                  for n, e in zip(g["group_names"], g["group_entities"])]
+        raw = F.RawMesh(g["nodes"], g["quads"], g["lines"], g["line_tags"], g["line_entity"], groups)
+        mesh = F.UnstructuredMesh(2, raw, refinement=w["unstructured"])
+        Qinf = F.vars_prim2cons((1.0, 0.5, 0.0, 1.0), F.EulerEquation(2, GAMMA))
+        for name in mesh.bdnames:
+            bcs[name] = (F.EulerInflowBC(Qinf) if name == "Left" else
+                         F.EulerOutflowBC() if name == "Right" else F.EulerSlipBC())
+    else:
+        start, finish = domain(w)
+        mesh = F.CartesianMesh(nd, start, finish, w["n"])
+        mesh.apply_periodicBCs(*[(str(2 * d + 1), str(2 * d + 2)) for d in range(nd)])
     basis = F.LagrangeBasis("GLL", w["np"])
     if w["eq"] == "adv":
         eq = F.LinearAdvection(2.0, -1.0)
@@ -277,7 +293,7 @@ def main():
         op = F.SplitDivOperator(F.ChandrasekharAverage(),
                                 F.MatrixDissipation(F.ChandrasekharAverage(), 1.0))
     std = {2: F.StdQuad, 3: F.StdHex}[nd](basis, F.DGSEMrec(basis), eq.nv)
-    disc = F.MultielementDisc(mesh, std, eq, op, {}, rank=rank, nranks=world, device=local_rank)
+    disc = F.MultielementDisc(mesh, std, eq, op, bcs, rank=rank, nranks=world, device=local_rank)
     if world > 1:
         ids = [F.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0, group=gloo)
@@ -289,6 +305,11 @@ def main():
     chunk = 1 << 15
     for e0 in range(0, verts.shape[0], chunk):
         x = G.element_coords(verts[e0:e0 + chunk], std.xi)
+        if w.get("unstructured"):      # uniform farfield + deterministic smooth perturbation
+            q0 = np.tile(Qinf, (x.shape[0], 1))
+            q0[:, 0] *= 1 + 0.02 * np.sin(3 * x[:, 0]) * np.cos(2 * x[:, 1])
+            Q[e0 * npts:e0 * npts + x.shape[0], :] = q0
+            continue
         Q[e0 * npts:(e0 + verts[e0:e0 + chunk].shape[0]) * npts, :] = initial_condition(x, w)
     del verts
     pinned = False

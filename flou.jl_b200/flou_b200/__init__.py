@@ -11,6 +11,7 @@ from .equations import (ChandrasekharAverage, EulerEquation, EulerInflowBC, Eule
                         ScalarDissipation, SplitDivOperator, StdAverage, StrongDivOperator,
                         gaussian_bump, normal_shockwave, nvariables, soundvelocity, spatialdim,
                         vars_prim2cons)
+from .gmshmesh import RawMesh, UnstructuredMesh, read_msh, refine, write_msh
 from .mesh import CartesianMesh, apply_periodicBCs, partition_offsets
 from .stdregions import DGSEMrec, LagrangeBasis, StdHex, StdQuad, StdSegment
 from .time import CarpenterKennedy2N54, ORK256, Solution, advance, timeintegrate

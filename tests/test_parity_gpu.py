@@ -185,3 +185,20 @@ def test_domain_error_is_reported(gpu):
     sol, _ = F.timeintegrate(Q, disc, eq, F.ORK256(), 1e-3, dt=1e-3)
     assert sol is None                  # FlouTime.jl:39-51 returns nothing after "crashed"
     disc.close()
+
+
+@pytest.mark.gpu
+def test_golden_cart3d_fixture(gpu):
+    """Committed golden vectors (tests/golden/make_golden.py): RHS and state after 5 steps."""
+    import os
+    import flou_b200 as F
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cart3d_p3.npz"))
+    disc, eq = Case(3, (3, 3, 3), 4).product()
+    Q = np.asfortranarray(g["Q"])
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert relerr(dQ, g["dQ"]) <= RHS_TOL
+    u = Q.copy(order="F")
+    sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), 5e-3, dt=1e-3)
+    assert relerr(sol.u[-1], g["u5"]) <= 1e-10
+    disc.close()
