@@ -3,6 +3,9 @@
 // so the instances build in parallel.  dispatch.cu stitches the per-pair tables together.
 #include <cstdlib>
 #include "launch.h"
+#ifdef FLOU_WS      // experimental warp-specialised persistent variant (slower, see profiles/)
+#include "stage_kernel_ws.cuh"
+#endif
 
 #ifndef FLOU_GRID_MULT_DEFAULT
 #define FLOU_GRID_MULT_DEFAULT 1
@@ -56,10 +59,57 @@ static cudaError_t do_launch(const KParams &P, cudaStream_t s)
     return cudaGetLastError();
 }
 
+#ifdef FLOU_WS
+// ---- warp-specialised persistent kernel -------------------------------------------------
+template <class C>
+static int ws_resident_ctas()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_kernel_ws<C>, WSCfg<C>::THREADS,
+                                                      WSCfg<C>::SMEM_BYTES);
+        n = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    }
+    return n;
+}
+
+template <class C>
+static cudaError_t ws_prepare()
+{
+    cudaError_t e = cudaFuncSetAttribute(stage_kernel_ws<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)WSCfg<C>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(stage_kernel_ws<C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    ws_resident_ctas<C>();
+    return cudaSuccess;
+}
+
+template <class C>
+static cudaError_t ws_launch(const KParams &P, cudaStream_t s)
+{
+    if (P.elem_count <= 0) return cudaSuccess;
+    const int ngroups = (P.elem_count + C::EPB - 1) / C::EPB;
+    const int resident = ws_resident_ctas<C>();
+    const int grid = ngroups < resident ? ngroups : resident;
+    stage_kernel_ws<C><<<grid, WSCfg<C>::THREADS, WSCfg<C>::SMEM_BYTES, s>>>(P);
+    return cudaGetLastError();
+}
+#endif
+
 template <class C>
 static constexpr StageLauncher make()
 {
+#ifdef FLOU_WS
+    return StageLauncher{&ws_launch<C>, &ws_prepare<C>, &ws_resident_ctas<C>, C::EPB, WSCfg<C>::THREADS,
+                         WSCfg<C>::SMEM_BYTES};
+#else
     return StageLauncher{&do_launch<C>, &do_prepare<C>, &resident_ctas<C>, C::EPB, C::THREADS, C::SMEM_BYTES};
+#endif
 }
 
 #define ND FLOU_ND

@@ -22,6 +22,9 @@
 #include <stdint.h>
 #include "physics.cuh"
 
+#ifndef FLOU_L2_PREFETCH
+#define FLOU_L2_PREFETCH 592   // groups ahead (= resident CTAs on a B200: 4 per SM x 148); 0 disables
+#endif
 #ifndef FLOU_TPB
 #define FLOU_TPB 128      // target threads per CTA (measured: 128 beats 256 on B200)
 #endif
@@ -434,6 +437,21 @@ stage_kernel(const __grid_constant__ KParams P)
         for (int v = 0; v < NV; v++) cp_async8(sT + v * NPTS + node, P.tmp + dof + ndof * v);
     }
     cp_async_commit();
+#if FLOU_L2_PREFETCH > 0
+    // warm L2 for the group that will occupy this SM slot one wave later: its first action is
+    // a dependent load of its own state, which then costs an L2 hit instead of a DRAM access
+    if (active && (node & 15) == 0 && P.elem_list == nullptr) {
+        const int idx = (g + FLOU_L2_PREFETCH) * EPB + el;
+        if (idx < P.elem_count) {
+            const int64_t pd = (int64_t)(P.elem_first + idx) * NPTS + node;
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.u_in + pd + ndof * v));
+                if (need_tmp) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.tmp + pd + ndof * v));
+            }
+        }
+    }
+#endif
 
     {
         // ---------------- phase 1: node primitives, contravariant fluxes
