@@ -138,6 +138,19 @@ class ClockSampler:
             os.unlink(self.path)
         except Exception:
             pass
+        if not sm:      # region shorter than one sampling period: one query right after it
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                   timeout=20).stdout
+                f = [x.strip() for x in o.strip().split(",")]
+                sm.append(float(f[1])); mx.append(float(f[2]))
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+                out["note"] = "timed region shorter than the sampling period; sampled right after it"
+            except Exception:
+                pass
         if sm:
             out["sm_mhz"] = float(np.median(sm))
             out["sm_max_mhz"] = float(max(mx))
@@ -385,6 +398,8 @@ def main():
     # ---- roofline of the dominant (only) kernel: the fused stage kernel
     peak, peak_src = hbm_peak()
     bytes_per_dof = 32 * eq.nv                      # read u,tmp + write u,tmp
+    if w.get("unstructured"):
+        bytes_per_dof += 8 * (nd * nd + 1)          # per-node metric + jac (config 5: 168 B)
     ndof_local = disc.ndofs
     stage_launches = nstages * args.steps
     achieved = ndof_local * bytes_per_dof / (ms_dev * 1e-3 / stage_launches) / 1e9

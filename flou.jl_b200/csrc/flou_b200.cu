@@ -276,13 +276,14 @@ struct flou_b200_handle {
     int *send_list = nullptr;          // [slot] = local element*2nd + local face
     int *interior_list = nullptr, *boundary_list = nullptr;
     int n_interior = 0, n_boundary = 0;
+    int interior_first = -1;          // >= 0: the interior elements are the contiguous range starting here
     ncclComm_t comm = nullptr;
     // streams / events
     cudaStream_t stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_emit = nullptr, ev_recv = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     // CUDA graph of two consecutive RK steps (returns to the same ping-pong buffer)
-    cudaGraphExec_t graph = nullptr;
-    std::vector<double> graph_key;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};      // one per starting ping-pong buffer
+    std::vector<double> graph_key[2];
     int64_t launches = 0;
     int64_t graph_launches_per_replay = 0;
 };
@@ -347,10 +348,12 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
     }
     NCCL_TRY(g_nccl.GroupEnd());
     CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
-    P.elem_first = 0;
-    P.elem_list = h->interior_list;
+    // interior elements: a contiguous range on slab partitions (no indirection), else a list
+    P.elem_first = h->interior_first >= 0 ? h->interior_first : 0;
+    P.elem_list = h->interior_first >= 0 ? nullptr : h->interior_list;
     P.elem_count = h->n_interior;
     CUDA_TRY(h->stage->launch(P, h->stream));
+    P.elem_first = 0;
     CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
     P.elem_list = h->boundary_list;
     P.elem_count = h->n_boundary;
@@ -375,9 +378,11 @@ int32_t run_steps_direct(flou_b200_handle *h, int nstages, const double *A, cons
 
 void destroy_graph(flou_b200_handle *h)
 {
-    if (h->graph) cudaGraphExecDestroy(h->graph);
-    h->graph = nullptr;
-    h->graph_key.clear();
+    for (int i = 0; i < 2; i++) {
+        if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
+        h->graph[i] = nullptr;
+        h->graph_key[i].clear();
+    }
 }
 
 }  // namespace
@@ -470,6 +475,9 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     h->nghost = (int64_t)pl.ghosts.size();
     h->n_interior = (int)pl.interior.size();
     h->n_boundary = (int)pl.boundary.size();
+    if (!pl.interior.empty() &&
+        pl.interior.back() - pl.interior.front() + 1 == (int)pl.interior.size())
+        h->interior_first = pl.interior.front();
     const std::vector<Conn> &conn = pl.conn;
     const std::vector<int> &send_list = pl.send_list, &interior = pl.interior,
                            &boundary = pl.boundary, &faceid = pl.faceid;
@@ -718,11 +726,13 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
     }
     if (use_graph) {
         std::vector<double> key;
-        key.push_back((double)nstages); key.push_back(dt); key.push_back((double)h->cur);
+        key.push_back((double)nstages); key.push_back(dt);
         key.insert(key.end(), A, A + nstages);
         key.insert(key.end(), B, B + nstages);
-        if (!h->graph || key != h->graph_key) {
-            destroy_graph(h);
+        const int gi = h->cur;           // two steps bring u back to the buffer they started in
+        if (!h->graph[gi] || key != h->graph_key[gi]) {
+            if (h->graph[gi]) cudaGraphExecDestroy(h->graph[gi]);
+            h->graph[gi] = nullptr;
             cudaGraph_t g = nullptr;
             const int cur0 = h->cur;
             const int64_t l0 = h->launches;
@@ -736,13 +746,13 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
             h->launches = l0;
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             CUDA_TRY(e);
-            e = cudaGraphInstantiate(&h->graph, g, 0);
+            e = cudaGraphInstantiate(&h->graph[gi], g, 0);
             cudaGraphDestroy(g);
             CUDA_TRY(e);
-            h->graph_key = key;
+            h->graph_key[gi] = key;
         }
         while (nsteps - done >= 2) {
-            CUDA_TRY(cudaGraphLaunch(h->graph, h->stream));
+            CUDA_TRY(cudaGraphLaunch(h->graph[gi], h->stream));
             h->launches += h->graph_launches_per_replay;
             done += 2;
             h->traces_valid = h->colloc;

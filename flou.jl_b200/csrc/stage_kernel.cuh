@@ -440,10 +440,10 @@ stage_kernel(const __grid_constant__ KParams P)
 #if FLOU_L2_PREFETCH > 0
     // warm L2 for the group that will occupy this SM slot one wave later: its first action is
     // a dependent load of its own state, which then costs an L2 hit instead of a DRAM access
-    if (active && (node & 15) == 0 && P.elem_list == nullptr) {
+    if (active && (node & 15) == 0) {
         const int idx = (g + FLOU_L2_PREFETCH) * EPB + el;
         if (idx < P.elem_count) {
-            const int64_t pd = (int64_t)(P.elem_first + idx) * NPTS + node;
+            const int64_t pd = (int64_t)elem_of(idx) * NPTS + node;
 #pragma unroll
             for (int v = 0; v < NV; v++) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(P.u_in + pd + ndof * v));
