@@ -113,7 +113,11 @@ struct Plan {
     std::vector<Ghost> ghosts;
     std::vector<Peer> peers;
     std::vector<int> send_list, interior, boundary, faceid;
-    std::vector<int64_t> slot_face;
+    std::vector<int64_t> slot_face;       // local face slot -> global face (0-based)
+    // two-kernel path: one record per local face slot (faces with a ghost side last)
+    std::vector<FaceRec> faces;
+    std::vector<int2> econn;              // [le*2nd + lf] = {slot, master | orient << 1}
+    int n_faces_local_only = 0;           // slots [0, n) touch no ghost
 };
 
 int32_t build_plan(const flou_b200_desc *d, bool cart, Plan &pl)
@@ -166,7 +170,7 @@ int32_t build_plan(const flou_b200_desc *d, bool cart, Plan &pl)
                 pl.ghosts.push_back({owner_of(gn), gf, (int)le, lf});
             }
             pl.conn[(size_t)le * NF + lf] = c;
-            if (!cart) {
+            {
                 auto it = face_slot.find(gf);
                 if (it == face_slot.end()) {
                     it = face_slot.emplace(gf, (int)pl.slot_face.size()).first;
@@ -192,6 +196,48 @@ int32_t build_plan(const flou_b200_desc *d, bool cart, Plan &pl)
     }
     for (int64_t le = 0; le < pl.ne_local; le++)
         (is_boundary_elem[le] ? pl.boundary : pl.interior).push_back((int)le);
+
+    // ---- face table of the two-kernel path: slots without a ghost side first
+    (void)cart;
+    const int nslots = (int)pl.slot_face.size();
+    std::vector<char> has_ghost((size_t)nslots, 0);
+    for (const Ghost &g : pl.ghosts) has_ghost[pl.faceid[(size_t)g.le * NF + g.lf]] = 1;
+    std::vector<int> newslot((size_t)nslots);
+    int n0 = 0;
+    for (int sidx = 0; sidx < nslots; sidx++) if (!has_ghost[sidx]) newslot[sidx] = n0++;
+    pl.n_faces_local_only = n0;
+    for (int sidx = 0; sidx < nslots; sidx++) if (has_ghost[sidx]) newslot[sidx] = n0++;
+    {
+        std::vector<int64_t> sf((size_t)nslots);
+        for (int sidx = 0; sidx < nslots; sidx++) sf[newslot[sidx]] = pl.slot_face[sidx];
+        pl.slot_face.swap(sf);
+        for (int &f : pl.faceid) f = newslot[f];
+    }
+    pl.faces.assign((size_t)nslots, FaceRec{-1, -1, 0, 0});
+    pl.econn.assign((size_t)pl.ne_local * NF, int2{0, 0});
+    std::vector<int> lfm((size_t)nslots, 0), lfs((size_t)nslots, 0), mk((size_t)nslots, 0),
+        sk((size_t)nslots, 0), bcidx((size_t)nslots, 0), ori((size_t)nslots, 0);
+    for (int64_t le = 0; le < pl.ne_local; le++)
+        for (int lf = 0; lf < NF; lf++) {
+            const Conn &c = pl.conn[(size_t)le * NF + lf];
+            const int slot = pl.faceid[(size_t)le * NF + lf];
+            const int kind = (c.info >> 7) & 3, nlf = c.info & 7, orient = (c.info >> 3) & 7;
+            const int master = (c.info >> 6) & 1;
+            FaceRec &r = pl.faces[slot];
+            pl.econn[(size_t)le * NF + lf] = int2{slot, master | (orient << 1)};
+            ori[slot] = orient;
+            if (master) { r.em = (int)le; lfm[slot] = lf; mk[slot] = 0; }
+            else { r.es = (int)le; lfs[slot] = lf; sk[slot] = 0; }
+            if (kind == FK_BOUNDARY) { r.es = c.nbr; sk[slot] = 2; bcidx[slot] = c.info >> 9; }
+            else if (kind == FK_GHOST) {
+                if (master) { r.es = c.nbr; lfs[slot] = nlf; sk[slot] = 1; }
+                else { r.em = c.nbr; lfm[slot] = nlf; mk[slot] = 1; }
+            } else {
+                if (master) lfs[slot] = nlf; else lfm[slot] = nlf;
+            }
+        }
+    for (int sidx = 0; sidx < nslots; sidx++)
+        pl.faces[sidx].info = facerec_pack(lfm[sidx], lfs[sidx], ori[sidx], mk[sidx], sk[sidx], bcidx[sidx]);
     return FLOU_B200_OK;
 }
 
@@ -286,6 +332,12 @@ struct flou_b200_handle {
     std::vector<double> graph_key[2];
     int64_t launches = 0;
     int64_t graph_launches_per_replay = 0;
+    // two-kernel path
+    bool split_faces = true;
+    FaceRec *faces = nullptr;
+    int2 *econn = nullptr;
+    double *Fn = nullptr;
+    int n_faces = 0, n_faces_local_only = 0;
 };
 
 namespace {
@@ -325,8 +377,17 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
         P.elem_first = 0;
         P.elem_count = (int)h->ne_local;
         P.elem_list = nullptr;
-        CUDA_TRY(h->stage->launch(P, h->stream));
-        h->launches += 1;
+        if (h->split_faces) {
+            // two-kernel stage: every face flux once, then volume + lift + RK update
+            P.face_first = 0;
+            P.face_count = h->n_faces;
+            CUDA_TRY(h->stage->launch_faces(P, h->stream));
+            CUDA_TRY(h->stage->launch_elements(P, h->stream));
+            h->launches += 2;
+        } else {
+            CUDA_TRY(h->stage->launch(P, h->stream));
+            h->launches += 1;
+        }
         if (mode != MODE_RHS) h->traces_valid = out_traces;
         return FLOU_B200_OK;
     }
@@ -348,6 +409,23 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
     }
     NCCL_TRY(g_nccl.GroupEnd());
     CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
+    if (h->split_faces) {
+        // faces without a ghost side while the halo is in flight, the rest after the receive
+        P.face_first = 0;
+        P.face_count = h->n_faces_local_only;
+        CUDA_TRY(h->stage->launch_faces(P, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
+        P.face_first = h->n_faces_local_only;
+        P.face_count = h->n_faces - h->n_faces_local_only;
+        CUDA_TRY(h->stage->launch_faces(P, h->stream));
+        P.elem_first = 0;
+        P.elem_count = (int)h->ne_local;
+        P.elem_list = nullptr;
+        CUDA_TRY(h->stage->launch_elements(P, h->stream));
+        h->launches += 3;
+        if (mode != MODE_RHS) h->traces_valid = out_traces;
+        return FLOU_B200_OK;
+    }
     // interior elements: a contiguous range on slab partitions (no indirection), else a list
     P.elem_first = h->interior_first >= 0 ? h->interior_first : 0;
     P.elem_list = h->interior_first >= 0 ? nullptr : h->interior_list;
@@ -537,6 +615,13 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     } while (0)
 
     H_TRY(upload(&h->conn, conn));
+    h->split_faces = !(d->flags & FLOU_B200_FLAG_FUSED);
+    h->n_faces = (int)pl.faces.size();
+    h->n_faces_local_only = pl.n_faces_local_only;
+    H_TRY(upload(&h->faces, pl.faces));
+    H_TRY(upload(&h->econn, pl.econn));
+    if (h->split_faces)
+        H_TRY(cudaMalloc((void **)&h->Fn, sizeof(double) * std::max<size_t>((size_t)h->n_faces * h->nfp * h->nv, 1)));
     if (!cart) {
         // re-lay geometry as plane-major SoA restricted to owned elements / touched faces
         const int64_t ndof = h->ndof, npts = h->npts, nfp = h->nfp;
@@ -617,6 +702,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
 #undef H_TRY
     P.jac = h->jac; P.metric = h->metric; P.fjac = h->fjac; P.frames = h->frames;
     P.faceid = h->faceid; P.conn = h->conn;
+    P.faces = h->faces; P.econn = h->econn; P.Fn = h->Fn; P.split_faces = h->split_faces ? 1 : 0;
     P.bc_kind = h->bc_kind; P.bc_state = h->bc_state; P.bc_table = h->bc_table;
     P.ghost = h->ghost;
     P.ndof = h->ndof;
@@ -634,7 +720,7 @@ int32_t flou_b200_destroy(flou_b200_handle *h)
     destroy_graph(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void *ptrs[] = {h->u[0], h->u[1], h->tr[0], h->tr[1], h->tr_all, h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
-                    h->frames, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
+                    h->frames, h->faces, h->econn, h->Fn, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
                     h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ev_emit) cudaEventDestroy(h->ev_emit);

@@ -3,6 +3,7 @@
 // so the instances build in parallel.  dispatch.cu stitches the per-pair tables together.
 #include <cstdlib>
 #include "launch.h"
+#include "face_kernel.cuh"
 #ifdef FLOU_WS      // experimental warp-specialised persistent variant (slower, see profiles/)
 #include "stage_kernel_ws.cuh"
 #endif
@@ -23,11 +24,17 @@ static int resident_ctas();
 template <class C>
 static cudaError_t do_prepare()
 {
-    cudaError_t e = cudaFuncSetAttribute(stage_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(stage_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(stage_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     // ask for the largest shared-memory carve-out so several CTAs fit per SM
-    e = cudaFuncSetAttribute(stage_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(stage_kernel<C, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(stage_kernel<C, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     resident_ctas<C>();      // occupancy query outside any stream capture
@@ -43,7 +50,7 @@ static int resident_ctas()
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_kernel<C>, C::THREADS, C::SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_kernel<C, true>, C::THREADS, C::SMEM_BYTES);
         n = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
     }
     return n;
@@ -55,7 +62,26 @@ static cudaError_t do_launch(const KParams &P, cudaStream_t s)
     if (P.elem_count <= 0) return cudaSuccess;
     const int ngroups = (P.elem_count + C::EPB - 1) / C::EPB;
     const int grid = ngroups;      // one CTA per group of EPB consecutive elements
-    stage_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(P);
+    stage_kernel<C, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(P);
+    return cudaGetLastError();
+}
+
+template <class C>
+static cudaError_t do_launch_elements(const KParams &P, cudaStream_t s)
+{
+    if (P.elem_count <= 0) return cudaSuccess;
+    const int grid = (P.elem_count + C::EPB - 1) / C::EPB;
+    stage_kernel<C, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(P);
+    return cudaGetLastError();
+}
+
+template <class C>
+static cudaError_t do_launch_faces(const KParams &P, cudaStream_t s)
+{
+    if (P.face_count <= 0) return cudaSuccess;
+    const int64_t n = (int64_t)P.face_count * C::NFP;
+    const int grid = (int)((n + 127) / 128);
+    face_flux_kernel<C::ND, C::NP, C::EQ, C::CART><<<grid, 128, 0, s>>>(P);
     return cudaGetLastError();
 }
 
@@ -105,10 +131,11 @@ template <class C>
 static constexpr StageLauncher make()
 {
 #ifdef FLOU_WS
-    return StageLauncher{&ws_launch<C>, &ws_prepare<C>, &ws_resident_ctas<C>, C::EPB, WSCfg<C>::THREADS,
-                         WSCfg<C>::SMEM_BYTES};
+    return StageLauncher{&ws_launch<C>, &do_launch_elements<C>, &do_launch_faces<C>, &ws_prepare<C>,
+                         &ws_resident_ctas<C>, C::EPB, WSCfg<C>::THREADS, WSCfg<C>::SMEM_BYTES};
 #else
-    return StageLauncher{&do_launch<C>, &do_prepare<C>, &resident_ctas<C>, C::EPB, C::THREADS, C::SMEM_BYTES};
+    return StageLauncher{&do_launch<C>, &do_launch_elements<C>, &do_launch_faces<C>, &do_prepare<C>,
+                         &resident_ctas<C>, C::EPB, C::THREADS, C::SMEM_BYTES};
 #endif
 }
 
@@ -120,7 +147,7 @@ static const StageLauncher table[2][3][2] = {
     {   // linear advection: strong, split (StdAverage two-point flux); no Chandrasekhar
         {make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, true>>()},
-        {StageLauncher{nullptr, nullptr, nullptr, 0, 0, 0}, StageLauncher{nullptr, nullptr, nullptr, 0, 0, 0}},
+        {StageLauncher{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0}, StageLauncher{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0}},
     },
     {   // Euler
         {make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, true>>()},

@@ -6,7 +6,9 @@
 namespace flou {
 
 struct StageLauncher {
-    cudaError_t (*launch)(const KParams &, cudaStream_t);
+    cudaError_t (*launch)(const KParams &, cudaStream_t);         // fused single-kernel stage
+    cudaError_t (*launch_elements)(const KParams &, cudaStream_t); // two-kernel path: volume+lift+RK
+    cudaError_t (*launch_faces)(const KParams &, cudaStream_t);    // two-kernel path: Riemann fluxes
     cudaError_t (*prepare)();
     int (*resident)();          // persistent grid size (CTAs per SM x SMs)
     int epb, threads;

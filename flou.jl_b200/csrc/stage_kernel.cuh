@@ -60,6 +60,19 @@ struct Conn {
     int info;
 };
 
+// One record per local face (two-kernel path).  Side A = master, side B = slave.
+//   em / es : local element id, ghost slot, or (slave only) ordinal of the boundary face
+//   info    : [0:3) master local face  [3:6) slave local face  [6:9) orientation
+//             [9:11) master kind (0 local, 1 ghost)  [11:13) slave kind (0 local, 1 ghost, 2 boundary)
+//             [13:..) boundary index
+struct FaceRec {
+    int em, es, info, pad;
+};
+__host__ __device__ inline int facerec_pack(int lfm, int lfs, int orient, int mkind, int skind, int bc)
+{
+    return (lfm & 7) | ((lfs & 7) << 3) | ((orient & 7) << 6) | ((mkind & 3) << 9) | ((skind & 3) << 11) | (bc << 13);
+}
+
 struct KParams {
     // operators, column-major NP x NP : Dvol = Ds (strong) or Dsharp (split)
     double Dvol[64];
@@ -90,6 +103,12 @@ struct KParams {
     double *tr_out;             // traces of u_out (written together with u_out)
     // Gauss nodes only: interpolated traces of the remaining faces, [(e*2nd + lf)*nv + v]*NFP + k
     const double *tr_hi;
+    // two-kernel path: face table, per (element, face) flux slot, flux array
+    const FaceRec *faces;       // [local face slot]
+    const int2 *econn;          // [e*2nd + lf] = {flux slot, info: bit0 master, bits 1..3 orientation}
+    double *Fn;                 // [(slot*nv + v)*NFP + i]: master-outward normal flux * face jac
+    int face_first, face_count;
+    int split_faces;            // 1: stage kernel reads Fn instead of evaluating Riemann fluxes
     // halo
     const double *ghost;        // [(slot*nv + v)*NFP + k] in the sender's face-dof order
     // state
@@ -322,7 +341,7 @@ struct KCfg {
     // neighbour traces are prefetched into the slots the face fluxes later overwrite
     static constexpr int FOFF = XOFF + (NXCH + NACC) * NPTS;
     static constexpr int PER_ELEM = FOFF + NFACES * NV * NFP;
-    static constexpr int OPS = NP * NP + 4 * NP;
+    static constexpr int OPS = NP * NP + 4 * NP + EPB * NFACES;
     static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OPS + EPB * PER_ELEM);
     static constexpr int MIN_BLOCKS_WANTED =
 #ifdef FLOU_MIN_BLOCKS
@@ -333,6 +352,15 @@ struct KCfg {
     static constexpr int SMEM_BLOCKS = (int)((227 * 1024) / (SMEM_BYTES + 1024));
     static constexpr int MIN_BLOCKS =
         SMEM_BLOCKS < 1 ? 1 : (SMEM_BLOCKS < MIN_BLOCKS_WANTED ? SMEM_BLOCKS : MIN_BLOCKS_WANTED);
+    // element kernel of the two-kernel path (no Riemann solver inside: fewer registers)
+    static constexpr int MIN_BLOCKS_E_WANTED =
+#ifdef FLOU_MIN_BLOCKS_E
+        FLOU_MIN_BLOCKS_E;
+#else
+        (THREADS > 256) ? 1 : (THREADS > 128 ? 2 : 4);
+#endif
+    static constexpr int MIN_BLOCKS_E =
+        SMEM_BLOCKS < 1 ? 1 : (SMEM_BLOCKS < MIN_BLOCKS_E_WANTED ? SMEM_BLOCKS : MIN_BLOCKS_E_WANTED);
 };
 
 template <int N>
@@ -348,8 +376,11 @@ __device__ __forceinline__ Conn pick_conn(const Conn *cn, int j)
 // (cp.async) of `tmp` and of the neighbours' face traces -- contiguous blocks of the trace
 // array, so they coalesce -- and they are only waited for right before the face / update
 // phases, i.e. behind the volume work.
-template <class C>
-__global__ void __launch_bounds__(C::THREADS, C::MIN_BLOCKS)
+// SPLITF = true: the Riemann fluxes come from face_flux_kernel through P.Fn (each face
+// evaluated once); phase 3 disappears and phase 0 copies the six flux blocks instead of the
+// neighbours' traces.  SPLITF = false: the fully fused single-kernel stage.
+template <class C, bool SPLITF>
+__global__ void __launch_bounds__(C::THREADS, SPLITF ? C::MIN_BLOCKS_E : C::MIN_BLOCKS)
 stage_kernel(const __grid_constant__ KParams P)
 {
     constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
@@ -360,7 +391,8 @@ stage_kernel(const __grid_constant__ KParams P)
     extern __shared__ double smem[];
     double *sD = smem;                       // [ii + NP*jj]
     double *sLm = sD + NP * NP, *sLp = sLm + NP, *sGl = sLp + NP, *sGr = sGl + NP;
-    double *sElem = sGr + NP;
+    double *sSign = sGr + NP;                // [el][lf]: +1 master, -1 slave (two-kernel path)
+    double *sElem = sSign + EPB * NFACES;
 
     const int tid = threadIdx.x;
     for (int i = tid; i < NP * NP; i += C::THREADS) sD[i] = P.Dvol[i];
@@ -396,6 +428,18 @@ stage_kernel(const __grid_constant__ KParams P)
             const int tel = task / NFT, r = task - tel * NFT;
             const int lf = r / NFP, k = r - lf * NFP;
             const int te = elem_of(g * EPB + tel);
+            if (SPLITF) {
+                // flux block of this face, permuted into my face-dof order while copying
+                const int2 ec = __ldg(P.econn + ((int64_t)te * NFACES + lf));
+                const bool master = ec.y & 1;
+                const int i = master ? k : slave2master<ND, NP>(k, (ec.y >> 1) & 7);
+                double *dst = sElem + (size_t)tel * C::PER_ELEM + C::FOFF + lf * NV * NFP + k;
+                const double *src = P.Fn + (int64_t)ec.x * (NV * NFP) + i;
+#pragma unroll
+                for (int v = 0; v < NV; v++) cp_async8(dst + v * NFP, src + v * NFP);
+                if (k == 0) sSign[tel * NFACES + lf] = master ? 1.0 : -1.0;
+                continue;
+            }
             const int2 c = __ldg(reinterpret_cast<const int2 *>(P.conn) + ((int64_t)te * NFACES + lf));
             cn_cur[j].nbr = c.x; cn_cur[j].info = c.y;
             const int kind = (c.y >> 7) & 3;
@@ -648,6 +692,7 @@ stage_kernel(const __grid_constant__ KParams P)
 #ifdef FLOU_EXPERIMENT_SKIP_FACES
         if (P.elem_count < 0)
 #endif
+        if (!SPLITF)
 #pragma unroll 1
         for (int j = 0; j < TPT; j++) {
             const int task = tid + j * C::THREADS;
@@ -778,12 +823,14 @@ stage_kernel(const __grid_constant__ KParams P)
                 const double gl = sGl[ii], gr = sGr[ii];
                 // collocated nodes: the lifting weights vanish away from the two end nodes
                 if (gl != 0.0) {
+                    const double w = SPLITF ? gl * sSign[el * NFACES + 2 * d] : gl;
 #pragma unroll
-                    for (int v = 0; v < NV; v++) acc[v] -= gl * sF[((2 * d) * NV + v) * NFP + k];
+                    for (int v = 0; v < NV; v++) acc[v] -= w * sF[((2 * d) * NV + v) * NFP + k];
                 }
                 if (gr != 0.0) {
+                    const double w = SPLITF ? gr * sSign[el * NFACES + 2 * d + 1] : gr;
 #pragma unroll
-                    for (int v = 0; v < NV; v++) acc[v] -= gr * sF[((2 * d + 1) * NV + v) * NFP + k];
+                    for (int v = 0; v < NV; v++) acc[v] -= w * sF[((2 * d + 1) * NV + v) * NFP + k];
                 }
             }
             // mass matrix: dQ / jac (Diagonal ldiv!, MultielementDiscontinuous.jl:132-137)

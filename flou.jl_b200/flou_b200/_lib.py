@@ -18,6 +18,7 @@ FLUX_STDAVERAGE, FLUX_LXF, FLUX_CHANDRASEKHAR, FLUX_SCALARDISSIPATION, FLUX_MATR
 BC_INFLOW, BC_OUTFLOW, BC_SLIP, BC_TABLE = range(4)
 GEOM_CARTESIAN, GEOM_GENERAL = 0, 1
 FLAG_NO_GRAPH = 1
+FLAG_FUSED = 2
 
 
 class DomainError(ArithmeticError):

@@ -29,7 +29,8 @@ class EquationConfig:
 
 class MultielementDisc:
     def __init__(self, mesh, std, equation, operators, bcs, source=None, *,
-                 rank=0, nranks=1, device=None, geometry=None, use_graph=True, create=True):
+                 rank=0, nranks=1, device=None, geometry=None, use_graph=True, create=True,
+                 fused=None):
         if source is not None:
             raise ValueError("source terms are not part of the B200 hot path (default no-op only)")
         if std.nd != mesh.nd or equation.nd != mesh.nd:
@@ -132,7 +133,10 @@ class MultielementDisc:
         d.rank, d.nranks = self.rank, self.nranks
         d.part_offsets = _ptr(keep["part_offsets"]) if self.nranks > 1 else None
         d.device = int(device if device is not None else 0)
-        d.flags = 0 if use_graph else L.FLAG_NO_GRAPH
+        import os as _os
+        if fused is None:
+            fused = _os.environ.get("FLOU_B200_FUSED", "0") == "1"
+        d.flags = (0 if use_graph else L.FLAG_NO_GRAPH) | (L.FLAG_FUSED if fused else 0)
         self._h = C.c_void_p()
         if create:
             L.check(L.lib().flou_b200_create(C.byref(d), C.byref(self._h)))
