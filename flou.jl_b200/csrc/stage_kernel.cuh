@@ -357,7 +357,7 @@ struct KCfg {
 #ifdef FLOU_MIN_BLOCKS_E
         FLOU_MIN_BLOCKS_E;
 #else
-        (THREADS > 256) ? 1 : (THREADS > 128 ? 2 : 4);
+        (THREADS > 256) ? 1 : (THREADS > 128 ? 2 : 5);
 #endif
     static constexpr int MIN_BLOCKS_E =
         SMEM_BLOCKS < 1 ? 1 : (SMEM_BLOCKS < MIN_BLOCKS_E_WANTED ? SMEM_BLOCKS : MIN_BLOCKS_E_WANTED);
@@ -681,8 +681,8 @@ stage_kernel(const __grid_constant__ KParams P)
                 }
             }
         }
-        // park the volume accumulators: the face phase needs the registers
-        if (active) {
+        // fused kernel only: park the volume accumulators, the face phase needs the registers
+        if (!SPLITF && active) {
 #pragma unroll
             for (int v = 0; v < NV; v++) sAcc[v * NPTS + node] = acc[v];
         }
@@ -811,8 +811,10 @@ stage_kernel(const __grid_constant__ KParams P)
         // ---------------- phase 4: lift, mass matrix, RK stage update
         if (active) {
             const double *sF = sMine + C::FOFF;
+            if (!SPLITF) {
 #pragma unroll
-            for (int v = 0; v < NV; v++) acc[v] = sAcc[v * NPTS + node];
+                for (int v = 0; v < NV; v++) acc[v] = sAcc[v * NPTS + node];
+            }
 #ifdef FLOU_EXPERIMENT_SKIP_LIFT
             if (P.elem_count < 0)
 #endif
