@@ -39,8 +39,12 @@ __device__ __forceinline__ void load_trace(const KParams &P, int kind, int elem_
     }
 }
 
+#ifndef FLOU_FACE_MIN_BLOCKS
+#define FLOU_FACE_MIN_BLOCKS 5
+#endif
+
 template <int ND, int NP, int EQ, bool CART>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, FLOU_FACE_MIN_BLOCKS)
 face_flux_kernel(const __grid_constant__ KParams P)
 {
     constexpr int NV = (EQ == EQ_ADV) ? 1 : ND + 2;

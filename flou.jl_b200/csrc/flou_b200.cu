@@ -332,6 +332,9 @@ struct flou_b200_handle {
     std::vector<double> graph_key[2];
     int64_t launches = 0;
     int64_t graph_launches_per_replay = 0;
+    // per-kernel CUDA-event timing (flou_b200_profile): {before faces, after faces, after elements}
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;
     // two-kernel path
     bool split_faces = true;
     FaceRec *faces = nullptr;
@@ -381,8 +384,15 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
             // two-kernel stage: every face flux once, then volume + lift + RK update
             P.face_first = 0;
             P.face_count = h->n_faces;
+            cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+            if (h->profile) {
+                for (auto &e : ev) { CUDA_TRY(cudaEventCreate(&e)); h->prof_events.push_back(e); }
+                CUDA_TRY(cudaEventRecord(ev[0], h->stream));
+            }
             CUDA_TRY(h->stage->launch_faces(P, h->stream));
+            if (h->profile) CUDA_TRY(cudaEventRecord(ev[1], h->stream));
             CUDA_TRY(h->stage->launch_elements(P, h->stream));
+            if (h->profile) CUDA_TRY(cudaEventRecord(ev[2], h->stream));
             h->launches += 2;
         } else {
             CUDA_TRY(h->stage->launch(P, h->stream));
@@ -723,6 +733,7 @@ int32_t flou_b200_destroy(flou_b200_handle *h)
                     h->frames, h->faces, h->econn, h->Fn, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
                     h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev_emit) cudaEventDestroy(h->ev_emit);
     if (h->ev_recv) cudaEventDestroy(h->ev_recv);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -801,7 +812,8 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
     CUDA_TRY(cudaSetDevice(h->device));
     // CUDA graph of two steps (2*nstages passes bring u back to the same ping-pong buffer);
     // only for single-rank handles: NCCL calls are issued directly.
-    const bool use_graph = !(h->flags & FLOU_B200_FLAG_NO_GRAPH) && h->nranks == 1 && nsteps >= 4;
+    const bool use_graph = !(h->flags & FLOU_B200_FLAG_NO_GRAPH) && h->nranks == 1 && nsteps >= 4 &&
+                           !h->profile;
     int64_t done = 0;
     if (use_graph && !h->traces_valid) {
         // bring the traces of the current state up to date outside the captured region
@@ -881,6 +893,29 @@ int32_t flou_b200_kernel_info(flou_b200_handle *h, int32_t *grid_ctas, int32_t *
     if (threads) *threads = h->stage->threads;
     if (smem_bytes) *smem_bytes = (int32_t)h->stage->smem;
     if (elems_per_cta_iter) *elems_per_cta_iter = h->stage->epb;
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_profile(flou_b200_handle *h, int32_t enable, float *ms_faces, float *ms_elements,
+                          int64_t *npasses)
+{
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    double tf = 0.0, te = 0.0;
+    const size_t n = h->prof_events.size() / 3;
+    for (size_t i = 0; i < n; i++) {
+        float a = 0.f, b = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&a, h->prof_events[3 * i], h->prof_events[3 * i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, h->prof_events[3 * i + 1], h->prof_events[3 * i + 2]));
+        tf += a; te += b;
+    }
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    h->prof_events.clear();
+    if (ms_faces) *ms_faces = (float)tf;
+    if (ms_elements) *ms_elements = (float)te;
+    if (npasses) *npasses = (int64_t)n;
+    h->profile = enable != 0;
     return FLOU_B200_OK;
 }
 

@@ -72,6 +72,8 @@ SYMBOLS = {
     "flou_b200_device_state": (C.c_void_p, [C.c_void_p]),
     "flou_b200_kernel_launches": (C.c_int64, [C.c_void_p]),
     "flou_b200_kernel_info": (C.c_int32, [C.c_void_p] + [C.POINTER(C.c_int32)] * 4),
+    "flou_b200_profile": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_int64)]),
     "flou_b200_timer_start": (C.c_int32, [C.c_void_p]),
     "flou_b200_timer_stop": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
     "flou_b200_pin_host": (C.c_int32, [C.c_void_p, C.c_uint64]),

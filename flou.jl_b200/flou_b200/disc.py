@@ -219,6 +219,14 @@ class MultielementDisc:
         return dict(grid_ctas=v[0].value, threads=v[1].value, smem_bytes=v[2].value,
                     elems_per_cta_iter=v[3].value)
 
+    def profile(self, enable):
+        """Per-kernel event timing: returns (ms in face kernel, ms in element kernel, passes)
+        accumulated since the last call and switches the instrumentation on/off."""
+        a, b, n = C.c_float(0), C.c_float(0), C.c_int64(0)
+        L.check(L.lib().flou_b200_profile(self.handle, 1 if enable else 0, C.byref(a), C.byref(b),
+                                          C.byref(n)))
+        return a.value, b.value, n.value
+
     def timer_start(self):
         L.check(L.lib().flou_b200_timer_start(self.handle))
 

@@ -188,6 +188,11 @@ int64_t flou_b200_kernel_launches(const flou_b200_handle *h); /* stage/rhs/halo 
  * per CTA, dynamic shared memory per CTA, elements a CTA processes per loop iteration */
 int32_t flou_b200_kernel_info(flou_b200_handle *h, int32_t *grid_ctas, int32_t *threads,
                               int32_t *smem_bytes, int32_t *elems_per_cta_iter);
+/* Per-kernel CUDA-event timing of the two-kernel stage (single-rank handles): returns the time
+ * accumulated since the previous call in the face-flux kernel and in the element kernel over
+ * `npasses` passes, then switches the instrumentation on/off (graph replay is off while on). */
+int32_t flou_b200_profile(flou_b200_handle *h, int32_t enable, float *ms_faces, float *ms_elements,
+                          int64_t *npasses);
 /* CUDA-event stopwatch on the compute stream (kernel timing for the roofline figure) */
 int32_t flou_b200_timer_start(flou_b200_handle *h);
 int32_t flou_b200_timer_stop(flou_b200_handle *h, float *ms);
