@@ -5,9 +5,9 @@ file:line map).  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_
 / `--impl reference` legs may import this package; the product (`flou.jl_b200/`) never
 does, and fails loudly when its CUDA library is missing.
 
-Parity pinning: checked against the reference's own known-answer tests
-(`test/runtests.jl:24-39`: SodTube1D min/max to rtol 1e-7, Advection1D/2D periodic return)
-in `tests/test_oracle_kat.py`.  Third-party pieces restated from published algorithms:
+Parity pinning: checked against ALL of the reference's own known-answer tests
+(`test/runtests.jl:24-44`: SodTube1D min/max and Shockwave2D max to rtol 1e-7 -- reproduced to
+~1e-13 -- and the Advection1D/2D periodic returns) in `tests/test_oracle_kat.py`.  Third-party pieces restated from published algorithms:
 OrdinaryDiffEq v6.49.1 `ORK256` / `CarpenterKennedy2N54` 2N tableaus (ORK256 pinned through
 the Sod KAT; CarpenterKennedy2N54 parity unpinned), FastGaussQuadrature v0.5.0 nodes,
 Polynomials v3.2.7 `fit`.  Nothing in the reference's tests pins 3-D or unstructured
@@ -25,7 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 EQ_ADVECTION, EQ_EULER = 0, 1
-OP_STRONG, OP_SPLIT = 0, 1
+OP_STRONG, OP_SPLIT, OP_HYBRID = 0, 1, 2
 FLUX_STDAVG, FLUX_LXF, FLUX_CHANDRASEKHAR, FLUX_SCALARDISS, FLUX_MATRIXDISS = range(5)
 BC_INFLOW, BC_OUTFLOW, BC_SLIP, BC_TABLE = range(4)
 
@@ -63,6 +63,7 @@ class _Problem(C.Structure):
         ("nbound", C.c_int32), ("bc_kind", C.c_void_p), ("bc_offsets", C.c_void_p),
         ("bc_faces", C.c_void_p), ("bc_state", C.c_void_p), ("bc_table", C.c_void_p),
         ("Qf", C.c_void_p * 2), ("Fn", C.c_void_p * 2),
+        ("blend", C.c_double), ("w1d", C.c_void_p), ("sub_jac", C.c_double * 3),
     ]
 
 
@@ -103,7 +104,7 @@ class Problem:
 
     def __init__(self, mesh, nodetype, npn, equation, op, numflux, *, tpflux=None,
                  numflux_avg=FLUX_STDAVG, intensity=1.0, gamma=1.4, a=(0.0, 0.0, 0.0),
-                 bcs=(), cartesian=True):
+                 bcs=(), cartesian=True, blend=0.0):
         self.mesh = mesh
         nd = mesh.nd
         self.nd, self.np = nd, npn
@@ -184,6 +185,17 @@ class Problem:
                      "Dsharp", "lm", "lp", "dgl", "dgr", "jac", "metric", "fjac", "frames",
                      "bc_kind", "bc_offsets", "bc_faces", "bc_state", "bc_table"):
             setattr(p, name, _ptr(k[name]))
+        # HybridDivOperator (oracle only): 1-D weights, Cartesian sub-grid face Jacobians
+        k["w1d"] = np.ascontiguousarray(self.ops["w"])
+        p.w1d, p.blend = _ptr(k["w1d"]), float(blend)
+        if op == OP_HYBRID:
+            if not (cartesian and self.ops["hasboundaries"]):
+                raise ValueError("the oracle's HybridDivOperator covers GLL nodes on Cartesian meshes")
+            dx = mesh.dx
+            sub = [1.0] if nd == 1 else [dx[1] / 2, dx[0] / 2] if nd == 2 else \
+                [dx[1] * dx[2] / 4, dx[0] * dx[2] / 4, dx[0] * dx[1] / 4]
+            for d_, v_ in enumerate(sub):
+                p.sub_jac[d_] = v_
         p.Qf[0], p.Qf[1] = _ptr(k["Qf0"]), _ptr(k["Qf1"])
         p.Fn[0], p.Fn[1] = _ptr(k["Fn0"]), _ptr(k["Fn1"])
 

@@ -11,6 +11,9 @@
  *   _volumeflux!             src/FlouSpatial/Equations/OpDivergence.jl:28-37
  *   StrongDivOperator        OpDivergence.jl:105-173
  *   SplitDivOperator         OpDivergence.jl:184-299
+ *   HybridDivOperator        OpDivergence.jl:452-612, 781-801 (GLL nodes, Cartesian sub-grid
+ *                            frames PhysicalRegions.jl:72-148); ORACLE ONLY -- it exists to
+ *                            pin the 2-D machinery against the reference's Shockwave2D KAT
  *   applyBCs!                Interfaces.jl:25-49
  *   interface_fluxes!        Interfaces.jl:111-136
  *   _surface_contribution!   OpDivergence.jl:42-100
@@ -43,7 +46,7 @@
 #define MAXNP 16
 
 enum { EQ_ADVECTION = 0, EQ_EULER = 1 };
-enum { OP_STRONG = 0, OP_SPLIT = 1 };
+enum { OP_STRONG = 0, OP_SPLIT = 1, OP_HYBRID = 2 };
 enum { FLUX_STDAVG = 0, FLUX_LXF = 1, FLUX_CHANDRASEKHAR = 2, FLUX_SCALARDISS = 3,
        FLUX_MATRIXDISS = 4 };
 enum { BC_INFLOW = 0, BC_OUTFLOW = 1, BC_SLIP = 2, BC_TABLE = 3 };
@@ -83,6 +86,10 @@ typedef struct {
     /* work arrays (allocated by the caller) */
     double *Qf[2];            /* each (nf*nfp) * nv column-major */
     double *Fn[2];
+    /* HybridDivOperator only */
+    double blend;             /* op.blend */
+    const double *w1d;        /* 1-D weights of the standard region */
+    double sub_jac[3];        /* Cartesian sub-grid face Jacobians by direction */
 } oracle_problem;
 
 static inline int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
@@ -556,6 +563,61 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
                                        * Ft[((base + jj * stride) * nv + v) * nd + d];
                                 dQ[e * npts + base + ii * stride + ndof * v] -= s;
                             }
+                    }
+                } else if (P->op == OP_HYBRID) {
+                    /* _vol_hybrid_tensorproduct!   OpDivergence.jl:554-612 (fvflux = numflux) */
+                    for (int k = 0; k < nlines; k++) {
+                        int base, stride;
+                        line_of(nd, np, d, k, &base, &stride);
+                        double Fb[MAXNP + 1][MAXV];
+                        memset(Fb, 0, sizeof Fb);
+                        /* Cartesian sub-grid frame of direction d: PhysicalRegions.jl:72-148 */
+                        double fr[9];
+                        memset(fr, 0, sizeof fr);
+                        fr[d] = 1.0;
+                        if (nd == 2) fr[nd + (1 - d)] = (d == 0) ? 1.0 : -1.0;
+                        if (nd == 3) { fr[nd + (d + 1) % 3] = 1.0; fr[2 * nd + (d + 2) % 3] = 1.0; }
+                        for (int ii = 1; ii < np; ii++) {          /* Julia ii = 2..npts */
+                            for (int ik = ii; ik < np; ik++) {
+                                int kk = base + ik * stride;
+                                for (int il = 0; il < ii; il++) {
+                                    int l = base + il * stride;
+                                    double Ql[MAXV], Qk[MAXV], F[MAXV];
+                                    for (int v = 0; v < nv; v++) {
+                                        Ql[v] = Q[e * npts + l + ndof * v];
+                                        Qk[v] = Q[e * npts + kk + ndof * v];
+                                    }
+                                    twopointflux(P, Ql, Qk, Ja + l * nd * nd + nd * d,
+                                                 Ja + kk * nd * nd + nd * d, F);
+                                    for (int v = 0; v < nv; v++)
+                                        Fb[ii][v] += 2 * P->w1d[il] * P->D[il + np * ik] * F[v];
+                                }
+                            }
+                            int i = base + ii * stride, il = base + (ii - 1) * stride;
+                            double Qa[MAXV], Qb[MAXV], Qln[MAXV], Qrn[MAXV], Fn_[MAXV], Fv[MAXV];
+                            for (int v = 0; v < nv; v++) {
+                                Qa[v] = Q[e * npts + il + ndof * v];
+                                Qb[v] = Q[e * npts + i + ndof * v];
+                            }
+                            rotate2face(P, Qa, fr, Qln);
+                            rotate2face(P, Qb, fr, Qrn);
+                            numericalflux(P, Qln, Qrn, fr, Fn_);
+                            rotate2phys(P, Fn_, fr, Fv);
+                            for (int v = 0; v < nv; v++) Fv[v] *= P->sub_jac[d];
+                            double Wl[MAXV], Wr[MAXV], b = 0;
+                            cons2entropy(Qa, nd, P->gamma, Wl);
+                            cons2entropy(Qb, nd, P->gamma, Wr);
+                            for (int v = 0; v < nv; v++) b += (Wr[v] - Wl[v]) * (Fb[ii][v] - Fv[v]);
+                            double delta = sqrt(b * b + P->blend);      /* _hybrid_compute_delta */
+                            delta = (delta - b) / delta;
+                            delta = fmax(delta, 0.5);
+                            for (int v = 0; v < nv; v++)
+                                Fb[ii][v] = (1 - delta) * Fv[v] + delta * Fb[ii][v];
+                        }
+                        for (int ii = 0; ii < np; ii++)
+                            for (int v = 0; v < nv; v++)
+                                dQ[e * npts + base + ii * stride + ndof * v] +=
+                                    (Fb[ii][v] - Fb[ii + 1][v]) / P->w1d[ii];
                     }
                 } else {
                     /* _flux_splitdiv_tensorproduct!   OpDivergence.jl:248-271 */

@@ -62,3 +62,36 @@ def test_advection_2d_periodic_return():
         Q[i, 0] = O.gaussian_bump(pb.coords[i], [0.75, 1.0], [0.2, 0.2], 1.0)
     u = pb.lsrk2n(Q, O.ORK256, 1e-3, 500)
     assert _isapprox(u, Q, KAT["Advection2D"]["rtol"])
+
+
+def test_shockwave_2d_kat():
+    """Shockwave2D (runtests.jl:40-44, setup tests.jl:136-185): 11x3, GLL(6),
+    HybridDivOperator(MatrixDissipation(ChandrasekharAverage(), 1.0), 1.0), y-periodic,
+    ORK256, dt=1e-2, tf=1: maximum(u(tf)) to rtol 1e-7.  Pins the 2-D machinery: face frames and
+    rotations, the periodic seam with its inward master normal, face-dof ordering, the 2-D
+    MatrixDissipation flux and tabulated GenericBC (the hybrid operator itself is oracle-only)."""
+    g = 1.4
+    mesh = cn.cartesian_mesh((-1, 0), (1, 1), (11, 3))
+    cn.apply_periodic_bcs(mesh, ("3", "4"))
+    rho0, M0, p0 = 1.0, 2.0, 1.0
+    u0 = M0 * np.sqrt(g * p0 / rho0)
+    rho1 = rho0 * M0 ** 2 * (g + 1) / ((g - 1) * M0 ** 2 + 2)          # normal_shockwave,
+    p1 = p0 * (2 * g * M0 ** 2 - (g - 1)) / (g + 1)                     # FlouCommon/Euler.jl:337-358
+    M1 = np.sqrt(((g - 1) * M0 ** 2 + 2) / (2 * g * M0 ** 2 - (g - 1)))
+    u1 = M1 * np.sqrt(g * p1 / rho1)
+    Q0 = O.vars_prim2cons((rho0, u0, 0.0, p0), g)
+    Q1 = O.vars_prim2cons((rho1, u1, 0.0, p1), g)
+
+    def qext(x):
+        return Q0 if x[0] < 0 else Q1
+    pb = O.Problem(mesh, "GLL", 6, O.EQ_EULER, O.OP_HYBRID, O.FLUX_MATRIXDISS,
+                   numflux_avg=O.FLUX_CHANDRASEKHAR, intensity=1.0, gamma=g, blend=1.0,
+                   bcs={"1": (O.BC_TABLE, qext), "2": (O.BC_TABLE, qext)})
+    Q = pb.new_state()
+    for i in range(pb.ndof):
+        Q[i] = qext(pb.coords[i])
+    u = pb.lsrk2n(Q, O.ORK256, 1e-2, 100)
+    k = KAT["Shockwave2D"]
+    assert abs(u.max() / k["maximum"] - 1) <= k["rtol"]
+    assert abs(u.max() / k["maximum"] - 1) <= 1e-11
+    assert abs(u.min()) < 1e-9          # reference: -4.68e-13 with rtol 1 (round-off noise in rho*v)
