@@ -19,6 +19,7 @@
 
 #include "flou_b200.h"
 #include "launch.h"
+#include "cfl_kernel.cuh"
 
 using namespace flou;
 
@@ -55,6 +56,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load()
     {
@@ -73,6 +75,7 @@ struct NcclApi {
         SYM(GroupEnd, "ncclGroupEnd")
         SYM(Send, "ncclSend")
         SYM(Recv, "ncclRecv")
+        SYM(AllReduce, "ncclAllReduce")
         SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
         return true;
@@ -335,6 +338,12 @@ struct flou_b200_handle {
     // per-kernel CUDA-event timing (flou_b200_profile): {before faces, after faces, after elements}
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
+    // get_max_dt
+    double *elem_dx = nullptr;           // general geometry: (volume_e/npts)^(1/nd) per element
+    double cart_dx = 0.0;
+    unsigned long long *dt_bits = nullptr;
+    double gamma = 0.0, anorm = 0.0;
+    int equation = 0;
     // two-kernel path
     bool split_faces = true;
     FaceRec *faces = nullptr;
@@ -675,6 +684,43 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         H_TRY(upload(&h->d_lm, lm));
         H_TRY(upload(&h->d_lp, lp));
     }
+    {
+        // dx_e = (volume_e / npts)^(1/nd), volume_e = sum_i jac_i * w_i with the tensor-product
+        // weights w = wx*wy*wz (StdQuad.jl:49, StdHex.jl:54; PhysicalRegions.jl:403-405)
+        if (!d->weights) { flou_b200_destroy(h); return fail(FLOU_B200_EINVAL, "weights (std.w) missing"); }
+        const int npts = h->npts;
+        std::vector<double> w((size_t)npts);
+        for (int i = 0; i < npts; i++) {
+            double x = d->weights[i % np];
+            if (nd > 1) x *= d->weights[(i / np) % np];
+            if (nd > 2) x *= d->weights[i / (np * np)];
+            w[i] = x;
+        }
+        auto to_dx = [&](double vol) {
+            const double r = vol / npts;
+            return nd == 1 ? r : (nd == 2 ? std::sqrt(r) : std::cbrt(r));
+        };
+        if (cart) {
+            double vol = 0.0;
+            for (int i = 0; i < npts; i++) vol += P.cjac * w[i];
+            h->cart_dx = to_dx(vol);
+        } else {
+            std::vector<double> edx((size_t)h->ne_local);
+            for (int64_t le = 0; le < h->ne_local; le++) {
+                double vol = 0.0;
+                const double *j = d->jac + (d->elem_begin + le) * npts;
+                for (int i = 0; i < npts; i++) vol += j[i] * w[i];
+                edx[le] = to_dx(vol);
+            }
+            H_TRY(upload(&h->elem_dx, edx));
+        }
+        h->gamma = d->gamma;
+        h->equation = d->equation;
+        double a2 = 0.0;
+        for (int c = 0; c < nd; c++) a2 += d->a[c] * d->a[c];
+        h->anorm = std::sqrt(a2);
+        H_TRY(cudaMalloc((void **)&h->dt_bits, sizeof(unsigned long long)));
+    }
     H_TRY(upload(&h->send_list, send_list));
     H_TRY(upload(&h->interior_list, interior));
     H_TRY(upload(&h->boundary_list, boundary));
@@ -730,7 +776,7 @@ int32_t flou_b200_destroy(flou_b200_handle *h)
     destroy_graph(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void *ptrs[] = {h->u[0], h->u[1], h->tr[0], h->tr[1], h->tr_all, h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
-                    h->frames, h->faces, h->econn, h->Fn, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
+                    h->frames, h->faces, h->econn, h->Fn, h->elem_dx, h->dt_bits, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
                     h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -762,6 +808,39 @@ int32_t flou_b200_download_state(flou_b200_handle *h, double *Q)
     CUDA_TRY(cudaMemcpyAsync(Q, h->u[h->cur], sizeof(double) * (size_t)h->ndof * h->nv,
                              cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_max_dt(flou_b200_handle *h, const double *Q, double cfl, double *dt)
+{
+    if (!h || !dt) return fail(FLOU_B200_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (Q) {
+        CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, sizeof(double) * (size_t)h->ndof * h->nv,
+                                 cudaMemcpyHostToDevice, h->stream));
+        h->traces_valid = false;
+    }
+    const unsigned long long inf_bits = 0x7ff0000000000000ULL;
+    CUDA_TRY(cudaMemcpyAsync(h->dt_bits, &inf_bits, sizeof(inf_bits), cudaMemcpyHostToDevice, h->stream));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int threads = 256;
+    const int64_t want = (h->ndof + threads - 1) / threads;
+    const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 8);
+    max_dt_kernel<<<grid, threads, 0, h->stream>>>(h->u[h->cur], h->ndof, h->npts, h->nd,
+                                                   h->equation == FLOU_B200_EQ_EULER, h->gamma, h->anorm,
+                                                   cfl, h->elem_dx, h->cart_dx, h->dt_bits);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    if (h->nranks > 1) {
+        if (!h->comm) return fail(FLOU_B200_EINVAL, "partitioned handle used before flou_b200_comm_init");
+        // the bit pattern of a positive double is monotone: reduce it as float64 with ncclMin
+        NCCL_TRY(g_nccl.AllReduce(h->dt_bits, h->dt_bits, 1, ncclFloat64, 3 /* ncclMin */, h->comm, h->stream));
+    }
+    double out = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(&out, h->dt_bits, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *dt = out;
     return FLOU_B200_OK;
 }
 

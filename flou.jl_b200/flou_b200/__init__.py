@@ -14,4 +14,4 @@ from .equations import (ChandrasekharAverage, EulerEquation, EulerInflowBC, Eule
 from .gmshmesh import RawMesh, UnstructuredMesh, read_msh, refine, write_msh
 from .mesh import CartesianMesh, apply_periodicBCs, partition_offsets
 from .stdregions import DGSEMrec, LagrangeBasis, StdHex, StdQuad, StdSegment
-from .time import CarpenterKennedy2N54, ORK256, Solution, advance, timeintegrate
+from .time import CarpenterKennedy2N54, ORK256, Solution, advance, get_max_dt, timeintegrate

@@ -42,7 +42,7 @@ class Desc(C.Structure):
         ("elempos", C.c_void_p), ("orientation", C.c_void_p),
         ("D", C.c_void_p), ("Ds", C.c_void_p), ("Dsharp", C.c_void_p),
         ("lminus", C.c_void_p), ("lplus", C.c_void_p),
-        ("dgminus", C.c_void_p), ("dgplus", C.c_void_p),
+        ("dgminus", C.c_void_p), ("dgplus", C.c_void_p), ("weights", C.c_void_p),
         ("jac", C.c_void_p), ("metric", C.c_void_p), ("fjac", C.c_void_p), ("frames", C.c_void_p),
         ("nbound", C.c_int32), ("bc_kind", C.c_void_p), ("bc_offsets", C.c_void_p),
         ("bc_faces", C.c_void_p), ("bc_state", C.c_void_p), ("bc_table", C.c_void_p),
@@ -64,6 +64,7 @@ SYMBOLS = {
     "flou_b200_timeintegrate": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                             C.c_int64]),
+    "flou_b200_max_dt": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double)]),
     "flou_b200_synchronize": (C.c_int32, [C.c_void_p]),
     "flou_b200_status": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     "flou_b200_last_error": (C.c_char_p, []),

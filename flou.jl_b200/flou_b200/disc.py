@@ -100,6 +100,7 @@ class MultielementDisc:
             keep[name] = np.ascontiguousarray(np.asarray(arr).T)   # column-major for the ABI
         keep["lminus"], keep["lplus"] = (np.ascontiguousarray(v) for v in std.l)
         keep["dgminus"], keep["dgplus"] = (np.ascontiguousarray(v) for v in std.dg)
+        keep["weights"] = np.ascontiguousarray(std.w1d)
         kinds = np.array([bc.kind for bc in self.bcs] + [0], dtype=np.int32)
         offs = np.concatenate(([0], np.cumsum([len(b) for b in mesh.bdfaces]))).astype(np.int64)
         faces = (np.concatenate(list(mesh.bdfaces) + [np.zeros(1, dtype=np.int64)])
@@ -122,7 +123,7 @@ class MultielementDisc:
                     bc_state=np.ascontiguousarray(state), bc_table=np.ascontiguousarray(table),
                     part_offsets=np.ascontiguousarray(self.part_offsets))
         for name in ("faceinds", "facepos", "eleminds", "elempos", "orientation", "D", "Ds",
-                     "Dsharp", "lminus", "lplus", "dgminus", "dgplus", "bc_kind", "bc_offsets",
+                     "Dsharp", "lminus", "lplus", "dgminus", "dgplus", "weights", "bc_kind", "bc_offsets",
                      "bc_faces", "bc_state", "bc_table"):
             setattr(d, name, _ptr(keep[name]))
         if not cart:
@@ -201,6 +202,13 @@ class MultielementDisc:
         out = self.new_state() if out is None else _state(out, self.ndofs, self.nv, writable=True)
         L.check(L.lib().flou_b200_download_state(self.handle, _ptr(out)))
         return out
+
+    def get_max_dt(self, cfl, Q=None):
+        """get_max_dt(q, disc, equation, cfl): global CFL time step (device reduction)."""
+        dt = C.c_double(0.0)
+        q = None if Q is None else _ptr(_state(Q, self.ndofs, self.nv))
+        L.check(L.lib().flou_b200_max_dt(self.handle, q, float(cfl), C.byref(dt)))
+        return dt.value
 
     def synchronize(self):
         L.check(L.lib().flou_b200_synchronize(self.handle))

@@ -60,6 +60,13 @@ def advance(disc, solver, dt, nsteps, t0=0.0):
                                              float(dt), float(t0), int(nsteps)))
 
 
+def get_max_dt(q, disc, equation, cfl):
+    """FlouCommon.get_max_dt(q, disc, eq, cfl) (MultielementDiscontinuous.jl:162-178): what
+    `get_cfl_callback` (FlouTime.jl:92-105) evaluates every step; `q=None` uses the state that
+    lives on the device."""
+    return disc.get_max_dt(cfl, q)
+
+
 class Solution:
     """Minimal stand-in for the ODE solution: `u[0]` initial and `u[-1]` final state, `t`."""
 

@@ -35,6 +35,7 @@ struct Desc
     orientation::Ptr{UInt8}
     D::Ptr{Float64}; Ds::Ptr{Float64}; Dsharp::Ptr{Float64}
     lminus::Ptr{Float64}; lplus::Ptr{Float64}; dgminus::Ptr{Float64}; dgplus::Ptr{Float64}
+    weights::Ptr{Float64}
     jac::Ptr{Float64}; metric::Ptr{Float64}; fjac::Ptr{Float64}; frames::Ptr{Float64}
     nbound::Int32
     bc_kind::Ptr{Int32}; bc_offsets::Ptr{Int64}; bc_faces::Ptr{Int64}
@@ -87,6 +88,7 @@ function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,R
     # operators: Julia matrices are column-major, which is what the ABI expects
     D, Ds, Dsharp = std.D, std.Ds, std.D♯
     lm, lp = std.l; dgm, dgp = std.∂g
+    w1d = ND == 1 ? std.ω : (ND == 2 ? std.face.ω : std.edge.ω)
     # general geometry tables (unused for CartesianMesh)
     jac = cart ? Float64[] : geometry.elements.jac
     metric = cart ? Float64[] : collect(reinterpret(Float64, geometry.elements.metric))
@@ -115,7 +117,7 @@ function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,R
     dx = cart ? ntuple(i -> i <= ND ? Float64(mesh.Δx[i]) : 0.0, 3) : (0.0, 0.0, 0.0)
     ne = nelements(mesh)
     handle = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve faceinds facepos eleminds elempos orientation D Ds Dsharp lm lp dgm dgp jac metric fjac frames kinds offsets bcfaces state table begin
+    GC.@preserve faceinds facepos eleminds elempos orientation D Ds Dsharp lm lp dgm dgp w1d jac metric fjac frames kinds offsets bcfaces state table begin
         desc = Desc(
             Int32(sizeof(Desc)), Int32(ND), Int32(nv), Int32(size(D, 1)),
             equation isa EulerEquation ? Int32(1) : Int32(0),
@@ -126,6 +128,7 @@ function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,R
             Int64(ne), Int64(nfaces(mesh)),
             pointer(faceinds), pointer(facepos), pointer(eleminds), pointer(elempos), pointer(orientation),
             pointer(D), pointer(Ds), pointer(Dsharp), pointer(lm), pointer(lp), pointer(dgm), pointer(dgp),
+            pointer(w1d),
             cart ? C_NULL : pointer(jac), cart ? C_NULL : pointer(metric),
             cart ? C_NULL : pointer(fjac), cart ? C_NULL : pointer(frames),
             Int32(length(bcs)), pointer(kinds), pointer(offsets), pointer(bcfaces),
@@ -143,6 +146,14 @@ function rhs!(dQ::Matrix{Float64}, Q::Matrix{Float64}, p::EquationConfig{<:B200D
     check(ccall((:flou_b200_rhs, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
                 p.disc.handle, Q, dQ, Float64(time)))
     return nothing
+end
+
+# get_max_dt(q, disc, equation, cfl): used by get_cfl_callback (FlouTime.jl:92-105)
+function Flou.FlouCommon.get_max_dt(q::Matrix{Float64}, disc::B200Disc, ::Any, cfl)
+    dt = Ref{Float64}(0.0)
+    check(ccall((:flou_b200_max_dt, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64, Ref{Float64}),
+                disc.handle, q, Float64(cfl), dt))
+    return dt[]
 end
 
 # 2N tableaus straight from the OrdinaryDiffEq solver objects' caches

@@ -110,6 +110,7 @@ typedef struct flou_b200_desc {
     const double *lplus;      /* std.l[2]                                                    */
     const double *dgminus;    /* std.∂g[1]                                                   */
     const double *dgplus;     /* std.∂g[2]                                                   */
+    const double *weights;    /* std.ω of the 1-D region (np): element volume for get_max_dt */
 
     /* GEOM_GENERAL only (NULL otherwise); indexed by GLOBAL dof / face-dof */
     const double *jac;        /* ne*npts            geometry.elements.jac                    */
@@ -173,6 +174,12 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
 int32_t flou_b200_timeintegrate(flou_b200_handle *h, double *Q, int32_t nstages,
                                 const double *A, const double *B, const double *c,
                                 double dt, double t0, int64_t nsteps);
+
+/* get_max_dt(q, disc, equation, cfl) (MultielementDiscontinuous.jl:162-178 with the
+ * per-node rule of FlouCommon/Euler.jl:116-135 / LinearAdvection.jl:46-48): the global minimum
+ * of cfl*dx/(|v| + c), dx = (volume/npts)^(1/nd), over the device-resident state (Q == NULL) or
+ * an uploaded one; an ncclAllReduce(min) joins the ranks of a partitioned run.  Row f1. */
+int32_t flou_b200_max_dt(flou_b200_handle *h, const double *Q, double cfl, double *dt);
 
 int32_t flou_b200_synchronize(flou_b200_handle *h);
 /* sticky device flags: bit 0 = non-positive density/pressure or NaN seen */

@@ -90,6 +90,8 @@ def lib():
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_double, C.c_double, C.c_int64]
         _LIB.oracle_lsrk2n.restype = None
+        _LIB.oracle_max_dt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        _LIB.oracle_max_dt.restype = C.c_double
         assert _LIB.oracle_sizeof_problem() == C.sizeof(_Problem)
     return _LIB
 
@@ -208,6 +210,12 @@ class Problem:
         dQ = np.zeros_like(Q, order="F")
         lib().oracle_rhs(C.byref(self.c), _ptr(Q), _ptr(dQ), t)
         return dQ
+
+    def max_dt(self, Q, cfl):
+        """get_max_dt(q, disc, equation, cfl) (MultielementDiscontinuous.jl:162-178)."""
+        Q = np.asfortranarray(Q, dtype=np.float64)
+        vol = np.ascontiguousarray((self.jac * np.tile(self.weights, self.ne)).reshape(self.ne, -1).sum(axis=1))
+        return float(lib().oracle_max_dt(C.byref(self.c), _ptr(Q), _ptr(vol), float(cfl)))
 
     def lsrk2n(self, Q, tableau, dt, nsteps, t0=0.0):
         u = np.array(Q, dtype=np.float64, order="F", copy=True)

@@ -773,4 +773,35 @@ void oracle_lsrk2n(const oracle_problem *P, double *u, double *k, double *tmp,
     }
 }
 
+/* get_max_dt(q, disc, eq, cfl)   MultielementDiscontinuous.jl:162-178 (serial loop) with
+ * FlouCommon/Euler.jl:116-135 and LinearAdvection.jl:46-48; `volume` = per-element sum(J*w),
+ * PhysicalRegions.jl:403-405. */
+double oracle_max_dt(const oracle_problem *P, const double *Q, const double *volume, double cfl)
+{
+    const int nd = P->nd, npts = ipow(P->np, nd);
+    const int64_t ndof = P->ne * npts;
+    double dt = INFINITY;
+    for (int64_t e = 0; e < P->ne; e++) {
+        double dx = volume[e] / npts;
+        dx = nd == 1 ? dx : (nd == 2 ? sqrt(dx) : cbrt(dx));
+        for (int i = 0; i < npts; i++) {
+            double v;
+            if (P->equation == EQ_ADVECTION) {
+                double a2 = 0;
+                for (int d = 0; d < nd; d++) a2 += P->a[d] * P->a[d];
+                v = cfl * dx / sqrt(a2);
+            } else {
+                double Qi[MAXV];
+                for (int k = 0; k < P->nv; k++) Qi[k] = Q[e * npts + i + ndof * k];
+                double c = sqrt(P->gamma * pressure(Qi, nd, P->gamma) / Qi[0]);
+                double s2 = 0;
+                for (int d = 0; d < nd; d++) { double w = Qi[1 + d] / Qi[0]; s2 += w * w; }
+                v = cfl * dx / ((nd == 1 ? fabs(Qi[1] / Qi[0]) : sqrt(s2)) + c);
+            }
+            dt = fmin(dt, v);
+        }
+    }
+    return dt;
+}
+
 int oracle_sizeof_problem(void) { return (int)sizeof(oracle_problem); }

@@ -45,11 +45,12 @@ def main():
         Q = np.asfortranarray(Qg[rows])
         dQ = disc.new_state()
         F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+        dtn = F.get_max_dt(Q, disc, eq, 0.4)       # ncclAllReduce(min) over the ranks (row f1)
         u = Q.copy(order="F")
         sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), nsteps * 1e-3, dt=1e-3)
         assert sol is not None
         parts = [None] * world
-        dist.all_gather_object(parts, (dQ, sol.u[-1]))
+        dist.all_gather_object(parts, (dQ, sol.u[-1], dtn))
         if rank == 0:
             dQ1 = full.new_state()
             F.rhs(dQ1, Qg, F.EquationConfig(full, eq1), 0.0)
@@ -57,7 +58,9 @@ def main():
             F.timeintegrate(u1, full, eq1, F.ORK256(), nsteps * 1e-3, dt=1e-3)
             dQn = np.concatenate([p[0] for p in parts], axis=0)
             un = np.concatenate([p[1] for p in parts], axis=0)
-            same = np.array_equal(dQn, dQ1) and np.array_equal(un, u1)
+            dt1 = F.get_max_dt(Qg, full, eq1, 0.4)
+            same = (np.array_equal(dQn, dQ1) and np.array_equal(un, u1)
+                    and all(p[2] == dt1 for p in parts))
             print(f"[multigpu] {case!r}: ranks={world} bitwise_equal={same} "
                   f"max|d rhs|={np.max(np.abs(dQn - dQ1)):.3e} max|d u|={np.max(np.abs(un - u1)):.3e}",
                   flush=True)

@@ -133,3 +133,31 @@ def test_carpenter_kennedy_tableau_is_fourth_order_consistent():
         tmp = t["A"][s] * tmp + 1.0
         u += t["B"][s] * tmp
     assert abs(u - 1.0) < 1e-4     # ORK256 coefficients are published to 5 digits
+
+
+@pytest.mark.parametrize("case", [
+    Case(1, (7,), 4), Case(2, (4, 3), 5), Case(3, (2, 3, 2), 4), Case(2, (4, 3), 4, perturb_amp=0.1),
+    Case(2, (3, 3), 3, eq="adv", op="strong", nf="lxf", avg="std", nodes="GL"),
+], ids=repr)
+def test_max_dt_follows_the_reference_rule(case):
+    """get_max_dt (MultielementDiscontinuous.jl:162-178, FlouCommon/Euler.jl:116-135,
+    LinearAdvection.jl:46-48) against an independent vectorised restatement; on a Cartesian
+    mesh dx is the geometric mean of the edge lengths divided by np."""
+    orc = case.oracle()
+    Q = random_state(orc.ndof, case.nd, case.eq, amp=case.amp)
+    cfl = 0.35
+    npts = case.np ** case.nd
+    vol = (orc.jac * np.tile(orc.weights, orc.ne)).reshape(orc.ne, npts).sum(axis=1)
+    dx = np.repeat((vol / npts) ** (1.0 / case.nd), npts)
+    if not case.general:
+        start, finish = np.array([0.0] * case.nd), np.array([1.0 + 0.5 * d for d in range(case.nd)])
+        edges = (finish - start) / np.array(case.n)
+        assert np.allclose(dx, np.prod(edges) ** (1 / case.nd) / case.np, rtol=1e-13)
+    if case.eq == "adv":
+        want = np.min(cfl * dx / np.linalg.norm(case.a))
+    else:
+        rho, E = Q[:, 0], Q[:, case.nd + 1]
+        vel = Q[:, 1:case.nd + 1] / rho[:, None]
+        p = (case.gamma - 1) * (E - 0.5 * rho * np.sum(vel ** 2, axis=1))
+        want = np.min(cfl * dx / (np.sqrt(np.sum(vel ** 2, axis=1)) + np.sqrt(case.gamma * p / rho)))
+    assert abs(orc.max_dt(Q, cfl) / want - 1) <= 1e-13

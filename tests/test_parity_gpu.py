@@ -176,6 +176,26 @@ def test_sod_tube_kat_on_gpu(gpu):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    Case(1, (9,), 4), Case(2, (5, 4), 5), Case(3, (3, 2, 3), 4), Case(3, (2, 2, 2), 5, perturb_amp=0.08),
+    Case(2, (4, 3), 6, perturb_amp=0.1),
+    Case(2, (6, 5), 4, nodes="GL", eq="adv", op="strong", nf="lxf", avg="std"),
+], ids=repr)
+def test_max_dt_matches_oracle(gpu, case):
+    """Row f1: get_max_dt as a device reduction (host state and device-resident state)."""
+    import flou_b200 as F
+    orc = case.oracle()
+    disc, eq = case.product()
+    Q = random_state(orc.ndof, case.nd, case.eq, amp=case.amp)
+    want = orc.max_dt(Q, 0.4)
+    got = F.get_max_dt(Q, disc, eq, 0.4)
+    assert abs(got / want - 1) <= 1e-14
+    disc.upload(Q)
+    assert F.get_max_dt(None, disc, eq, 0.4) == got
+    disc.close()
+
+
+@pytest.mark.gpu
 def test_domain_error_is_reported(gpu):
     import flou_b200 as F
     case = Case(2, (3, 3), 4, eq="euler", op="split", nf="mat", avg="cha")
