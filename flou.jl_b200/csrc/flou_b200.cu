@@ -346,6 +346,7 @@ struct flou_b200_handle {
     int equation = 0;
     // two-kernel path
     bool split_faces = true;
+    bool line_kernel = true;             // element kernel of the two-kernel stage: line per thread
     FaceRec *faces = nullptr;
     int2 *econn = nullptr;
     double *Fn = nullptr;
@@ -400,7 +401,7 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
             }
             CUDA_TRY(h->stage->launch_faces(P, h->stream));
             if (h->profile) CUDA_TRY(cudaEventRecord(ev[1], h->stream));
-            CUDA_TRY(h->stage->launch_elements(P, h->stream));
+            CUDA_TRY((h->line_kernel ? h->stage->launch_lines : h->stage->launch_elements)(P, h->stream));
             if (h->profile) CUDA_TRY(cudaEventRecord(ev[2], h->stream));
             h->launches += 2;
         } else {
@@ -440,7 +441,7 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
         P.elem_first = 0;
         P.elem_count = (int)h->ne_local;
         P.elem_list = nullptr;
-        CUDA_TRY(h->stage->launch_elements(P, h->stream));
+        CUDA_TRY((h->line_kernel ? h->stage->launch_lines : h->stage->launch_elements)(P, h->stream));
         h->launches += 3;
         if (mode != MODE_RHS) h->traces_valid = out_traces;
         return FLOU_B200_OK;
@@ -593,6 +594,16 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         if (std::fabs(d->lminus[i] - em) > 1e-13 || std::fabs(d->lplus[i] - ep) > 1e-13) colloc = false;
     }
     P.colloc = colloc ? 1 : 0;
+    {
+        // split form: the diagonal of D# is analytically zero on GLL nodes; the reference carries
+        // round-off there (<= 4e-13 at np = 8, 1e-14 relative to max|D#|).  Entries below
+        // 1e-12 max|D| are skipped by the line kernel.
+        double dmax = 0.0;
+        for (int i = 0; i < np * np; i++) dmax = std::max(dmax, std::fabs(Dvol[i]));
+        P.diag_mask = 0;
+        for (int j = 0; j < np; j++)
+            if (std::fabs(Dvol[j + np * j]) > 1e-12 * dmax) P.diag_mask |= 1 << j;
+    }
     h->colloc = colloc;
     if (colloc) {
         // GLL: l(-1) = e_1 and l(+1) = e_np up to the reference's monomial round-off
@@ -621,6 +632,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
             P.cmet[2] = d->dx[0] * d->dx[1] / 4;
             for (int c = 0; c < 3; c++) P.cfjac[c] = P.cmet[c];
         }
+        for (int c = 0; c < nd; c++) P.rcmet[c] = 1.0 / P.cmet[c];
     }
 
 #define H_TRY(expr)                                                                            \
@@ -635,6 +647,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
 
     H_TRY(upload(&h->conn, conn));
     h->split_faces = !(d->flags & FLOU_B200_FLAG_FUSED);
+    h->line_kernel = h->split_faces && !(d->flags & FLOU_B200_FLAG_NODE_KERNEL);
     h->n_faces = (int)pl.faces.size();
     h->n_faces_local_only = pl.n_faces_local_only;
     H_TRY(upload(&h->faces, pl.faces));
@@ -969,9 +982,9 @@ int32_t flou_b200_kernel_info(flou_b200_handle *h, int32_t *grid_ctas, int32_t *
     if (!h) return fail(FLOU_B200_EINVAL, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     if (grid_ctas) *grid_ctas = h->stage->resident();
-    if (threads) *threads = h->stage->threads;
-    if (smem_bytes) *smem_bytes = (int32_t)h->stage->smem;
-    if (elems_per_cta_iter) *elems_per_cta_iter = h->stage->epb;
+    if (threads) *threads = h->line_kernel ? h->stage->line_t : h->stage->threads;
+    if (smem_bytes) *smem_bytes = (int32_t)(h->line_kernel ? h->stage->line_smem : h->stage->smem);
+    if (elems_per_cta_iter) *elems_per_cta_iter = h->line_kernel ? h->stage->line_e : h->stage->epb;
     return FLOU_B200_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include "launch.h"
 #include "face_kernel.cuh"
+#include "line_kernel.cuh"
 #ifdef FLOU_WS      // experimental warp-specialised persistent variant (slower, see profiles/)
 #include "stage_kernel_ws.cuh"
 #endif
@@ -20,6 +21,8 @@ namespace flou {
 
 template <class C>
 static int resident_ctas();
+template <class C>
+static cudaError_t line_prepare();
 
 template <class C>
 static cudaError_t do_prepare()
@@ -38,7 +41,7 @@ static cudaError_t do_prepare()
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     resident_ctas<C>();      // occupancy query outside any stream capture
-    return cudaSuccess;
+    return line_prepare<C>();
 }
 
 // persistent grid: (CTAs that fit per SM) x (SM count), queried once per kernel instance
@@ -72,6 +75,51 @@ static cudaError_t do_launch_elements(const KParams &P, cudaStream_t s)
     if (P.elem_count <= 0) return cudaSuccess;
     const int grid = (P.elem_count + C::EPB - 1) / C::EPB;
     stage_kernel<C, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(P);
+    return cudaGetLastError();
+}
+
+// ---- line-per-thread element kernel (default element kernel of the two-kernel stage)
+template <class C>
+using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART>;
+
+template <class C>
+static int line_resident_ctas()
+{
+    static int n = 0;
+    if (n == 0) {
+        using L = LineOf<C>;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, line_kernel<L>, L::T, L::SMEM_BYTES);
+        n = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    }
+    return n;
+}
+
+template <class C>
+static cudaError_t line_prepare()
+{
+    using L = LineOf<C>;
+    cudaError_t e = cudaFuncSetAttribute(line_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)L::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(line_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    line_resident_ctas<C>();
+    return cudaSuccess;
+}
+
+template <class C>
+static cudaError_t do_launch_lines(const KParams &P0, cudaStream_t s)
+{
+    using L = LineOf<C>;
+    if (P0.elem_count <= 0) return cudaSuccess;
+    KParams P = P0;
+    const int grid = (P.elem_count + L::E - 1) / L::E;
+    P.prefetch_groups = line_resident_ctas<C>();
+    line_kernel<L><<<grid, L::T, L::SMEM_BYTES, s>>>(P);
     return cudaGetLastError();
 }
 
@@ -131,11 +179,13 @@ template <class C>
 static constexpr StageLauncher make()
 {
 #ifdef FLOU_WS
-    return StageLauncher{&ws_launch<C>, &do_launch_elements<C>, &do_launch_faces<C>, &ws_prepare<C>,
-                         &ws_resident_ctas<C>, C::EPB, WSCfg<C>::THREADS, WSCfg<C>::SMEM_BYTES};
+    return StageLauncher{&ws_launch<C>, &do_launch_elements<C>, &do_launch_lines<C>, &do_launch_faces<C>, &ws_prepare<C>,
+                         &ws_resident_ctas<C>, C::EPB, WSCfg<C>::THREADS, WSCfg<C>::SMEM_BYTES,
+                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES};
 #else
-    return StageLauncher{&do_launch<C>, &do_launch_elements<C>, &do_launch_faces<C>, &do_prepare<C>,
-                         &resident_ctas<C>, C::EPB, C::THREADS, C::SMEM_BYTES};
+    return StageLauncher{&do_launch<C>, &do_launch_elements<C>, &do_launch_lines<C>, &do_launch_faces<C>, &do_prepare<C>,
+                         &resident_ctas<C>, C::EPB, C::THREADS, C::SMEM_BYTES,
+                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES};
 #endif
 }
 
@@ -147,7 +197,7 @@ static const StageLauncher table[2][3][2] = {
     {   // linear advection: strong, split (StdAverage two-point flux); no Chandrasekhar
         {make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, true>>()},
-        {StageLauncher{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0}, StageLauncher{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0}},
+        {StageLauncher{}, StageLauncher{}},
     },
     {   // Euler
         {make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, true>>()},

@@ -7,12 +7,15 @@ namespace flou {
 
 struct StageLauncher {
     cudaError_t (*launch)(const KParams &, cudaStream_t);         // fused single-kernel stage
-    cudaError_t (*launch_elements)(const KParams &, cudaStream_t); // two-kernel path: volume+lift+RK
+    cudaError_t (*launch_elements)(const KParams &, cudaStream_t); // two-kernel path: volume+lift+RK, node per thread
+    cudaError_t (*launch_lines)(const KParams &, cudaStream_t);    // two-kernel path: volume+lift+RK, line per thread
     cudaError_t (*launch_faces)(const KParams &, cudaStream_t);    // two-kernel path: Riemann fluxes
     cudaError_t (*prepare)();
     int (*resident)();          // persistent grid size (CTAs per SM x SMs)
     int epb, threads;
     size_t smem;
+    int line_e, line_t;         // line kernel: elements and threads per CTA
+    size_t line_smem;
 };
 
 struct EmitLauncher {

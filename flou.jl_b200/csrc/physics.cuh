@@ -65,7 +65,7 @@ __device__ __forceinline__ void logmean_F2(double a1, double a2, double ia, doub
     const double ua = fa * fa, ub = fb * fb;
     Fa = 1.0 + ua * (1.0 / 3.0 + ua * (1.0 / 5.0 + ua * (1.0 / 7.0)));
     Fb = 1.0 + ub * (1.0 / 3.0 + ub * (1.0 / 5.0 + ub * (1.0 / 7.0)));
-    if (fmax(ua, ub) >= 0.01) {
+    if (ua >= 0.01 || ub >= 0.01) {
         if (ua >= 0.01) Fa = logmean_F_slow(a1, a2, fa);
         if (ub >= 0.01) Fb = logmean_F_slow(b1, b2, fb);
     }

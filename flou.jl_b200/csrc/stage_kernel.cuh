@@ -84,6 +84,9 @@ struct KParams {
     double crjac;               // 1/cjac
     double cmet[3];             // metric diagonal  Ja^d_d
     double cfjac[3];            // face jac by direction
+    double rcmet[3];            // 1/cmet (line kernel: lift pre-division in the folded split form)
+    int diag_mask;              // bit j: |Dvol[j,j]| is not round-off (line kernel, split form)
+    int prefetch_groups;        // line kernel: CTAs resident on the device (L2 prefetch distance)
     // general geometry, device SoA
     const double *jac;          // [dof]
     const double *metric;       // [(c + nd*d)][dof]  (plane-major)

@@ -19,6 +19,7 @@ BC_INFLOW, BC_OUTFLOW, BC_SLIP, BC_TABLE = range(4)
 GEOM_CARTESIAN, GEOM_GENERAL = 0, 1
 FLAG_NO_GRAPH = 1
 FLAG_FUSED = 2
+FLAG_NODE_KERNEL = 4
 
 
 class DomainError(ArithmeticError):

@@ -137,7 +137,9 @@ class MultielementDisc:
         import os as _os
         if fused is None:
             fused = _os.environ.get("FLOU_B200_FUSED", "0") == "1"
-        d.flags = (0 if use_graph else L.FLAG_NO_GRAPH) | (L.FLAG_FUSED if fused else 0)
+        node_kernel = _os.environ.get("FLOU_B200_NODE_KERNEL", "0") == "1"     # A/B switch
+        d.flags = ((0 if use_graph else L.FLAG_NO_GRAPH) | (L.FLAG_FUSED if fused else 0)
+                   | (L.FLAG_NODE_KERNEL if node_kernel else 0))
         self._h = C.c_void_p()
         if create:
             L.check(L.lib().flou_b200_create(C.byref(d), C.byref(self._h)))

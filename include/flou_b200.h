@@ -141,6 +141,8 @@ typedef struct flou_b200_desc {
 #define FLOU_B200_FLAG_NO_GRAPH 1  /* launch stages directly instead of replaying a CUDA graph */
 #define FLOU_B200_FLAG_FUSED    2  /* single fused stage kernel (both neighbours recompute each
                                       face flux) instead of face-flux kernel + element kernel */
+#define FLOU_B200_FLAG_NODE_KERNEL 4 /* two-kernel stage with the node-per-thread element kernel
+                                      instead of the default line-per-thread one (A/B testing) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */
 /* Replaces MultielementDisc(...) + construct_cache (Hyperbolic.jl:21-29): uploads tables,
