@@ -117,8 +117,9 @@ static cudaError_t do_launch_lines(const KParams &P0, cudaStream_t s)
     using L = LineOf<C>;
     if (P0.elem_count <= 0) return cudaSuccess;
     KParams P = P0;
-    const int grid = (P.elem_count + L::E - 1) / L::E;
-    P.prefetch_groups = line_resident_ctas<C>();
+    const int ngroups = (P.elem_count + L::E - 1) / L::E;
+    const int resident = line_resident_ctas<C>();
+    const int grid = ngroups < resident ? ngroups : resident;      // persistent CTAs
     line_kernel<L><<<grid, L::T, L::SMEM_BYTES, s>>>(P);
     return cudaGetLastError();
 }

@@ -1,4 +1,5 @@
-// Element kernel of the two-kernel RK stage, LINE-PER-THREAD formulation.
+// Element kernel of the two-kernel RK stage, LINE-PER-THREAD formulation, persistent CTAs with an
+// asynchronous-copy pipeline.
 //
 //   k = volume(u_in) + lift(Fn);  k /= jac;  tmp = A*tmp + dt*k;  u_out = u_in + B*tmp
 //
@@ -15,16 +16,22 @@
 // one third of the shared-memory traffic of the node-per-thread kernel (which ncu showed to be
 // bound by the shared-memory pipe at 83 % L1TEX, profiles/r1_kernel_notes.md).
 //
-// Phases of a CTA (E consecutive elements, T threads):
-//   1. node tasks:  load u_in, node primitives -> shared memory (NAUX planes per element)
-//   2. line tasks:  (element, direction, line) -> partial sums, one plane set per direction
-//   3. node tasks:  sum the ND partial sums, 1/jac, RK update, x-face traces of u_out
+// A CTA (T threads) walks over groups of E consecutive elements, g = blockIdx.x, +gridDim.x, ...:
+//   phase 1  node tasks:  state of group g (already in shared memory) -> node primitives
+//   barrier
+//   issue    cp.async: face fluxes of group g, tmp of group g, STATE OF THE NEXT GROUP
+//   phase 2  line tasks:  (element, direction, line) -> partial sums, one plane set per direction
+//   barrier
+//   phase 3  node tasks:  sum the ND partial sums, 1/jac, RK update, x-face traces of u_out
+// so every global load of the kernel is in flight behind the flux arithmetic of phase 2 (the
+// first, non-pipelined line kernel spent 45 % of its stall samples on long-scoreboard waits).
 #pragma once
 #include "stage_kernel.cuh"
 
 namespace flou {
 
 struct ETPick { int e, t; };
+
 
 // elements per CTA / threads per CTA: maximise the lane utilisation of the line phase
 constexpr ETPick pick_et(int nlines, int per_elem_doubles)
@@ -36,7 +43,7 @@ constexpr ETPick pick_et(int nlines, int per_elem_doubles)
         const int t = ts[q];
         int e = t / nlines;
         if (e < 1) e = 1;
-        const int emax = (48 * 1024 / 8) / per_elem_doubles;     // <= 48 KB of shared memory per CTA
+        const int emax = (96 * 1024 / 8) / per_elem_doubles;     // <= 96 KB of shared memory per CTA
         if (e > emax) e = emax < 1 ? 1 : emax;
         if (e > 64) e = 64;
         const int rounds = (e * nlines + t - 1) / t;
@@ -63,13 +70,25 @@ struct LCfg {
     static constexpr int NAUX = (EQ == EQ_ADV) ? (SPLIT ? 1 : ND)
                               : (VOL == VOL_SPLIT_CHA ? ND + 2 : (VOL == VOL_SPLIT_STD ? NV + ND + 1 : ND * NV));
     static constexpr int NPART = ND * NV;
-    static constexpr int PER_ELEM = (NAUX + NPART) * NPTS;
+    // shared memory per element (doubles): state x2 (this group / next group), tmp, node data,
+    // partial sums, face fluxes + signs of every line
+    static constexpr int PER_ELEM = (3 * NV + NAUX + NPART) * NPTS + (2 * NV + 2) * NLINES;
 #if defined(FLOU_LINE_E) && defined(FLOU_LINE_T)
     static constexpr int E = FLOU_LINE_E, T = FLOU_LINE_T;
 #else
     static constexpr int E = pick_et(NLINES, PER_ELEM).e, T = pick_et(NLINES, PER_ELEM).t;
 #endif
-    static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)E * PER_ELEM;
+    static constexpr int N = E * NPTS;                    // nodes of a group = plane stride
+    static constexpr int L = E * NLINES;                  // line tasks of a group
+    static constexpr int ROUNDS = (L + T - 1) / T;
+    static constexpr int LT = ROUNDS * T;
+    static constexpr bool ONE_ROUND = (ROUNDS == 1);
+    static constexpr int OFF_U = 0;                       // [2][NV][N]  state of this / the next group
+    static constexpr int OFF_T = OFF_U + 2 * NV * N;      // [NV][N]     tmp
+    static constexpr int OFF_A = OFF_T + NV * N;          // [NAUX][N]   node data
+    static constexpr int OFF_P = OFF_A + NAUX * N;        // [ND*NV][N]  partial sums by direction
+    static constexpr int OFF_F = OFF_P + NPART * N;       // [2*NV + 2][LT]  face fluxes and signs by line
+    static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OFF_F + (2 * NV + 2) * LT);
     // registers: a line task holds NP nodes and NP*NV accumulators
     static constexpr int MINB =
 #ifdef FLOU_LINE_MINB
@@ -82,16 +101,19 @@ struct LCfg {
 // ------------------------------------------------------------------ two-point fluxes of a line
 // Chandrasekhar two-point flux (Equations/Euler.jl:474-536) along the (permuted) axis 0 with a
 // unit metric; node data (rho, v/2, beta).  -|v1|^2/4 - |v2|^2/4 + |v_avg|^2 = 2 (v1/2).(v2/2).
-template <int ND>
+// FAST: branch-free (series-only logarithmic means), `redo` is raised when a jump is too large for
+// the series -- ten such fluxes then form one basic block the scheduler can interleave.
+template <int ND, bool FAST>
 __device__ __forceinline__ void tp_cha_axis(double r1, const double *hv1, double b1,
                                             double r2, const double *hv2, double b2,
-                                            double inv_gm1, double *F)
+                                            double inv_gm1, double *F, bool &redo)
 {
     const double rs = r1 + r2, bs = b1 + b2;
     const double irb = fast_rcp(rs * bs);
     const double irs = irb * bs, ibs = irb * rs;
     double Fr, Fb;
-    logmean_F2(r1, r2, irs, b1, b2, ibs, Fr, Fb);
+    if (FAST) redo |= logmean_F2_series(r1, r2, irs, b1, b2, ibs, Fr, Fb);
+    else logmean_F2(r1, r2, irs, b1, b2, ibs, Fr, Fb);
     const double rho = 0.5 * rs * fast_rcp(Fr);
     const double p = rs * ibs * 0.5;
     double vavg[ND], dot = hv1[0] * hv2[0];
@@ -109,16 +131,17 @@ __device__ __forceinline__ void tp_cha_axis(double r1, const double *hv1, double
 }
 
 // the same contracted with a general metric vector n (curved / unstructured elements)
-template <int ND>
+template <int ND, bool FAST>
 __device__ __forceinline__ void tp_cha_n(double r1, const double *hv1, double b1,
                                          double r2, const double *hv2, double b2,
-                                         double inv_gm1, const double *n, double *F)
+                                         double inv_gm1, const double *n, double *F, bool &redo)
 {
     const double rs = r1 + r2, bs = b1 + b2;
     const double irb = fast_rcp(rs * bs);
     const double irs = irb * bs, ibs = irb * rs;
     double Fr, Fb;
-    logmean_F2(r1, r2, irs, b1, b2, ibs, Fr, Fb);
+    if (FAST) redo |= logmean_F2_series(r1, r2, irs, b1, b2, ibs, Fr, Fb);
+    else logmean_F2(r1, r2, irs, b1, b2, ibs, Fr, Fb);
     const double rho = 0.5 * rs * fast_rcp(Fr);
     const double p = rs * ibs * 0.5;
     double vavg[ND], dot = hv1[0] * hv2[0], vn = 0.0;
@@ -153,145 +176,92 @@ __device__ __forceinline__ void diag_cha_n(double r, const double *hv, double b,
     F[ND + 1] = mdot * h;
 }
 
-// ------------------------------------------------------------------ the kernel
-template <class C>
-__global__ void __launch_bounds__(C::T, C::MINB)
-line_kernel(const __grid_constant__ KParams P)
+// Pair (J, L) of a line and, recursively, every pair after it: template recursion instead of
+// `#pragma unroll` so that every array index is a compile-time constant (nvcc declined to unroll
+// the equivalent double loop and moved the node data to local memory).
+template <class C, bool FAST, int J, int L>
+__device__ __forceinline__ void cha_pair_rec(const KParams &P, const double (&r)[C::NP], const double (&hv)[C::NP][C::ND],
+                                             const double (&b)[C::NP],
+                                             const double (&mt)[C::CART ? 1 : C::NP][C::CART ? 1 : C::ND],
+                                             double (&a_)[C::NP][C::NV], bool &redo)
 {
-    constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
-    constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NLINES = C::NLINES;
-    constexpr int E = C::E, T = C::T, NAUX = C::NAUX;
-    constexpr bool CART = C::CART, SPLIT = C::SPLIT, FOLD = C::FOLD;
-
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x;
-    const int g = blockIdx.x;
-    const int nact = min(E, P.elem_count - g * E);
-    const int64_t ndof = P.ndof;
-    auto elem_of = [&](int idx) { return P.elem_list ? P.elem_list[idx] : P.elem_first + idx; };
-
-    // The two face fluxes at the ends of a line (surface_contribution!): Fn is the master-outward
-    // flux in the master's face-dof order.  With one line task per thread the connectivity is
-    // requested before phase 1 and the fluxes before the barrier, so both latencies hide behind
-    // phase 1 and the volume work; they are consumed last.
-    constexpr bool ONE_ROUND = (E * NLINES <= T);
-    auto get_ec = [&](int task, int2 &ecL, int2 &ecR) {
-        const int el = task / NLINES, r_ = task - el * NLINES;
-        const int d = r_ / NFP;
-        const int e = elem_of(g * E + el);
-        ecL = __ldg(P.econn + ((int64_t)e * NFACES + 2 * d));
-        ecR = __ldg(P.econn + ((int64_t)e * NFACES + 2 * d + 1));
-    };
-    auto get_fn = [&](int task, int2 ecL, int2 ecR, double (&FnL)[NV], double (&FnR)[NV], double &sgL, double &sgR) {
-        const int r_ = task % NLINES;
-        const int d = r_ / NFP, k = r_ - d * NFP;
-        const int iL = (ecL.y & 1) ? k : slave2master<ND, NP>(k, (ecL.y >> 1) & 7);
-        const int iR = (ecR.y & 1) ? k : slave2master<ND, NP>(k, (ecR.y >> 1) & 7);
-        const double *sL = P.Fn + (int64_t)ecL.x * (NV * NFP) + iL;
-        const double *sR = P.Fn + (int64_t)ecR.x * (NV * NFP) + iR;
+    constexpr int ND = C::ND, NP = C::NP, NV = C::NV;
+    if constexpr (L < NP) {
+        double F[NV];
+        if constexpr (C::CART) {
+            tp_cha_axis<ND, FAST>(r[J], hv[J], b[J], r[L], hv[L], b[L], P.fp.inv_gm1, F, redo);
+        } else {
+            double n[ND];
+#pragma unroll
+            for (int c = 0; c < ND; c++) n[c] = 0.5 * (mt[J][c] + mt[L][c]);
+            tp_cha_n<ND, FAST>(r[J], hv[J], b[J], r[L], hv[L], b[L], P.fp.inv_gm1, n, F, redo);
+        }
+        const double djl = P.Dvol[J + NP * L], dlj = P.Dvol[L + NP * J];
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-            // FOLD mode handles the momentum components in cyclic order starting at d
-            int vv = v;
-            if (FOLD && EQ == EQ_EULER && v >= 1 && v <= ND) { const int s_ = d + v - 1; vv = 1 + (s_ >= ND ? s_ - ND : s_); }
-            FnL[v] = __ldg(sL + vv * NFP);
-            FnR[v] = __ldg(sR + vv * NFP);
+            a_[J][v] = fma(-djl, F[v], a_[J][v]);
+            a_[L][v] = fma(-dlj, F[v], a_[L][v]);
         }
-        sgL = (ecL.y & 1) ? 1.0 : -1.0;
-        sgR = (ecR.y & 1) ? 1.0 : -1.0;
-    };
-    const bool has_task = ONE_ROUND && tid < nact * NLINES;
-    int2 ec0L = make_int2(0, 0), ec0R = make_int2(0, 0);
-    double Fn0L[NV], Fn0R[NV], sg0L = 1.0, sg0R = 1.0;
-    if (has_task) get_ec(tid, ec0L, ec0R);
+        if constexpr (L + 1 < NP) cha_pair_rec<C, FAST, J, L + 1>(P, r, hv, b, mt, a_, redo);
+        else if constexpr (J + 2 < NP) cha_pair_rec<C, FAST, J + 1, J + 2>(P, r, hv, b, mt, a_, redo);
+    }
+}
 
-    // ---------------- phase 1: node primitives -> shared memory
-    for (int n = tid; n < nact * NPTS; n += T) {
-        const int el = n / NPTS, node = n - el * NPTS;
-        const int e = elem_of(g * E + el);
-        const int64_t dof = (int64_t)e * NPTS + node;
-        double *ax = smem + (size_t)el * C::PER_ELEM;
-        double Q[NV];
+// All NP(NP-1)/2 Chandrasekhar pair fluxes of one line, applied with D# to both partners.
+// FAST = branch-free; returns true when some density or beta ratio is outside the series range
+// of the logarithmic mean, in which case the caller redoes the line with FAST = false.
+template <class C, bool FAST>
+__device__ __forceinline__ bool cha_pairs(const KParams &P, const double (&r)[C::NP], const double (&hv)[C::NP][C::ND],
+                                          const double (&b)[C::NP],
+                                          const double (&mt)[C::CART ? 1 : C::NP][C::CART ? 1 : C::ND],
+                                          double (&a_)[C::NP][C::NV])
+{
+    constexpr int ND = C::ND, NP = C::NP, NV = C::NV;
+    bool redo = false;
+    // the diagonal of D# is analytically zero on GLL nodes; when the host found entries that are
+    // not round-off (diag_mask), the line goes to the exact path, which applies them
+    if (FAST) {
+        if (P.diag_mask) return true;
+    } else {
 #pragma unroll
-        for (int v = 0; v < NV; v++) Q[v] = __ldg(P.u_in + dof + ndof * v);
-        double met[(CART || SPLIT) ? 1 : ND * ND];
-        if (!CART && !SPLIT) {
+        for (int j = 0; j < NP; j++) {
+            if (P.diag_mask & (1 << j)) {
+                double n[ND], F[NV];
 #pragma unroll
-            for (int m = 0; m < ND * ND; m++) met[m] = __ldg(P.metric + dof + ndof * m);
-        }
-        if (EQ == EQ_EULER) {
-            NodeAux<ND> A;
-            node_aux<ND>(Q, P.fp.gamma, A);
-            if (!(Q[0] > 0.0) || !(A.p > 0.0)) atomicOr(P.status, 1);
-            if (VOL == VOL_SPLIT_CHA) {
-                ax[node] = Q[0];
+                for (int c = 0; c < ND; c++) n[c] = C::CART ? (c == 0 ? 1.0 : 0.0) : mt[C::CART ? 0 : j][C::CART ? 0 : c];
+                diag_cha_n<ND>(r[j], hv[j], b[j], P.fp.inv_gm1, n, F);
+                const double djj = P.Dvol[j + NP * j];
 #pragma unroll
-                for (int c = 0; c < ND; c++) ax[(1 + c) * NPTS + node] = 0.5 * A.vel[c];
-                ax[(ND + 1) * NPTS + node] = A.beta;
-            } else if (VOL == VOL_SPLIT_STD) {
-#pragma unroll
-                for (int v = 0; v < NV; v++) ax[v * NPTS + node] = Q[v];
-#pragma unroll
-                for (int c = 0; c < ND; c++) ax[(NV + c) * NPTS + node] = A.vel[c];
-                ax[(NV + ND) * NPTS + node] = A.p;
-            } else {
-#pragma unroll
-                for (int d = 0; d < ND; d++) {
-                    double Fc[NV], Ft[NV];
-#pragma unroll
-                    for (int v = 0; v < NV; v++) Ft[v] = 0.0;
-#pragma unroll
-                    for (int c = 0; c < ND; c++) {
-                        if (CART && c != d) continue;
-                        const double m = CART ? P.cmet[d] : met[c + ND * d];
-                        euler_flux_dir<ND>(Q, A.vel, A.p, c, Fc);
-#pragma unroll
-                        for (int v = 0; v < NV; v++) Ft[v] += Fc[v] * m;
-                    }
-#pragma unroll
-                    for (int v = 0; v < NV; v++) ax[(d * NV + v) * NPTS + node] = Ft[v];
-                }
-            }
-        } else if (SPLIT) {
-            ax[node] = Q[0];
-        } else {
-#pragma unroll
-            for (int d = 0; d < ND; d++) {
-                double an = 0.0;
-#pragma unroll
-                for (int c = 0; c < ND; c++)
-                    an += P.fp.a[c] * (CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d]);
-                ax[d * NPTS + node] = an * Q[0];
-            }
-        }
-        // warm L2 for the CTA that occupies this SM slot one wave later
-        if (P.prefetch_groups > 0 && (node & 15) == 0) {
-            const int idx = (g + P.prefetch_groups) * E + el;
-            if (idx < P.elem_count) {
-                const int64_t pd = (int64_t)elem_of(idx) * NPTS + node;
-#pragma unroll
-                for (int v = 0; v < NV; v++) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.u_in + pd + ndof * v));
-                    if (P.mode == MODE_STAGE) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.tmp + pd + ndof * v));
-                }
+                for (int v = 0; v < NV; v++) a_[j][v] = fma(-djj, F[v], a_[j][v]);
             }
         }
     }
-    if (has_task) get_fn(tid, ec0L, ec0R, Fn0L, Fn0R, sg0L, sg0R);
-    __syncthreads();
+    cha_pair_rec<C, FAST, 0, 1>(P, r, hv, b, mt, a_, redo);
+    return redo;
+}
 
-    // ---------------- phase 2: one tensor-product line per thread
-    auto line_task = [&](int task, const double (&FnL)[NV], const double (&FnR)[NV], double sgL, double sgR) {
+// One line task: volume term of the line's NP nodes in direction d plus the lift of the two face
+// fluxes at its ends, written as the partial sums of direction d.  FAST (Chandrasekhar only):
+// branch-free pair fluxes; returns true when the line has to be redone with FAST = false.
+template <class C, bool FAST>
+__device__ __forceinline__ bool line_task(const KParams &P, const double *sA, double *sP, const double *sF,
+                                          int task, int64_t dof0)
+{
+    constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
+    constexpr int NPTS = C::NPTS, NFP = C::NFP, NLINES = C::NLINES;
+    constexpr int N = C::N, LT = C::LT;
+    constexpr bool CART = C::CART, SPLIT = C::SPLIT, FOLD = C::FOLD;
+    const int64_t ndof = P.ndof;
+    bool redo = false;
         const int el = task / NLINES, r_ = task - el * NLINES;
         const int d = r_ / NFP, k = r_ - d * NFP;
-        const int e = elem_of(g * E + el);
         int base, stride;
         line_of<ND, NP>(d, k, base, stride);
-        const double *ax = smem + (size_t)el * C::PER_ELEM;
-        double *pt = smem + (size_t)el * C::PER_ELEM + (NAUX + d * NV) * NPTS;
+        base += el * NPTS;
+        double *pt = sP + (d * NV) * N;
 
-        // Cartesian split form: momentum components are handled in the cyclic order that puts the
-        // line's direction first, so the flux code is the same instruction stream for every d
+        // Cartesian split form: momentum components are handled in the cyclic order that puts
+        // the line's direction first, so the flux code is the same instruction stream for every d
         int pc[ND];
 #pragma unroll
         for (int c = 0; c < ND; c++) { const int s = d + c; pc[c] = FOLD ? (s >= ND ? s - ND : s) : c; }
@@ -309,7 +279,7 @@ line_kernel(const __grid_constant__ KParams P)
             for (int v = 0; v < NV; v++) {
                 double f[NP];
 #pragma unroll
-                for (int j = 0; j < NP; j++) f[j] = ax[(d * NV + v) * NPTS + base + j * stride];
+                for (int j = 0; j < NP; j++) f[j] = sA[(d * NV + v) * N + base + j * stride];
 #pragma unroll
                 for (int i = 0; i < NP; i++)
 #pragma unroll
@@ -323,62 +293,33 @@ line_kernel(const __grid_constant__ KParams P)
                 for (int j = 0; j < NP; j++)
 #pragma unroll
                     for (int c = 0; c < ND; c++)
-                        mt[j][c] = __ldg(P.metric + (int64_t)e * NPTS + base + j * stride + ndof * (c + ND * d));
+                        mt[j][c] = __ldg(P.metric + dof0 + base + j * stride + ndof * (c + ND * d));
             }
             if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA) {
                 double r[NP], hv[NP][ND], b[NP];
 #pragma unroll
                 for (int j = 0; j < NP; j++) {
                     const int node = base + j * stride;
-                    r[j] = ax[node];
+                    r[j] = sA[node];
 #pragma unroll
-                    for (int c = 0; c < ND; c++) hv[j][c] = ax[(1 + pc[c]) * NPTS + node];
-                    b[j] = ax[(ND + 1) * NPTS + node];
+                    for (int c = 0; c < ND; c++) hv[j][c] = sA[(1 + pc[c]) * N + node];
+                    b[j] = sA[(ND + 1) * N + node];
                 }
-#pragma unroll
-                for (int j = 0; j < NP; j++) {
-                    if (P.diag_mask & (1 << j)) {
-                        double n[ND], F[NV];
-#pragma unroll
-                        for (int c = 0; c < ND; c++) n[c] = CART ? (c == 0 ? 1.0 : 0.0) : mt[j][c];
-                        diag_cha_n<ND>(r[j], hv[j], b[j], P.fp.inv_gm1, n, F);
-                        const double djj = P.Dvol[j + NP * j];
-#pragma unroll
-                        for (int v = 0; v < NV; v++) acc[j][v] = fma(-djj, F[v], acc[j][v]);
-                    }
-#pragma unroll
-                    for (int l = j + 1; l < NP; l++) {
-                        double F[NV];
-                        if (CART) {
-                            tp_cha_axis<ND>(r[j], hv[j], b[j], r[l], hv[l], b[l], P.fp.inv_gm1, F);
-                        } else {
-                            double n[ND];
-#pragma unroll
-                            for (int c = 0; c < ND; c++) n[c] = 0.5 * (mt[j][c] + mt[l][c]);
-                            tp_cha_n<ND>(r[j], hv[j], b[j], r[l], hv[l], b[l], P.fp.inv_gm1, n, F);
-                        }
-                        const double djl = P.Dvol[j + NP * l], dlj = P.Dvol[l + NP * j];
-#pragma unroll
-                        for (int v = 0; v < NV; v++) {
-                            acc[j][v] = fma(-djl, F[v], acc[j][v]);
-                            acc[l][v] = fma(-dlj, F[v], acc[l][v]);
-                        }
-                    }
-                }
+                redo = cha_pairs<C, FAST>(P, r, hv, b, mt, acc);
             } else if (EQ == EQ_EULER) {
                 // StdAverage two-point flux (Equations/Euler.jl:385-472); node data (Q, v, p)
                 double Qj[NP][NV], vj[NP][ND], pj[NP];
 #pragma unroll
                 for (int j = 0; j < NP; j++) {
                     const int node = base + j * stride;
-                    Qj[j][0] = ax[node];
+                    Qj[j][0] = sA[node];
 #pragma unroll
                     for (int c = 0; c < ND; c++) {
-                        Qj[j][1 + c] = ax[(1 + pc[c]) * NPTS + node];
-                        vj[j][c] = ax[(NV + pc[c]) * NPTS + node];
+                        Qj[j][1 + c] = sA[(1 + pc[c]) * N + node];
+                        vj[j][c] = sA[(NV + pc[c]) * N + node];
                     }
-                    Qj[j][ND + 1] = ax[(ND + 1) * NPTS + node];
-                    pj[j] = ax[(NV + ND) * NPTS + node];
+                    Qj[j][ND + 1] = sA[(ND + 1) * N + node];
+                    pj[j] = sA[(NV + ND) * N + node];
                 }
 #pragma unroll
                 for (int j = 0; j < NP; j++)
@@ -400,7 +341,7 @@ line_kernel(const __grid_constant__ KParams P)
                 // linear advection (Equations/LinearAdvection.jl:44-47)
                 double q[NP];
 #pragma unroll
-                for (int j = 0; j < NP; j++) q[j] = ax[base + j * stride];
+                for (int j = 0; j < NP; j++) q[j] = sA[base + j * stride];
                 const double ad = pick<ND>(P.fp.a, d);
 #pragma unroll
                 for (int j = 0; j < NP; j++)
@@ -422,20 +363,27 @@ line_kernel(const __grid_constant__ KParams P)
 
         // lift of the two face fluxes (OpDivergence.jl:42-100); in FOLD mode the partial sum is
         // later multiplied by the metric factor of direction d, so the lift is pre-divided by it
+        cp_async_wait<0>();
         {
             const double rm = FOLD ? pick<ND>(P.rcmet, d) : 1.0;
-            const double wl = sgL * rm, wr = sgR * rm;
+            const double wl = sF[(2 * NV) * LT + task] * rm, wr = sF[(2 * NV + 1) * LT + task] * rm;
+            if (P.colloc) {
+                // GLL: only the two end nodes of the line see the face fluxes
+                const double w0 = P.dgl[0] * wl, w1 = P.dgr[NP - 1] * wr;
 #pragma unroll
-            for (int j = 0; j < NP; j++) {
-                if (P.dgl[j] != 0.0) {
-                    const double w = P.dgl[j] * wl;
-#pragma unroll
-                    for (int v = 0; v < NV; v++) acc[j][v] = fma(-w, FnL[v], acc[j][v]);
+                for (int v = 0; v < NV; v++) {
+                    acc[0][v] = fma(-w0, sF[v * LT + task], acc[0][v]);
+                    acc[NP - 1][v] = fma(-w1, sF[(NV + v) * LT + task], acc[NP - 1][v]);
                 }
-                if (P.dgr[j] != 0.0) {
-                    const double w = P.dgr[j] * wr;
+            } else {
 #pragma unroll
-                    for (int v = 0; v < NV; v++) acc[j][v] = fma(-w, FnR[v], acc[j][v]);
+                for (int j = 0; j < NP; j++) {
+                    const double w0 = P.dgl[j] * wl, w1 = P.dgr[j] * wr;
+#pragma unroll
+                    for (int v = 0; v < NV; v++) {
+                        acc[j][v] = fma(-w0, sF[v * LT + task], acc[j][v]);
+                        acc[j][v] = fma(-w1, sF[(NV + v) * LT + task], acc[j][v]);
+                    }
                 }
             }
         }
@@ -444,73 +392,237 @@ line_kernel(const __grid_constant__ KParams P)
         for (int j = 0; j < NP; j++) {
             const int node = base + j * stride;
 #pragma unroll
-            for (int v = 0; v < NV; v++) pt[var_of(v) * NPTS + node] = acc[j][v];
+            for (int v = 0; v < NV; v++) pt[var_of(v) * N + node] = acc[j][v];
+        }
+    return redo;
+}
+
+// exact redo of a line, kept out of line so that its register allocation (library log, calls) does
+// not weigh on the fast path
+template <class C>
+__device__ __noinline__ void line_task_exact(const KParams &P, const double *sA, double *sP, const double *sF,
+                                             int task, int64_t dof0)
+{
+    line_task<C, false>(P, sA, sP, sF, task, dof0);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <class C>
+__global__ void
+#ifdef FLOU_LINE_MAXREG
+__maxnreg__(FLOU_LINE_MAXREG)
+#else
+__launch_bounds__(C::T, C::MINB)
+#endif
+line_kernel(const __grid_constant__ KParams P)
+{
+    constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
+    constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NLINES = C::NLINES;
+    constexpr int E = C::E, T = C::T, N = C::N, LT = C::LT;
+    constexpr bool CART = C::CART, SPLIT = C::SPLIT, FOLD = C::FOLD, ONE_ROUND = C::ONE_ROUND;
+
+    extern __shared__ __align__(16) double lsmem[];
+    double *const smem = lsmem;
+    double *sU = smem + C::OFF_U, *sT = smem + C::OFF_T, *sA = smem + C::OFF_A;
+    double *sP = smem + C::OFF_P, *sF = smem + C::OFF_F;
+
+    const int tid = threadIdx.x;
+    const int ngroups = (P.elem_count + E - 1) / E;
+    const int64_t ndof = P.ndof;
+    const bool need_tmp = (P.mode == MODE_STAGE);
+    int g = blockIdx.x;
+    if (g >= ngroups) return;
+
+    // NV planes of the nodes of group gg: global -> shared.  16-byte copies that bypass L1
+    // (cp.async.cg) when the planes are 16-byte aligned -- the streaming data then does not evict
+    // the few local-memory lines of the kernel from L1 -- else 8-byte copies.
+    const bool wide = ((ndof & 1) == 0) && (((int64_t)P.elem_first * NPTS & 1) == 0) && ((N & 1) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(P.u_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.tmp) & 15) == 0);
+    auto issue_planes = [&](const double *src, double *dst, int gg) {
+        const int nn = min(E, P.elem_count - gg * E) * NPTS;
+        const double *s0 = src + (int64_t)(P.elem_first + gg * E) * NPTS;
+        if (wide && (nn & 1) == 0) {
+            for (int n = 2 * tid; n < nn; n += 2 * T) {
+#pragma unroll
+                for (int v = 0; v < NV; v++) cp_async16(dst + v * N + n, s0 + n + ndof * v);
+            }
+        } else {
+            for (int n = tid; n < nn; n += T) {
+#pragma unroll
+                for (int v = 0; v < NV; v++) cp_async8(dst + v * N + n, s0 + n + ndof * v);
+            }
         }
     };
-    if (ONE_ROUND) {
-        if (has_task) line_task(tid, Fn0L, Fn0R, sg0L, sg0R);
-    } else {
-        for (int task = tid; task < nact * NLINES; task += T) {
-            int2 ecL, ecR;
-            double FnL[NV], FnR[NV], sgL, sgR;
-            get_ec(task, ecL, ecR);
-            get_fn(task, ecL, ecR, FnL, FnR, sgL, sgR);
-            line_task(task, FnL, FnR, sgL, sgR);
-        }
-    }
-    __syncthreads();
-
-    // ---------------- phase 3: sum the directions, mass matrix, RK stage update
-    for (int n = tid; n < nact * NPTS; n += T) {
-        const int el = n / NPTS, node = n - el * NPTS;
-        const int e = elem_of(g * E + el);
-        const int64_t dof = (int64_t)e * NPTS + node;
-        const double *pt = smem + (size_t)el * C::PER_ELEM + NAUX * NPTS;
-        double acc[NV];
+    // connectivity of line task `task` of group gg: the two faces at the ends of the line
+    auto load_ec = [&](int gg, int task, int2 &ecL, int2 &ecR) {
+        const int el = task / NLINES, d = (task - el * NLINES) / NFP;
+        const int e = P.elem_first + gg * E + el;
+        ecL = __ldg(P.econn + ((int64_t)e * NFACES + 2 * d));
+        ecR = __ldg(P.econn + ((int64_t)e * NFACES + 2 * d + 1));
+    };
+    // face fluxes of a line (surface_contribution!): Fn is the master-outward flux in the
+    // master's face-dof order; the slave side sees it negated and permuted.  Column `task` of
+    // sF belongs to the thread that owns the line, so no barrier is needed, only wait_group.
+    auto issue_fn = [&](int task, int2 ecL, int2 ecR) {
+        const int r_ = task % NLINES;
+        const int d = r_ / NFP, k = r_ - d * NFP;
+        const int iL = (ecL.y & 1) ? k : slave2master<ND, NP>(k, (ecL.y >> 1) & 7);
+        const int iR = (ecR.y & 1) ? k : slave2master<ND, NP>(k, (ecR.y >> 1) & 7);
+        const double *sL = P.Fn + (int64_t)ecL.x * (NV * NFP) + iL;
+        const double *sR = P.Fn + (int64_t)ecR.x * (NV * NFP) + iR;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-            double s = 0.0;
-#pragma unroll
-            for (int d = 0; d < ND; d++) {
-                const double x = pt[(d * NV + v) * NPTS + node];
-                s = FOLD ? fma(P.cmet[d], x, s) : s + x;
-            }
-            acc[v] = s;
+            // FOLD mode handles the momentum components in cyclic order starting at d
+            int vv = v;
+            if (FOLD && EQ == EQ_EULER && v >= 1 && v <= ND) { const int s_ = d + v - 1; vv = 1 + (s_ >= ND ? s_ - ND : s_); }
+            cp_async8(sF + v * LT + task, sL + vv * NFP);
+            cp_async8(sF + (NV + v) * LT + task, sR + vv * NFP);
         }
-        const double rjac = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof));
-        if (P.mode == MODE_RHS) {
+        sF[(2 * NV) * LT + task] = (ecL.y & 1) ? 1.0 : -1.0;
+        sF[(2 * NV + 1) * LT + task] = (ecR.y & 1) ? 1.0 : -1.0;
+    };
+
+    // ---------------- prologue: state of the first group, connectivity of its lines
+    issue_planes(P.u_in, sU, g);
+    cp_async_commit();
+    int2 ecL = make_int2(0, 0), ecR = make_int2(0, 0);
+    if (ONE_ROUND && tid < min(E, P.elem_count - g * E) * NLINES) load_ec(g, tid, ecL, ecR);
+    cp_async_wait<0>();
+    __syncthreads();
+
+    for (int cur = 0; g < ngroups; g += gridDim.x, cur ^= 1) {
+        const int nact = min(E, P.elem_count - g * E);
+        const int nn = nact * NPTS, nl = nact * NLINES;
+        const int gn = g + gridDim.x;
+        const int64_t dof0 = (int64_t)(P.elem_first + g * E) * NPTS;
+        const double *U = sU + cur * (NV * N);
+
+        // ---------------- phase 1: node primitives -> shared memory
+        for (int n = tid; n < nn; n += T) {
+            double Q[NV];
 #pragma unroll
-            for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[v] * rjac;
+            for (int v = 0; v < NV; v++) Q[v] = U[v * N + n];
+            double met[(CART || SPLIT) ? 1 : ND * ND];
+            if (!CART && !SPLIT) {
+#pragma unroll
+                for (int m = 0; m < ND * ND; m++) met[m] = __ldg(P.metric + dof0 + n + ndof * m);
+            }
+            if (EQ == EQ_EULER) {
+                NodeAux<ND> A;
+                node_aux<ND>(Q, P.fp.gamma, A);
+                if (!(Q[0] > 0.0) || !(A.p > 0.0)) atomicOr(P.status, 1);
+                if (VOL == VOL_SPLIT_CHA) {
+                    sA[n] = Q[0];
+#pragma unroll
+                    for (int c = 0; c < ND; c++) sA[(1 + c) * N + n] = 0.5 * A.vel[c];
+                    sA[(ND + 1) * N + n] = A.beta;
+                } else if (VOL == VOL_SPLIT_STD) {
+#pragma unroll
+                    for (int v = 0; v < NV; v++) sA[v * N + n] = Q[v];
+#pragma unroll
+                    for (int c = 0; c < ND; c++) sA[(NV + c) * N + n] = A.vel[c];
+                    sA[(NV + ND) * N + n] = A.p;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < ND; d++) {
+                        double Fc[NV], Ft[NV];
+#pragma unroll
+                        for (int v = 0; v < NV; v++) Ft[v] = 0.0;
+#pragma unroll
+                        for (int c = 0; c < ND; c++) {
+                            if (CART && c != d) continue;
+                            const double m = CART ? P.cmet[d] : met[c + ND * d];
+                            euler_flux_dir<ND>(Q, A.vel, A.p, c, Fc);
+#pragma unroll
+                            for (int v = 0; v < NV; v++) Ft[v] += Fc[v] * m;
+                        }
+#pragma unroll
+                        for (int v = 0; v < NV; v++) sA[(d * NV + v) * N + n] = Ft[v];
+                    }
+                }
+            } else if (SPLIT) {
+                sA[n] = Q[0];
+            } else {
+#pragma unroll
+                for (int d = 0; d < ND; d++) {
+                    double an = 0.0;
+#pragma unroll
+                    for (int c = 0; c < ND; c++)
+                        an += P.fp.a[c] * (CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d]);
+                    sA[d * N + n] = an * Q[0];
+                }
+            }
+        }
+        __syncthreads();      // node data visible; every warp has left phase 3 of the previous group
+
+        // ---------------- issue: face fluxes and tmp of this group, state of the next group
+        if (ONE_ROUND) {
+            if (tid < nl) issue_fn(tid, ecL, ecR);
         } else {
-            // every load before the first store: tmp and u_out may alias as far as the compiler
-            // knows, and five serialised DRAM round trips were 32 % of the kernel's stall samples
-            double un[NV], tv[NV];
+            for (int task = tid; task < nl; task += T) {
+                int2 a, b;
+                load_ec(g, task, a, b);
+                issue_fn(task, a, b);
+            }
+        }
+        if (need_tmp) issue_planes(P.tmp, sT, g);
+        if (gn < ngroups) issue_planes(P.u_in, sU + (cur ^ 1) * (NV * N), gn);
+        cp_async_commit();
+
+        // ---------------- phase 2: one tensor-product line per thread
+        for (int task = tid; task < nl; task += T) {
+            if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA) {
+                if (line_task<C, true>(P, sA, sP, sF, task, dof0)) line_task_exact<C>(P, sA, sP, sF, task, dof0);
+            } else {
+                line_task<C, false>(P, sA, sP, sF, task, dof0);
+            }
+        }
+        cp_async_wait<0>();    // this thread's share of tmp and of the next state has landed
+        __syncthreads();
+
+        // connectivity of my line in the next group: in flight during phase 3 and phase 1
+        if (ONE_ROUND && gn < ngroups && tid < min(E, P.elem_count - gn * E) * NLINES) load_ec(gn, tid, ecL, ecR);
+
+        // ---------------- phase 3: sum the directions, mass matrix, RK stage update
+        for (int n = tid; n < nn; n += T) {
+            const int64_t dof = dof0 + n;
+            double acc[NV];
 #pragma unroll
             for (int v = 0; v < NV; v++) {
-                un[v] = __ldg(P.u_in + dof + ndof * v);
-                tv[v] = (P.mode == MODE_STAGE_FIRST) ? 0.0 : __ldcs(P.tmp + dof + ndof * v);
-            }
+                double s = 0.0;
 #pragma unroll
-            for (int v = 0; v < NV; v++) {
-                const double kv = acc[v] * rjac;
-                const double t = (P.mode == MODE_STAGE_FIRST) ? P.dt * kv : fma(P.dt, kv, P.rkA * tv[v]);
-                un[v] = fma(P.rkB, t, un[v]);
-                tv[v] = t;
+                for (int d = 0; d < ND; d++) {
+                    const double x = sP[(d * NV + v) * N + n];
+                    s = FOLD ? fma(P.cmet[d], x, s) : s + x;
+                }
+                acc[v] = s;
             }
+            const double rjac = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof));
+            if (P.mode == MODE_RHS) {
 #pragma unroll
-            for (int v = 0; v < NV; v++) {
-                P.tmp[dof + ndof * v] = tv[v];
-                P.u_out[dof + ndof * v] = un[v];
-            }
-            // x-face traces of the new state for the next stage (collocated nodes only; Gauss
-            // nodes are handled by emit_traces_kernel)
-            if (P.colloc) {
-                int k, ii;
-                node_line<ND, NP>(node, 0, k, ii);
-                if (ii == 0 || ii == NP - 1) {
-                    double *dst = P.tr_out + ((int64_t)e * 2 + (ii == 0 ? 0 : 1)) * (NV * NFP) + k;
+                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[v] * rjac;
+            } else {
+                double un[NV];
 #pragma unroll
-                    for (int v = 0; v < NV; v++) dst[v * NFP] = un[v];
+                for (int v = 0; v < NV; v++) {
+                    const double kv = acc[v] * rjac;
+                    const double t = need_tmp ? fma(P.dt, kv, P.rkA * sT[v * N + n]) : P.dt * kv;
+                    P.tmp[dof + ndof * v] = t;
+                    un[v] = fma(P.rkB, t, U[v * N + n]);
+                    P.u_out[dof + ndof * v] = un[v];
+                }
+                // x-face traces of the new state for the next stage (collocated nodes only; Gauss
+                // nodes are handled by emit_traces_kernel)
+                if (P.colloc) {
+                    const int el = n / NPTS, node = n - el * NPTS;
+                    int k, ii;
+                    node_line<ND, NP>(node, 0, k, ii);
+                    if (ii == 0 || ii == NP - 1) {
+                        const int64_t e = P.elem_first + g * E + el;
+                        double *dst = P.tr_out + (e * 2 + (ii == 0 ? 0 : 1)) * (NV * NFP) + k;
+#pragma unroll
+                        for (int v = 0; v < NV; v++) dst[v * NFP] = un[v];
+                    }
                 }
             }
         }

@@ -71,6 +71,18 @@ __device__ __forceinline__ void logmean_F2(double a1, double a2, double ia, doub
     }
 }
 
+// Branch-free variant for the line kernel: series only; the return value says whether either
+// argument pair lies outside the series range (the caller then redoes its work with logmean_F2).
+__device__ __forceinline__ bool logmean_F2_series(double a1, double a2, double ia, double b1, double b2,
+                                                  double ib, double &Fa, double &Fb)
+{
+    const double fa = (a1 - a2) * ia, fb = (b1 - b2) * ib;
+    const double ua = fa * fa, ub = fb * fb;
+    Fa = 1.0 + ua * (1.0 / 3.0 + ua * (1.0 / 5.0 + ua * (1.0 / 7.0)));
+    Fb = 1.0 + ub * (1.0 / 3.0 + ub * (1.0 / 5.0 + ub * (1.0 / 7.0)));
+    return (ua >= 0.01) | (ub >= 0.01);
+}
+
 static __device__ __noinline__ double log_ratio_slow(double al, double ar) { return log(al / ar); }
 
 // log(al/ar) = 2 atanh(f) from f = (al-ar)/(al+ar): 8-term series below u = f^2 < 0.01
