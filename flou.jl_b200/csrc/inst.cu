@@ -5,6 +5,7 @@
 #include "launch.h"
 #include "face_kernel.cuh"
 #include "line_kernel.cuh"
+#include "line_kernel_ws.cuh"
 #ifdef FLOU_WS      // experimental warp-specialised persistent variant (slower, see profiles/)
 #include "stage_kernel_ws.cuh"
 #endif
@@ -79,8 +80,15 @@ static cudaError_t do_launch_elements(const KParams &P, cudaStream_t s)
 }
 
 // ---- line-per-thread element kernel (default element kernel of the two-kernel stage)
+#ifdef FLOU_LINE_WS      // warp-specialised variant: TL line threads + one update warp
 template <class C>
-using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART>;
+using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, true>;
+#define FLOU_LINE_KERNEL line_kernel_ws
+#else
+template <class C>
+using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, false>;
+#define FLOU_LINE_KERNEL line_kernel
+#endif
 
 template <class C>
 static int line_resident_ctas()
@@ -91,7 +99,7 @@ static int line_resident_ctas()
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, line_kernel<L>, L::T, L::SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, FLOU_LINE_KERNEL<L>, L::T, L::SMEM_BYTES);
         n = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
     }
     return n;
@@ -101,10 +109,10 @@ template <class C>
 static cudaError_t line_prepare()
 {
     using L = LineOf<C>;
-    cudaError_t e = cudaFuncSetAttribute(line_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(FLOU_LINE_KERNEL<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)L::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(line_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(FLOU_LINE_KERNEL<L>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     line_resident_ctas<C>();
@@ -120,7 +128,7 @@ static cudaError_t do_launch_lines(const KParams &P0, cudaStream_t s)
     const int ngroups = (P.elem_count + L::E - 1) / L::E;
     const int resident = line_resident_ctas<C>();
     const int grid = ngroups < resident ? ngroups : resident;      // persistent CTAs
-    line_kernel<L><<<grid, L::T, L::SMEM_BYTES, s>>>(P);
+    FLOU_LINE_KERNEL<L><<<grid, L::T, L::SMEM_BYTES, s>>>(P);
     return cudaGetLastError();
 }
 

@@ -30,11 +30,37 @@
 
 namespace flou {
 
+// ---- mbarrier helpers (shared::cta addresses as 32-bit values)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// arrive once every cp.async this thread issued before has completed (no pending-count increment:
+// the arrival is part of the barrier's initial count)
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
 struct ETPick { int e, t; };
 
 
-// elements per CTA / threads per CTA: maximise the lane utilisation of the line phase
-constexpr ETPick pick_et(int nlines, int per_elem_doubles)
+// elements per CTA / line threads per CTA: maximise the lane utilisation of the line phase
+constexpr ETPick pick_et(int nlines, int per_elem_doubles, int max_kb)
 {
     const int ts[7] = {128, 160, 96, 192, 64, 224, 256};
     ETPick best{1, 64};
@@ -43,7 +69,7 @@ constexpr ETPick pick_et(int nlines, int per_elem_doubles)
         const int t = ts[q];
         int e = t / nlines;
         if (e < 1) e = 1;
-        const int emax = (96 * 1024 / 8) / per_elem_doubles;     // <= 96 KB of shared memory per CTA
+        const int emax = (max_kb * 1024 / 8) / per_elem_doubles;      // shared memory per CTA
         if (e > emax) e = emax < 1 ? 1 : emax;
         if (e > 64) e = 64;
         const int rounds = (e * nlines + t - 1) / t;
@@ -53,10 +79,12 @@ constexpr ETPick pick_et(int nlines, int per_elem_doubles)
     return best;
 }
 
-template <int ND_, int NP_, int EQ_, int VOL_, bool CART_>
+// WS = warp-specialised variant (line_kernel_ws.cuh): TL line threads plus one update warp, three
+// state buffers and two node-data buffers.
+template <int ND_, int NP_, int EQ_, int VOL_, bool CART_, bool WS_ = false>
 struct LCfg {
     static constexpr int ND = ND_, NP = NP_, EQ = EQ_, VOL = VOL_;
-    static constexpr bool CART = CART_;
+    static constexpr bool CART = CART_, WS = WS_;
     static constexpr int NV = (EQ == EQ_ADV) ? 1 : ND + 2;
     static constexpr int NPTS = ipow_c(NP, ND);
     static constexpr int NFP = ipow_c(NP, ND - 1);
@@ -70,25 +98,30 @@ struct LCfg {
     static constexpr int NAUX = (EQ == EQ_ADV) ? (SPLIT ? 1 : ND)
                               : (VOL == VOL_SPLIT_CHA ? ND + 2 : (VOL == VOL_SPLIT_STD ? NV + ND + 1 : ND * NV));
     static constexpr int NPART = ND * NV;
-    // shared memory per element (doubles): state x2 (this group / next group), tmp, node data,
-    // partial sums, face fluxes + signs of every line
-    static constexpr int PER_ELEM = (3 * NV + NAUX + NPART) * NPTS + (2 * NV + 2) * NLINES;
+    static constexpr int NUB = WS ? 3 : 2;                // state buffers
+    static constexpr int NAB = WS ? 2 : 1;                // node-data buffers
+    // shared memory per element (doubles): state buffers, tmp, node data, partial sums, face
+    // fluxes + signs of every line
+    static constexpr int PER_ELEM = ((NUB + 1) * NV + NAB * NAUX + NPART) * NPTS + (2 * NV + 2) * NLINES;
 #if defined(FLOU_LINE_E) && defined(FLOU_LINE_T)
-    static constexpr int E = FLOU_LINE_E, T = FLOU_LINE_T;
+    static constexpr int E = FLOU_LINE_E, TL = FLOU_LINE_T;
 #else
-    static constexpr int E = pick_et(NLINES, PER_ELEM).e, T = pick_et(NLINES, PER_ELEM).t;
+    static constexpr int E = pick_et(NLINES, PER_ELEM, WS ? 108 : 96).e, TL = pick_et(NLINES, PER_ELEM, WS ? 108 : 96).t;
 #endif
+    static constexpr int T = WS ? TL + 32 : TL;           // threads per CTA
     static constexpr int N = E * NPTS;                    // nodes of a group = plane stride
     static constexpr int L = E * NLINES;                  // line tasks of a group
-    static constexpr int ROUNDS = (L + T - 1) / T;
-    static constexpr int LT = ROUNDS * T;
+    static constexpr int ROUNDS = (L + TL - 1) / TL;
+    static constexpr int LT = ROUNDS * TL;
     static constexpr bool ONE_ROUND = (ROUNDS == 1);
-    static constexpr int OFF_U = 0;                       // [2][NV][N]  state of this / the next group
-    static constexpr int OFF_T = OFF_U + 2 * NV * N;      // [NV][N]     tmp
-    static constexpr int OFF_A = OFF_T + NV * N;          // [NAUX][N]   node data
-    static constexpr int OFF_P = OFF_A + NAUX * N;        // [ND*NV][N]  partial sums by direction
+    static constexpr int OFF_U = 0;                       // [NUB][NV][N]    state of this / the next group(s)
+    static constexpr int OFF_T = OFF_U + NUB * NV * N;    // [NV][N]         tmp
+    static constexpr int OFF_A = OFF_T + NV * N;          // [NAB][NAUX][N]  node data
+    static constexpr int OFF_P = OFF_A + NAB * NAUX * N;  // [ND*NV][N]      partial sums by direction
     static constexpr int OFF_F = OFF_P + NPART * N;       // [2*NV + 2][LT]  face fluxes and signs by line
-    static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OFF_F + (2 * NV + 2) * LT);
+    static constexpr int OFF_EC = OFF_F + (2 * NV + 2) * LT;    // [2][E*NFACES] int2: face connectivity of this / the next group
+    static constexpr int OFF_BAR = OFF_EC + 2 * E * NFACES;     // WS: 8 mbarriers
+    static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OFF_BAR + (WS ? 8 : 0));
     // registers: a line task holds NP nodes and NP*NV accumulators
     static constexpr int MINB =
 #ifdef FLOU_LINE_MINB
@@ -245,7 +278,7 @@ __device__ __forceinline__ bool cha_pairs(const KParams &P, const double (&r)[C:
 // branch-free pair fluxes; returns true when the line has to be redone with FAST = false.
 template <class C, bool FAST>
 __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, double *sP, const double *sF,
-                                          int task, int64_t dof0)
+                                          int task, int64_t dof0, unsigned free_bar = 0, unsigned free_parity = 0)
 {
     constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
     constexpr int NPTS = C::NPTS, NFP = C::NFP, NLINES = C::NLINES;
@@ -387,7 +420,9 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
                 }
             }
         }
-        // partial sums of direction d, momentum components back in physical order
+        // partial sums of direction d, momentum components back in physical order (warp-specialised
+        // kernel: once the update warp has consumed the partial sums of the previous group)
+        if (free_bar) mbar_wait(free_bar, free_parity);
 #pragma unroll
         for (int j = 0; j < NP; j++) {
             const int node = base + j * stride;
@@ -401,9 +436,238 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
 // not weigh on the fast path
 template <class C>
 __device__ __noinline__ void line_task_exact(const KParams &P, const double *sA, double *sP, const double *sF,
-                                             int task, int64_t dof0)
+                                             int task, int64_t dof0, unsigned free_bar = 0, unsigned free_parity = 0)
 {
-    line_task<C, false>(P, sA, sP, sF, task, dof0);
+    line_task<C, false>(P, sA, sP, sF, task, dof0, free_bar, free_parity);
+}
+
+// Node data of the line phase from the conservative state of one node (phase 1):
+// Chandrasekhar (rho, v/2, beta); StdAverage (Q, v, p); strong form: the ND contravariant fluxes
+// F~_d = sum_c F_c metric[c,d] (OpDivergence.jl:28-37); advection: q (split) or a~_d q (strong).
+template <class C>
+__device__ __forceinline__ void node_data(const KParams &P, const double (&Q)[C::NV], int64_t dof, double (&ax)[C::NAUX])
+{
+    constexpr int ND = C::ND, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
+    constexpr bool CART = C::CART, SPLIT = C::SPLIT;
+    double met[(CART || SPLIT) ? 1 : ND * ND];
+    if (!CART && !SPLIT) {
+#pragma unroll
+        for (int m = 0; m < ND * ND; m++) met[m] = __ldg(P.metric + dof + P.ndof * m);
+    }
+    if (EQ == EQ_EULER) {
+        NodeAux<ND> A;
+        node_aux<ND>(Q, P.fp.gamma, A);
+        if (!(Q[0] > 0.0) || !(A.p > 0.0)) atomicOr(P.status, 1);
+        if (VOL == VOL_SPLIT_CHA) {
+            ax[0] = Q[0];
+#pragma unroll
+            for (int c = 0; c < ND; c++) ax[1 + c] = 0.5 * A.vel[c];
+            ax[ND + 1] = A.beta;
+        } else if (VOL == VOL_SPLIT_STD) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) ax[v] = Q[v];
+#pragma unroll
+            for (int c = 0; c < ND; c++) ax[NV + c] = A.vel[c];
+            ax[NV + ND] = A.p;
+        } else {
+#pragma unroll
+            for (int d = 0; d < ND; d++) {
+                double Fc[NV], Ft[NV];
+#pragma unroll
+                for (int v = 0; v < NV; v++) Ft[v] = 0.0;
+#pragma unroll
+                for (int c = 0; c < ND; c++) {
+                    if (CART && c != d) continue;
+                    const double m = CART ? P.cmet[d] : met[c + ND * d];
+                    euler_flux_dir<ND>(Q, A.vel, A.p, c, Fc);
+#pragma unroll
+                    for (int v = 0; v < NV; v++) Ft[v] += Fc[v] * m;
+                }
+#pragma unroll
+                for (int v = 0; v < NV; v++) ax[d * NV + v] = Ft[v];
+            }
+        }
+    } else if (SPLIT) {
+        ax[0] = Q[0];
+    } else {
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+            double an = 0.0;
+#pragma unroll
+            for (int c = 0; c < ND; c++)
+                an += P.fp.a[c] * (CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d]);
+            ax[d] = an * Q[0];
+        }
+    }
+}
+
+// Phase 1 of a group: node data of every node, RU nodes per thread at a time.
+template <class C, int RU, int T>
+__device__ __forceinline__ void phase1_nodes(const KParams &P, const double *U, double *sA, int tid, int nn, int64_t dof0)
+{
+    constexpr int NV = C::NV, N = C::N, NAUX = C::NAUX;
+    for (int n0 = tid; n0 < nn; n0 += RU * T) {
+        double Q[RU][NV], ax[RU][NAUX];
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            const int n = min(n0 + u * T, nn - 1);
+#pragma unroll
+            for (int v = 0; v < NV; v++) Q[u][v] = U[v * N + n];
+        }
+#pragma unroll
+        for (int u = 0; u < RU; u++) node_data<C>(P, Q[u], dof0 + min(n0 + u * T, nn - 1), ax[u]);
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            const int n = n0 + u * T;
+            if (n < nn) {
+#pragma unroll
+                for (int c = 0; c < NAUX; c++) sA[c * N + n] = ax[u][c];
+            }
+        }
+    }
+}
+
+// Phase 3 of a group: sum of the directional partial sums, mass matrix, RK stage update, traces.
+template <class C, int RU, int T>
+__device__ __forceinline__ void phase3_nodes(const KParams &P, const double *U, const double *sT, const double *sP,
+                                             int tid, int nn, int64_t dof0, int g)
+{
+    constexpr int ND = C::ND, NP = C::NP, NV = C::NV, NPTS = C::NPTS, NFP = C::NFP, N = C::N, E = C::E;
+    constexpr bool CART = C::CART, FOLD = C::FOLD;
+    const int64_t ndof = P.ndof;
+    const bool need_tmp = (P.mode == MODE_STAGE);
+    for (int n0 = tid; n0 < nn; n0 += RU * T) {
+        double acc[RU][NV], tv[RU][NV], uv[RU][NV], rjac[RU];
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            const int n = min(n0 + u * T, nn - 1);
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                double s = 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; d++) {
+                    const double x = sP[(d * NV + v) * N + n];
+                    s = FOLD ? fma(P.cmet[d], x, s) : s + x;
+                }
+                acc[u][v] = s;
+                tv[u][v] = need_tmp ? sT[v * N + n] : 0.0;
+                uv[u][v] = U[v * N + n];
+            }
+            rjac[u] = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof0 + n));
+        }
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            const int n = n0 + u * T;
+            if (n >= nn) break;
+            const int64_t dof = dof0 + n;
+            if (P.mode == MODE_RHS) {
+#pragma unroll
+                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[u][v] * rjac[u];
+            } else {
+                double un[NV];
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const double kv = acc[u][v] * rjac[u];
+                    const double t = need_tmp ? fma(P.dt, kv, P.rkA * tv[u][v]) : P.dt * kv;
+                    P.tmp[dof + ndof * v] = t;
+                    un[v] = fma(P.rkB, t, uv[u][v]);
+                    P.u_out[dof + ndof * v] = un[v];
+                }
+                // x-face traces of the new state for the next stage (collocated nodes only;
+                // Gauss nodes are handled by emit_traces_kernel)
+                if (P.colloc) {
+                    const int el = n / NPTS, node = n - el * NPTS;
+                    int k, ii;
+                    node_line<ND, NP>(node, 0, k, ii);
+                    if (ii == 0 || ii == NP - 1) {
+                        const int64_t e = P.elem_first + g * E + el;
+                        double *dst = P.tr_out + (e * 2 + (ii == 0 ? 0 : 1)) * (NV * NFP) + k;
+#pragma unroll
+                        for (int v = 0; v < NV; v++) dst[v * NFP] = un[v];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Phase 3 on PAIRS of adjacent nodes with 128-bit shared loads and global stores (half the
+// instructions of phase3_nodes): needs an even node count and 16-byte aligned planes (the `wide`
+// condition of the copies).  RP pairs per thread at a time, loads first.
+template <class C, int RP, int T>
+__device__ __forceinline__ void phase3_pairs(const KParams &P, const double *U, const double *sT, const double *sP,
+                                             int tid, int nn, int64_t dof0, int g)
+{
+    constexpr int ND = C::ND, NP = C::NP, NV = C::NV, NPTS = C::NPTS, NFP = C::NFP, N = C::N, E = C::E;
+    constexpr bool CART = C::CART, FOLD = C::FOLD;
+    const int64_t ndof = P.ndof;
+    const bool need_tmp = (P.mode == MODE_STAGE);
+    const int npairs = nn >> 1;
+    for (int p0 = tid; p0 < npairs; p0 += RP * T) {
+        double2 acc[RP][NV], tv[RP][NV], uv[RP][NV], rjac[RP];
+#pragma unroll
+        for (int r = 0; r < RP; r++) {
+            const int n = 2 * min(p0 + r * T, npairs - 1);
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int d = 0; d < ND; d++) {
+                    const double2 x = *reinterpret_cast<const double2 *>(sP + (d * NV + v) * N + n);
+                    if (FOLD) { s.x = fma(P.cmet[d], x.x, s.x); s.y = fma(P.cmet[d], x.y, s.y); }
+                    else { s.x += x.x; s.y += x.y; }
+                }
+                acc[r][v] = s;
+                tv[r][v] = need_tmp ? *reinterpret_cast<const double2 *>(sT + v * N + n) : make_double2(0.0, 0.0);
+                uv[r][v] = *reinterpret_cast<const double2 *>(U + v * N + n);
+            }
+            if (CART) rjac[r] = make_double2(P.crjac, P.crjac);
+            else {
+                const double2 j = __ldg(reinterpret_cast<const double2 *>(P.jac + dof0 + n));
+                rjac[r] = make_double2(fast_rcp(j.x), fast_rcp(j.y));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RP; r++) {
+            const int n = 2 * (p0 + r * T);
+            if (n >= nn) break;
+            const int64_t dof = dof0 + n;
+            if (P.mode == MODE_RHS) {
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+                    *reinterpret_cast<double2 *>(P.k_out + dof + ndof * v) =
+                        make_double2(acc[r][v].x * rjac[r].x, acc[r][v].y * rjac[r].y);
+            } else {
+                double2 un[NV];
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const double kx = acc[r][v].x * rjac[r].x, ky = acc[r][v].y * rjac[r].y;
+                    double2 t;
+                    t.x = need_tmp ? fma(P.dt, kx, P.rkA * tv[r][v].x) : P.dt * kx;
+                    t.y = need_tmp ? fma(P.dt, ky, P.rkA * tv[r][v].y) : P.dt * ky;
+                    *reinterpret_cast<double2 *>(P.tmp + dof + ndof * v) = t;
+                    un[v].x = fma(P.rkB, t.x, uv[r][v].x);
+                    un[v].y = fma(P.rkB, t.y, uv[r][v].y);
+                    *reinterpret_cast<double2 *>(P.u_out + dof + ndof * v) = un[v];
+                }
+                if (P.colloc) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int m = n + h;
+                        const int el = m / NPTS, node = m - el * NPTS;
+                        int k, ii;
+                        node_line<ND, NP>(node, 0, k, ii);
+                        if (ii == 0 || ii == NP - 1) {
+                            const int64_t e = P.elem_first + g * E + el;
+                            double *dst = P.tr_out + (e * 2 + (ii == 0 ? 0 : 1)) * (NV * NFP) + k;
+#pragma unroll
+                            for (int v = 0; v < NV; v++) dst[v * NFP] = h ? un[v].y : un[v].x;
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -420,13 +684,14 @@ line_kernel(const __grid_constant__ KParams P)
     constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NLINES = C::NLINES;
     constexpr int E = C::E, T = C::T, N = C::N, LT = C::LT;
     constexpr bool CART = C::CART, SPLIT = C::SPLIT, FOLD = C::FOLD, ONE_ROUND = C::ONE_ROUND;
+    constexpr bool RU2 = (N > T);        // some threads own two nodes of a group
 
     extern __shared__ __align__(16) double lsmem[];
     double *const smem = lsmem;
     double *sU = smem + C::OFF_U, *sT = smem + C::OFF_T, *sA = smem + C::OFF_A;
     double *sP = smem + C::OFF_P, *sF = smem + C::OFF_F;
 
-    const int tid = threadIdx.x;
+    int tid = threadIdx.x;      // refreshed at the top of every group iteration (see below)
     const int ngroups = (P.elem_count + E - 1) / E;
     const int64_t ndof = P.ndof;
     const bool need_tmp = (P.mode == MODE_STAGE);
@@ -438,6 +703,10 @@ line_kernel(const __grid_constant__ KParams P)
     // the few local-memory lines of the kernel from L1 -- else 8-byte copies.
     const bool wide = ((ndof & 1) == 0) && (((int64_t)P.elem_first * NPTS & 1) == 0) && ((N & 1) == 0) &&
                       ((reinterpret_cast<uintptr_t>(P.u_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.tmp) & 15) == 0);
+    // the same alignment for the 128-bit stores of phase 3
+    const bool wide3 = wide && ((reinterpret_cast<uintptr_t>(P.u_out) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(P.k_out) & 15) == 0) &&
+                       (CART || (reinterpret_cast<uintptr_t>(P.jac) & 15) == 0);
     auto issue_planes = [&](const double *src, double *dst, int gg) {
         const int nn = min(E, P.elem_count - gg * E) * NPTS;
         const double *s0 = src + (int64_t)(P.elem_first + gg * E) * NPTS;
@@ -453,19 +722,23 @@ line_kernel(const __grid_constant__ KParams P)
             }
         }
     };
-    // connectivity of line task `task` of group gg: the two faces at the ends of the line
-    auto load_ec = [&](int gg, int task, int2 &ecL, int2 &ecR) {
-        const int el = task / NLINES, d = (task - el * NLINES) / NFP;
-        const int e = P.elem_first + gg * E + el;
-        ecL = __ldg(P.econn + ((int64_t)e * NFACES + 2 * d));
-        ecR = __ldg(P.econn + ((int64_t)e * NFACES + 2 * d + 1));
+    // face connectivity (flux slot, master flag, orientation) of the elements of group gg ->
+    // shared memory, one 8-byte record per (element, local face); staged one group ahead so that
+    // neither the load latency nor registers holding the records cross the line phase
+    int2 *sEC = reinterpret_cast<int2 *>(smem + C::OFF_EC);
+    auto issue_ec = [&](int gg, int buf) {
+        const int nrec = min(E, P.elem_count - gg * E) * NFACES;
+        if (tid < nrec)
+            cp_async8(reinterpret_cast<double *>(sEC + buf * (E * NFACES) + tid),
+                      reinterpret_cast<const double *>(P.econn + (int64_t)(P.elem_first + gg * E) * NFACES + tid));
     };
     // face fluxes of a line (surface_contribution!): Fn is the master-outward flux in the
     // master's face-dof order; the slave side sees it negated and permuted.  Column `task` of
     // sF belongs to the thread that owns the line, so no barrier is needed, only wait_group.
-    auto issue_fn = [&](int task, int2 ecL, int2 ecR) {
-        const int r_ = task % NLINES;
+    auto issue_fn = [&](int task, const int2 *ec) {
+        const int el = task / NLINES, r_ = task - el * NLINES;
         const int d = r_ / NFP, k = r_ - d * NFP;
+        const int2 ecL = ec[el * NFACES + 2 * d], ecR = ec[el * NFACES + 2 * d + 1];
         const int iL = (ecL.y & 1) ? k : slave2master<ND, NP>(k, (ecL.y >> 1) & 7);
         const int iR = (ecR.y & 1) ? k : slave2master<ND, NP>(k, (ecR.y >> 1) & 7);
         const double *sL = P.Fn + (int64_t)ecL.x * (NV * NFP) + iL;
@@ -485,88 +758,33 @@ line_kernel(const __grid_constant__ KParams P)
     // ---------------- prologue: state of the first group, connectivity of its lines
     issue_planes(P.u_in, sU, g);
     cp_async_commit();
-    int2 ecL = make_int2(0, 0), ecR = make_int2(0, 0);
-    if (ONE_ROUND && tid < min(E, P.elem_count - g * E) * NLINES) load_ec(g, tid, ecL, ecR);
+    issue_ec(g, 0);
+    cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
 
     for (int cur = 0; g < ngroups; g += gridDim.x, cur ^= 1) {
+        // thread index re-read every iteration: everything derived from it (line number, face-dof
+        // permutations, copy addresses) is then recomputed with a few integer instructions instead
+        // of living across the line phase, where the spills of such loop invariants cost two
+        // ~300-cycle local-memory round trips per iteration (ncu: 7 % of the kernel)
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
         const int nact = min(E, P.elem_count - g * E);
         const int nn = nact * NPTS, nl = nact * NLINES;
         const int gn = g + gridDim.x;
         const int64_t dof0 = (int64_t)(P.elem_first + g * E) * NPTS;
         const double *U = sU + cur * (NV * N);
 
-        // ---------------- phase 1: node primitives -> shared memory
-        for (int n = tid; n < nn; n += T) {
-            double Q[NV];
-#pragma unroll
-            for (int v = 0; v < NV; v++) Q[v] = U[v * N + n];
-            double met[(CART || SPLIT) ? 1 : ND * ND];
-            if (!CART && !SPLIT) {
-#pragma unroll
-                for (int m = 0; m < ND * ND; m++) met[m] = __ldg(P.metric + dof0 + n + ndof * m);
-            }
-            if (EQ == EQ_EULER) {
-                NodeAux<ND> A;
-                node_aux<ND>(Q, P.fp.gamma, A);
-                if (!(Q[0] > 0.0) || !(A.p > 0.0)) atomicOr(P.status, 1);
-                if (VOL == VOL_SPLIT_CHA) {
-                    sA[n] = Q[0];
-#pragma unroll
-                    for (int c = 0; c < ND; c++) sA[(1 + c) * N + n] = 0.5 * A.vel[c];
-                    sA[(ND + 1) * N + n] = A.beta;
-                } else if (VOL == VOL_SPLIT_STD) {
-#pragma unroll
-                    for (int v = 0; v < NV; v++) sA[v * N + n] = Q[v];
-#pragma unroll
-                    for (int c = 0; c < ND; c++) sA[(NV + c) * N + n] = A.vel[c];
-                    sA[(NV + ND) * N + n] = A.p;
-                } else {
-#pragma unroll
-                    for (int d = 0; d < ND; d++) {
-                        double Fc[NV], Ft[NV];
-#pragma unroll
-                        for (int v = 0; v < NV; v++) Ft[v] = 0.0;
-#pragma unroll
-                        for (int c = 0; c < ND; c++) {
-                            if (CART && c != d) continue;
-                            const double m = CART ? P.cmet[d] : met[c + ND * d];
-                            euler_flux_dir<ND>(Q, A.vel, A.p, c, Fc);
-#pragma unroll
-                            for (int v = 0; v < NV; v++) Ft[v] += Fc[v] * m;
-                        }
-#pragma unroll
-                        for (int v = 0; v < NV; v++) sA[(d * NV + v) * N + n] = Ft[v];
-                    }
-                }
-            } else if (SPLIT) {
-                sA[n] = Q[0];
-            } else {
-#pragma unroll
-                for (int d = 0; d < ND; d++) {
-                    double an = 0.0;
-#pragma unroll
-                    for (int c = 0; c < ND; c++)
-                        an += P.fp.a[c] * (CART ? (c == d ? P.cmet[d] : 0.0) : met[c + ND * d]);
-                    sA[d * N + n] = an * Q[0];
-                }
-            }
-        }
+        // ---------------- phase 1: node primitives -> shared memory.  Warps whose threads own two
+        // nodes of the group handle both at once (loads first, stores last)
+        if (RU2 && (tid & ~31) + T < nn) phase1_nodes<C, 2, T>(P, U, sA, tid, nn, dof0);
+        else phase1_nodes<C, 1, T>(P, U, sA, tid, nn, dof0);
         __syncthreads();      // node data visible; every warp has left phase 3 of the previous group
 
         // ---------------- issue: face fluxes and tmp of this group, state of the next group
-        if (ONE_ROUND) {
-            if (tid < nl) issue_fn(tid, ecL, ecR);
-        } else {
-            for (int task = tid; task < nl; task += T) {
-                int2 a, b;
-                load_ec(g, task, a, b);
-                issue_fn(task, a, b);
-            }
-        }
+        for (int task = tid; task < nl; task += T) issue_fn(task, sEC + cur * (E * NFACES));
         if (need_tmp) issue_planes(P.tmp, sT, g);
-        if (gn < ngroups) issue_planes(P.u_in, sU + (cur ^ 1) * (NV * N), gn);
+        if (gn < ngroups) { issue_planes(P.u_in, sU + (cur ^ 1) * (NV * N), gn); issue_ec(gn, cur ^ 1); }
         cp_async_commit();
 
         // ---------------- phase 2: one tensor-product line per thread
@@ -580,52 +798,11 @@ line_kernel(const __grid_constant__ KParams P)
         cp_async_wait<0>();    // this thread's share of tmp and of the next state has landed
         __syncthreads();
 
-        // connectivity of my line in the next group: in flight during phase 3 and phase 1
-        if (ONE_ROUND && gn < ngroups && tid < min(E, P.elem_count - gn * E) * NLINES) load_ec(gn, tid, ecL, ecR);
 
         // ---------------- phase 3: sum the directions, mass matrix, RK stage update
-        for (int n = tid; n < nn; n += T) {
-            const int64_t dof = dof0 + n;
-            double acc[NV];
-#pragma unroll
-            for (int v = 0; v < NV; v++) {
-                double s = 0.0;
-#pragma unroll
-                for (int d = 0; d < ND; d++) {
-                    const double x = sP[(d * NV + v) * N + n];
-                    s = FOLD ? fma(P.cmet[d], x, s) : s + x;
-                }
-                acc[v] = s;
-            }
-            const double rjac = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof));
-            if (P.mode == MODE_RHS) {
-#pragma unroll
-                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[v] * rjac;
-            } else {
-                double un[NV];
-#pragma unroll
-                for (int v = 0; v < NV; v++) {
-                    const double kv = acc[v] * rjac;
-                    const double t = need_tmp ? fma(P.dt, kv, P.rkA * sT[v * N + n]) : P.dt * kv;
-                    P.tmp[dof + ndof * v] = t;
-                    un[v] = fma(P.rkB, t, U[v * N + n]);
-                    P.u_out[dof + ndof * v] = un[v];
-                }
-                // x-face traces of the new state for the next stage (collocated nodes only; Gauss
-                // nodes are handled by emit_traces_kernel)
-                if (P.colloc) {
-                    const int el = n / NPTS, node = n - el * NPTS;
-                    int k, ii;
-                    node_line<ND, NP>(node, 0, k, ii);
-                    if (ii == 0 || ii == NP - 1) {
-                        const int64_t e = P.elem_first + g * E + el;
-                        double *dst = P.tr_out + (e * 2 + (ii == 0 ? 0 : 1)) * (NV * NFP) + k;
-#pragma unroll
-                        for (int v = 0; v < NV; v++) dst[v * NFP] = un[v];
-                    }
-                }
-            }
-        }
+        if (wide3 && (nn & 1) == 0) phase3_pairs<C, 1, T>(P, U, sT, sP, tid, nn, dof0, g);
+        else if (RU2 && (tid & ~31) + T < nn) phase3_nodes<C, 2, T>(P, U, sT, sP, tid, nn, dof0, g);
+        else phase3_nodes<C, 1, T>(P, U, sT, sP, tid, nn, dof0, g);
     }
 }
 
