@@ -26,6 +26,7 @@
 // so every global load of the kernel is in flight behind the flux arithmetic of phase 2 (the
 // first, non-pipelined line kernel spent 45 % of its stall samples on long-scoreboard waits).
 #pragma once
+#include <type_traits>
 #include "stage_kernel.cuh"
 
 namespace flou {
@@ -44,6 +45,19 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 __device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar)
 {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// one arrival plus `bytes` of expected asynchronous-copy traffic (TMA bulk copies complete_tx on it)
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier; 16-byte aligned
+// addresses, size a multiple of 16 bytes
+__device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gmem_src, unsigned bytes, unsigned bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
@@ -594,8 +608,11 @@ __device__ __forceinline__ void phase3_nodes(const KParams &P, const double *U, 
 // Phase 3 on PAIRS of adjacent nodes with 128-bit shared loads and global stores (half the
 // instructions of phase3_nodes): needs an even node count and 16-byte aligned planes (the `wide`
 // condition of the copies).  RP pairs per thread at a time, loads first.
-template <class C, int RP, int T>
-__device__ __forceinline__ void phase3_pairs(const KParams &P, const double *U, const double *sT, const double *sP,
+// STAGE_TR: the new state is also written back over the old one in shared memory and the x-face
+// traces are emitted afterwards by trace_pass (warp-specialised kernel).
+template <class C, int RP, int T, bool STAGE_TR = false>
+__device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_t<STAGE_TR, double, const double> *U,
+                                             const double *sT, const double *sP,
                                              int tid, int nn, int64_t dof0, int g)
 {
     constexpr int ND = C::ND, NP = C::NP, NV = C::NV, NPTS = C::NPTS, NFP = C::NFP, N = C::N, E = C::E;
@@ -649,8 +666,9 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, const double *U, 
                     un[v].x = fma(P.rkB, t.x, uv[r][v].x);
                     un[v].y = fma(P.rkB, t.y, uv[r][v].y);
                     *reinterpret_cast<double2 *>(P.u_out + dof + ndof * v) = un[v];
+                    if constexpr (STAGE_TR) *reinterpret_cast<double2 *>(U + v * N + n) = un[v];
                 }
-                if (P.colloc) {
+                if (!STAGE_TR && P.colloc) {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const int m = n + h;
@@ -667,6 +685,23 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, const double *U, 
                 }
             }
         }
+    }
+}
+
+// x-face traces of the new state of a group from its copy in shared memory: one entry per
+// (element, side, face dof), coalesced over the face dof.
+template <class C, int T>
+__device__ __forceinline__ void trace_pass(const KParams &P, const double *Unew, int tid, int nact, int g)
+{
+    constexpr int NP = C::NP, NV = C::NV, NPTS = C::NPTS, NFP = C::NFP, N = C::N, E = C::E;
+    for (int t = tid; t < nact * 2 * NFP; t += T) {
+        const int el = t / (2 * NFP), r = t - el * (2 * NFP);
+        const int side = r / NFP, k = r - side * NFP;
+        const int n = el * NPTS + NP * k + (side ? NP - 1 : 0);       // line_of(0, k): base NP*k, stride 1
+        const int64_t e = P.elem_first + g * E + el;
+        double *dst = P.tr_out + (e * 2 + side) * (NV * NFP) + k;
+#pragma unroll
+        for (int v = 0; v < NV; v++) dst[v * NFP] = Unew[v * N + n];
     }
 }
 

@@ -49,10 +49,18 @@ line_kernel_ws(const __grid_constant__ KParams P)
     if (g0 >= ngroups) return;
     const int niter = (ngroups - g0 + gs - 1) / gs;
 
+    // 16-byte aligned planes and an even node count per group: the update warp moves the state with
+    // TMA bulk copies issued by one lane (and works on node pairs); otherwise 8-byte cp.async
+    const bool wide = ((ndof & 1) == 0) && (((int64_t)P.elem_first * NPTS & 1) == 0) && ((N & 1) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(P.u_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.tmp) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(P.u_out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.k_out) & 15) == 0) &&
+                      (C::CART || (reinterpret_cast<uintptr_t>(P.jac) & 15) == 0);
+    const unsigned fullT = bar0 + 40;
     if (threadIdx.x == 0) {
-        for (int b = 0; b < 3; b++) mbar_init(bar0 + 8 * b, 32);
+        for (int b = 0; b < 3; b++) mbar_init(bar0 + 8 * b, wide ? 1 : 32);
         mbar_init(fullP, TL);
         mbar_init(freeP, 32);
+        mbar_init(fullT, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -60,53 +68,52 @@ line_kernel_ws(const __grid_constant__ KParams P)
     if (threadIdx.x >= TL) {
         // =========================================================== update warp
         const int lane = threadIdx.x - TL;
-        const bool wide = ((ndof & 1) == 0) && (((int64_t)P.elem_first * NPTS & 1) == 0) && ((N & 1) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(P.u_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.tmp) & 15) == 0);
-        const bool wide3 = wide && ((reinterpret_cast<uintptr_t>(P.u_out) & 15) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(P.k_out) & 15) == 0) &&
-                           (C::CART || (reinterpret_cast<uintptr_t>(P.jac) & 15) == 0);
-        auto issue_planes = [&](const double *src, double *dst, int gg) {
+        // NV planes of the nodes of group gg -> shared memory, completion on `bar`
+        auto issue_planes = [&](const double *src, double *dst, int gg, unsigned bar) {
             const int nn = min(E, P.elem_count - gg * E) * NPTS;
             const double *s0 = src + (int64_t)(P.elem_first + gg * E) * NPTS;
-            if (wide && (nn & 1) == 0) {
-                for (int n = 2 * lane; n < nn; n += 64) {
+            if (wide) {
+                if (lane == 0) {
+                    mbar_expect_tx(bar, (unsigned)(NV * nn * sizeof(double)));
 #pragma unroll
-                    for (int v = 0; v < NV; v++) cp_async16(dst + v * N + n, s0 + n + ndof * v);
+                    for (int v = 0; v < NV; v++) bulk_g2s(dst + v * N, s0 + ndof * v, (unsigned)(nn * sizeof(double)), bar);
                 }
             } else {
                 for (int n = lane; n < nn; n += 32) {
 #pragma unroll
                     for (int v = 0; v < NV; v++) cp_async8(dst + v * N + n, s0 + n + ndof * v);
                 }
+                if (bar != fullT) mbar_arrive_cp_async(bar);       // tmp: this warp's own wait_group
             }
         };
-        for (int i = 0; i < 3 && i < niter; i++) {
-            issue_planes(P.u_in, sU + i * (NV * N), g0 + i * gs);
-            mbar_arrive_cp_async(bar0 + 8 * i);
-        }
-        if (need_tmp) issue_planes(P.tmp, sT, g0);
+        for (int i = 0; i < 3 && i < niter; i++) issue_planes(P.u_in, sU + i * (NV * N), g0 + i * gs, bar0 + 8 * i);
+        if (need_tmp) issue_planes(P.tmp, sT, g0, fullT);
         cp_async_commit();
 
         for (int i = 0; i < niter; i++) {
             const int g = g0 + i * gs, ub = i % 3;
-            const int nn = min(E, P.elem_count - g * E) * NPTS;
+            const int nact = min(E, P.elem_count - g * E), nn = nact * NPTS;
             const int64_t dof0 = (int64_t)(P.elem_first + g * E) * NPTS;
-            const double *U = sU + ub * (NV * N);
+            double *U = sU + ub * (NV * N);
             mbar_wait(fullP, i & 1);
-            cp_async_wait<0>();          // tmp of this group (and this lane's share of the state copies)
-            __syncwarp();
-            if (wide3 && (nn & 1) == 0) {
-                if (N >= 128) phase3_pairs<C, 2, 32>(P, U, sT, sP, lane, nn, dof0, g);
-                else phase3_pairs<C, 1, 32>(P, U, sT, sP, lane, nn, dof0, g);
+            if (wide) {
+                mbar_wait(bar0 + 8 * ub, (i / 3) & 1);      // completed long ago: makes the TMA writes visible here
+                if (need_tmp) mbar_wait(fullT, i & 1);
+            } else {
+                cp_async_wait<0>();      // tmp of this group and this lane's share of the state copies
+                __syncwarp();
+            }
+            if (wide) {
+                if (N >= 128) phase3_pairs<C, 2, 32, true>(P, U, sT, sP, lane, nn, dof0, g);
+                else phase3_pairs<C, 1, 32, true>(P, U, sT, sP, lane, nn, dof0, g);
+                __syncwarp();
+                if (P.mode != MODE_RHS && P.colloc) trace_pass<C, 32>(P, U, lane, nact, g);
             } else if (N >= 64) phase3_nodes<C, 2, 32>(P, U, sT, sP, lane, nn, dof0, g);
             else phase3_nodes<C, 1, 32>(P, U, sT, sP, lane, nn, dof0, g);
             __syncwarp();                // every lane is done with sP, sT and sU[ub]
             mbar_arrive(freeP);
-            if (need_tmp && i + 1 < niter) issue_planes(P.tmp, sT, g + gs);
-            if (i + 3 < niter) {
-                issue_planes(P.u_in, sU + ub * (NV * N), g + 3 * gs);
-                mbar_arrive_cp_async(bar0 + 8 * ub);
-            }
+            if (need_tmp && i + 1 < niter) issue_planes(P.tmp, sT, g + gs, fullT);
+            if (i + 3 < niter) issue_planes(P.u_in, sU + ub * (NV * N), g + 3 * gs, bar0 + 8 * ub);
             cp_async_commit();
         }
         return;
