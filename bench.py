@@ -376,7 +376,7 @@ def main():
         F.advance(disc, solver, dt, 2)
         ms_f, ms_e, npass = disc.profile(False)
         if npass > 0:
-            ksplit = {"face_flux_kernel_ms": ms_f / npass, "stage_kernel_ms": ms_e / npass,
+            ksplit = {"face_flux_kernel_ms": ms_f / npass, "element_kernel_ms": ms_e / npass,
                       "passes": int(npass)}
 
     # ---- end-to-end leg through the public API: host buffer in, host buffer out, per call
@@ -414,14 +414,14 @@ def main():
     stages = nstages * args.steps
     stage_ms = ms_dev / stages                      # whole stage: every kernel of one RK stage
     stage_gbs = ndof_local * bytes_per_dof / (stage_ms * 1e-3) / 1e9
-    # dominant kernel = the element kernel (stage_kernel: volume + lift + RK update; it moves all
+    # dominant kernel = the element kernel (line_kernel_ws: volume + lift + RK update; it moves all
     # of the algorithmic bytes); the face-flux kernel only adds non-algorithmic traffic
-    kernel_ms = ksplit["stage_kernel_ms"] if ksplit else stage_ms
+    kernel_ms = ksplit["element_kernel_ms"] if ksplit else stage_ms
     achieved = ndof_local * bytes_per_dof / (kernel_ms * 1e-3) / 1e9
     config["launch"] = disc.kernel_info()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
-                "kernel": "flou::stage_kernel (element kernel of the two-kernel stage)",
+                "kernel": "flou::line_kernel_ws (element kernel of the two-kernel stage)",
                 "algorithmic_bytes_per_dof": bytes_per_dof,
                 "dofs_per_launch": ndof_local, "avg_launch_ms": kernel_ms,
                 "stage_ms": stage_ms, "stage_achieved": stage_gbs, "stage_frac": stage_gbs / peak,

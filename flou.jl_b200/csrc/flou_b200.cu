@@ -647,6 +647,15 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
 
     H_TRY(upload(&h->conn, conn));
     h->split_faces = !(d->flags & FLOU_B200_FLAG_FUSED);
+    {
+        // meshes too small to fill the device with element groups are launch-latency-bound: one
+        // fused launch per stage beats two (config 1: 1024 elements = 64 groups on 148 SMs)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const int64_t groups = (h->ne_local + h->stage->line_e - 1) / std::max(1, h->stage->line_e);
+        if (h->nranks == 1 && groups < sms && !(d->flags & (FLOU_B200_FLAG_NODE_KERNEL | FLOU_B200_FLAG_LINE_KERNEL)))
+            h->split_faces = false;
+    }
     h->line_kernel = h->split_faces && !(d->flags & FLOU_B200_FLAG_NODE_KERNEL);
     h->n_faces = (int)pl.faces.size();
     h->n_faces_local_only = pl.n_faces_local_only;

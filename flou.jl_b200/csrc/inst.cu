@@ -80,7 +80,7 @@ static cudaError_t do_launch_elements(const KParams &P, cudaStream_t s)
 }
 
 // ---- line-per-thread element kernel (default element kernel of the two-kernel stage)
-#ifdef FLOU_LINE_WS      // warp-specialised variant: TL line threads + one update warp
+#ifndef FLOU_LINE_NOWS    // default: warp-specialised variant, TL line threads + one update warp
 template <class C>
 using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, true>;
 #define FLOU_LINE_KERNEL line_kernel_ws

@@ -32,7 +32,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
     constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
     constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NLINES = C::NLINES;
     constexpr int E = C::E, TL = C::TL, N = C::N, LT = C::LT, NAUX = C::NAUX;
-    constexpr bool FOLD = C::FOLD, ONE_ROUND = C::ONE_ROUND;
+    constexpr bool FOLD = C::FOLD;
     static_assert(C::WS, "line_kernel_ws needs the WS shared-memory layout");
 
     extern __shared__ __align__(16) double lsmem[];

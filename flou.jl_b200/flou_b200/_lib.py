@@ -20,6 +20,7 @@ GEOM_CARTESIAN, GEOM_GENERAL = 0, 1
 FLAG_NO_GRAPH = 1
 FLAG_FUSED = 2
 FLAG_NODE_KERNEL = 4
+FLAG_LINE_KERNEL = 8
 
 
 class DomainError(ArithmeticError):

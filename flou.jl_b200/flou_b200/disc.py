@@ -30,7 +30,7 @@ class EquationConfig:
 class MultielementDisc:
     def __init__(self, mesh, std, equation, operators, bcs, source=None, *,
                  rank=0, nranks=1, device=None, geometry=None, use_graph=True, create=True,
-                 fused=None):
+                 fused=None, kernel=None):
         if source is not None:
             raise ValueError("source terms are not part of the B200 hot path (default no-op only)")
         if std.nd != mesh.nd or equation.nd != mesh.nd:
@@ -137,9 +137,20 @@ class MultielementDisc:
         import os as _os
         if fused is None:
             fused = _os.environ.get("FLOU_B200_FUSED", "0") == "1"
-        node_kernel = _os.environ.get("FLOU_B200_NODE_KERNEL", "0") == "1"     # A/B switch
-        d.flags = ((0 if use_graph else L.FLAG_NO_GRAPH) | (L.FLAG_FUSED if fused else 0)
-                   | (L.FLAG_NODE_KERNEL if node_kernel else 0))
+        # kernel: None/"auto" (library heuristic: two-kernel stage with the line kernel, fused
+        # single-kernel stage on meshes too small to fill the GPU), "line", "node" (two-kernel
+        # stage with the node-per-thread element kernel), "fused"
+        kernel = kernel or _os.environ.get("FLOU_B200_KERNEL", "auto")
+        if _os.environ.get("FLOU_B200_NODE_KERNEL", "0") == "1":
+            kernel = "node"
+        if fused:
+            kernel = "fused"
+        if kernel not in ("auto", "line", "node", "fused"):
+            raise ValueError(f"unknown kernel choice {kernel!r}")
+        self.kernel = kernel
+        d.flags = ((0 if use_graph else L.FLAG_NO_GRAPH)
+                   | {"auto": 0, "line": L.FLAG_LINE_KERNEL, "node": L.FLAG_NODE_KERNEL,
+                      "fused": L.FLAG_FUSED}[kernel])
         self._h = C.c_void_p()
         if create:
             L.check(L.lib().flou_b200_create(C.byref(d), C.byref(self._h)))

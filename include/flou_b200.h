@@ -143,6 +143,8 @@ typedef struct flou_b200_desc {
                                       face flux) instead of face-flux kernel + element kernel */
 #define FLOU_B200_FLAG_NODE_KERNEL 4 /* two-kernel stage with the node-per-thread element kernel
                                       instead of the default line-per-thread one (A/B testing) */
+#define FLOU_B200_FLAG_LINE_KERNEL 8 /* two-kernel stage with the line-per-thread element kernel even on
+                                      meshes too small to fill the GPU (default there: fused kernel) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */
 /* Replaces MultielementDisc(...) + construct_cache (Hyperbolic.jl:21-29): uploads tables,

@@ -109,7 +109,10 @@ class Case:
             bcs=bcs, cartesian=not self.general)
 
     # ---------------------------------------------------------------- product side
-    def product(self, rank=0, nranks=1, device=0, use_graph=True, create=True):
+    def product(self, rank=0, nranks=1, device=0, use_graph=True, create=True, kernel="line"):
+        """kernel="line": the production path of meshes that fill a GPU (two-kernel stage,
+        line-per-thread element kernel) even on these small test meshes; "auto" lets the library
+        pick (fused single-kernel stage below one element group per SM)."""
         import flou_b200 as F
         start, finish = box(self.nd)
         mesh = F.CartesianMesh(self.nd, start, finish, self.n)
@@ -145,7 +148,7 @@ class Case:
                 bcs[name] = F.GenericBC(lambda Qin, x, frame, t, eq_, f=param: f(x))
         disc = F.MultielementDisc(mesh, std, eq, op, bcs, rank=rank, nranks=nranks, device=device,
                                   geometry="general" if self.general else None,
-                                  use_graph=use_graph, create=create)
+                                  use_graph=use_graph, create=create, kernel=kernel)
         return disc, eq
 
 

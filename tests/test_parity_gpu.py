@@ -52,6 +52,27 @@ def test_rhs_matches_oracle(gpu, case, state):
     disc.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["auto", "node", "fused"])
+@pytest.mark.parametrize("case", [CASES[1], CASES[6], CASES[8], CASES[11], CASES[16]], ids=repr)
+def test_rhs_other_kernel_paths(gpu, case, kernel):
+    """The parity cases above run the production path of large meshes (kernel="line"); the
+    library's own choice on these small meshes (fused single-kernel stage) and the node-per-thread
+    element kernel kept for A/B timing must agree with the oracle as well."""
+    import flou_b200 as F
+    orc = case.oracle()
+    disc, eq = case.product(kernel=kernel)
+    Q = random_state(orc.ndof, case.nd, case.eq, amp=case.amp)
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert relerr(dQ, orc.rhs(Q)) <= RHS_TOL
+    u = Q.copy(order="F")
+    sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), 3e-4, dt=1e-4)
+    import oracle as O
+    assert relerr(sol.u[-1], orc.lsrk2n(Q, O.ORK256, 1e-4, 3)) <= 1e-10
+    disc.close()
+
+
 BC_CASES = [
     Case(2, (5, 4), 4, eq="euler", op="split", nf="mat", avg="cha", periodic=[("3", "4")],
          bcs={"1": ("inflow", [1.1, 0.33, 0.02, 2.6]), "2": ("outflow", None)}),

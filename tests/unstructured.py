@@ -73,5 +73,6 @@ def build_pair(mshfile, npn, bcs, nf="mat", avg="cha", op="split", nodes="GLL", 
     for name, (kind, param) in bcs.items():
         pb[name] = {"inflow": lambda p=param: F.EulerInflowBC(p), "outflow": F.EulerOutflowBC,
                     "slip": F.EulerSlipBC}[kind]()
-    disc = F.MultielementDisc(mesh, std, eq, oper, pb, create=create, rank=rank, nranks=nranks)
+    # kernel="line": the production path of large meshes also on these small ones (see common.py)
+    disc = F.MultielementDisc(mesh, std, eq, oper, pb, create=create, rank=rank, nranks=nranks, kernel="line")
     return orc, disc, eq
