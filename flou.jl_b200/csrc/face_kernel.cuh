@@ -43,29 +43,61 @@ __device__ __forceinline__ void load_trace(const KParams &P, int kind, int elem_
 #define FLOU_FACE_MIN_BLOCKS 5
 #endif
 
-template <int ND, int NP, int EQ, bool CART>
-__global__ void __launch_bounds__(128, FLOU_FACE_MIN_BLOCKS)
-face_flux_kernel(const __grid_constant__ KParams P)
+// Rotation to / from the frame of a Cartesian face whose master-side local face is the
+// compile-time LFM: a fixed signed permutation (PhysicalRegions.jl:541-696), no selects.
+template <int ND, int EQ, int LFM>
+__device__ __forceinline__ void rot2face_c(const double *Q, double *R)
+{
+    constexpr int dm = LFM >> 1;
+    constexpr double s = (LFM & 1) ? 1.0 : -1.0;
+    R[0] = Q[0];
+    if (EQ == EQ_ADV) return;
+    R[1] = s * Q[1 + dm];
+    if (ND == 2) R[2] = ((dm == 0) ? s : -s) * Q[1 + (1 - dm)];
+    if (ND == 3) {
+        constexpr int tm = (dm == 2) ? 0 : dm + 1, bm = (dm == 0) ? 2 : dm - 1;
+        R[2] = s * Q[1 + tm];
+        R[3] = Q[1 + bm];
+    }
+    R[ND + 1] = Q[ND + 1];
+}
+
+template <int ND, int EQ, int LFM>
+__device__ __forceinline__ void rot2phys_c(const double *R, double *Q)
+{
+    constexpr int dm = LFM >> 1;
+    constexpr double s = (LFM & 1) ? 1.0 : -1.0;
+    Q[0] = R[0];
+    if (EQ == EQ_ADV) return;
+    if (ND == 1) Q[1] = s * R[1];
+    if (ND == 2) {
+        Q[1 + dm] = s * R[1];
+        Q[1 + (1 - dm)] = ((dm == 0) ? s : -s) * R[2];
+    }
+    if (ND == 3) {
+        constexpr int tm = (dm == 2) ? 0 : dm + 1, bm = (dm == 0) ? 2 : dm - 1;
+        Q[1 + dm] = s * R[1];
+        Q[1 + tm] = s * R[2];
+        Q[1 + bm] = R[3];
+    }
+    Q[ND + 1] = R[ND + 1];
+}
+
+// One face point with the master's local face LFM known at compile time: the master trace path
+// (trace array / node layer) and, on Cartesian meshes, the whole rotation are static.
+template <int ND, int NP, int EQ, bool CART, int LFM>
+__device__ __forceinline__ void face_point(const KParams &P, int f, int i, const FaceRec rec)
 {
     constexpr int NV = (EQ == EQ_ADV) ? 1 : ND + 2;
     constexpr int NFP = ipow_c(NP, ND - 1);
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)P.face_count * NFP) return;
-    const int fl = (int)(t / NFP), i = (int)(t - (int64_t)fl * NFP);
-    const int f = P.face_first + fl;
-    const FaceRec rec = P.faces[f];
-    const int lfm = rec.info & 7, lfs = (rec.info >> 3) & 7, orient = (rec.info >> 6) & 7;
+    const int lfs = (rec.info >> 3) & 7, orient = (rec.info >> 6) & 7;
     const int mkind = (rec.info >> 9) & 3, skind = (rec.info >> 11) & 3;
     const int j = master2slave<ND, NP>(i, orient);
 
     // frame and face Jacobian of the master side (PhysicalRegions.jl:541-696 / 797-971)
     double fr[CART ? 1 : 3 * ND], fj;
-    int dm = 0;
-    double sn_ = 1.0;
     if (CART) {
-        dm = lfm >> 1;
-        sn_ = (lfm & 1) ? 1.0 : -1.0;
-        fj = dm == 0 ? P.cfjac[0] : (dm == 1 ? P.cfjac[1] : P.cfjac[2]);
+        fj = P.cfjac[LFM >> 1];
     } else {
         const int64_t fi = (int64_t)f * NFP + i;
 #pragma unroll
@@ -75,7 +107,8 @@ face_flux_kernel(const __grid_constant__ KParams P)
     }
 
     double Ql[NV], Qr[NV];
-    load_trace<ND, NP, NV>(P, mkind, rec.em, lfm, i, Ql);
+    if (mkind == 1) load_trace<ND, NP, NV>(P, 1, rec.em, LFM, i, Ql);
+    else load_trace<ND, NP, NV>(P, 0, rec.em, LFM, i, Ql);          // LFM static: one path survives
     if (skind != 2) {
         load_trace<ND, NP, NV>(P, skind, rec.es, lfs, j, Qr);
     } else {
@@ -90,10 +123,10 @@ face_flux_kernel(const __grid_constant__ KParams P)
             for (int v = 0; v < NV; v++) Qr[v] = Ql[v];
         } else if (bk == FLOU_B200_BC_SLIP) {
             double R[NV];
-            if (CART) rotate2face_cart<ND, EQ>(Ql, dm, sn_, R);
+            if (CART) rot2face_c<ND, EQ, LFM>(Ql, R);
             else rotate2face<ND, EQ>(Ql, fr, R);
             if (NV > 1) R[NV > 1 ? 1 : 0] = -R[NV > 1 ? 1 : 0];
-            if (CART) rotate2phys_cart<ND, EQ>(R, dm, sn_, Qr);
+            if (CART) rot2phys_c<ND, EQ, LFM>(R, Qr);
             else rotate2phys<ND, EQ>(R, fr, Qr);
         } else {
 #pragma unroll
@@ -103,8 +136,8 @@ face_flux_kernel(const __grid_constant__ KParams P)
 
     double Rl[NV], Rr[NV], Fn[NV], Fp[NV];
     if (CART) {
-        rotate2face_cart<ND, EQ>(Ql, dm, sn_, Rl);
-        rotate2face_cart<ND, EQ>(Qr, dm, sn_, Rr);
+        rot2face_c<ND, EQ, LFM>(Ql, Rl);
+        rot2face_c<ND, EQ, LFM>(Qr, Rr);
     } else {
         rotate2face<ND, EQ>(Ql, fr, Rl);
         rotate2face<ND, EQ>(Qr, fr, Rr);
@@ -113,7 +146,7 @@ face_flux_kernel(const __grid_constant__ KParams P)
         euler_numflux<ND>(P.fp, Rl, Rr, Fn);
     } else {
         double an = 0.0;
-        if (CART) an = sn_ * pick<ND>(P.fp.a, dm);
+        if (CART) an = ((LFM & 1) ? 1.0 : -1.0) * P.fp.a[LFM >> 1];
         else {
 #pragma unroll
             for (int c = 0; c < ND; c++) an += P.fp.a[c] * fr[c];
@@ -121,11 +154,33 @@ face_flux_kernel(const __grid_constant__ KParams P)
         Fn[0] = an * (Rl[0] + Rr[0]) * 0.5;
         if (P.fp.numflux == FX_LXF) Fn[0] += fabs(an) * (Rl[0] - Rr[0]) * 0.5 * P.fp.intensity;
     }
-    if (CART) rotate2phys_cart<ND, EQ>(Fn, dm, sn_, Fp);
+    if (CART) rot2phys_c<ND, EQ, LFM>(Fn, Fp);
     else rotate2phys<ND, EQ>(Fn, fr, Fp);
     double *dst = P.Fn + (int64_t)f * (NV * NFP) + i;
 #pragma unroll
     for (int v = 0; v < NV; v++) dst[v * NFP] = Fp[v] * fj;
+}
+
+template <int ND, int NP, int EQ, bool CART>
+__global__ void __launch_bounds__(128, FLOU_FACE_MIN_BLOCKS)
+face_flux_kernel(const __grid_constant__ KParams P)
+{
+    constexpr int NFP = ipow_c(NP, ND - 1);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)P.face_count * NFP) return;
+    const int fl = (int)(t / NFP), i = (int)(t - (int64_t)fl * NFP);
+    const int f = P.face_first + fl;
+    const FaceRec rec = P.faces[f];
+    // faces keep Flou's global order, in which the master's local face changes rarely: the switch
+    // is warp-uniform almost everywhere
+    switch (rec.info & 7) {
+    case 0: face_point<ND, NP, EQ, CART, 0>(P, f, i, rec); break;
+    case 1: face_point<ND, NP, EQ, CART, 1>(P, f, i, rec); break;
+    case 2: if (ND >= 2) face_point<ND, NP, EQ, CART, (ND >= 2 ? 2 : 0)>(P, f, i, rec); break;
+    case 3: if (ND >= 2) face_point<ND, NP, EQ, CART, (ND >= 2 ? 3 : 0)>(P, f, i, rec); break;
+    case 4: if (ND >= 3) face_point<ND, NP, EQ, CART, (ND >= 3 ? 4 : 0)>(P, f, i, rec); break;
+    default: if (ND >= 3) face_point<ND, NP, EQ, CART, (ND >= 3 ? 5 : 0)>(P, f, i, rec); break;
+    }
 }
 
 }  // namespace flou

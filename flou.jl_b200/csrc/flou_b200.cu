@@ -205,11 +205,25 @@ int32_t build_plan(const flou_b200_desc *d, bool cart, Plan &pl)
     const int nslots = (int)pl.slot_face.size();
     std::vector<char> has_ghost((size_t)nslots, 0);
     for (const Ghost &g : pl.ghosts) has_ghost[pl.faceid[(size_t)g.le * NF + g.lf]] = 1;
+    // ... and, inside each class, grouped by the master's local face: face_flux_kernel is
+    // specialised on it and wants warps that do not mix directions (Flou's own face order
+    // interleaves them)
     std::vector<int> newslot((size_t)nslots);
-    int n0 = 0;
-    for (int sidx = 0; sidx < nslots; sidx++) if (!has_ghost[sidx]) newslot[sidx] = n0++;
-    pl.n_faces_local_only = n0;
-    for (int sidx = 0; sidx < nslots; sidx++) if (has_ghost[sidx]) newslot[sidx] = n0++;
+    {
+        std::vector<int> order((size_t)nslots);
+        for (int sidx = 0; sidx < nslots; sidx++) order[sidx] = sidx;
+        auto key = [&](int sidx) {
+            const int lfm_ = (int)d->elempos[pl.slot_face[sidx] * 2 + 0] - 1;
+            return (has_ghost[sidx] ? 8 : 0) + (lfm_ & 7);
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+        int n0 = 0;
+        for (int q = 0; q < nslots; q++) {
+            newslot[order[q]] = q;
+            if (!has_ghost[order[q]]) n0 = q + 1;
+        }
+        pl.n_faces_local_only = n0;
+    }
     {
         std::vector<int64_t> sf((size_t)nslots);
         for (int sidx = 0; sidx < nslots; sidx++) sf[newslot[sidx]] = pl.slot_face[sidx];
