@@ -53,11 +53,15 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
 }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier; 16-byte aligned
 // addresses, size a multiple of 16 bytes
+// The state and tmp are streamed exactly once per stage: L2 evict-first, so that the face-flux
+// blocks, which both neighbours of a face read, survive in L2 until their second use.
 __device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gmem_src, unsigned bytes, unsigned bar)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
@@ -652,8 +656,8 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
             if (P.mode == MODE_RHS) {
 #pragma unroll
                 for (int v = 0; v < NV; v++)
-                    *reinterpret_cast<double2 *>(P.k_out + dof + ndof * v) =
-                        make_double2(acc[r][v].x * rjac[r].x, acc[r][v].y * rjac[r].y);
+                    __stcs(reinterpret_cast<double2 *>(P.k_out + dof + ndof * v),
+                           make_double2(acc[r][v].x * rjac[r].x, acc[r][v].y * rjac[r].y));
             } else {
                 double2 un[NV];
 #pragma unroll
@@ -662,10 +666,10 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
                     double2 t;
                     t.x = need_tmp ? fma(P.dt, kx, P.rkA * tv[r][v].x) : P.dt * kx;
                     t.y = need_tmp ? fma(P.dt, ky, P.rkA * tv[r][v].y) : P.dt * ky;
-                    *reinterpret_cast<double2 *>(P.tmp + dof + ndof * v) = t;
+                    __stcs(reinterpret_cast<double2 *>(P.tmp + dof + ndof * v), t);
                     un[v].x = fma(P.rkB, t.x, uv[r][v].x);
                     un[v].y = fma(P.rkB, t.y, uv[r][v].y);
-                    *reinterpret_cast<double2 *>(P.u_out + dof + ndof * v) = un[v];
+                    __stcs(reinterpret_cast<double2 *>(P.u_out + dof + ndof * v), un[v]);
                     if constexpr (STAGE_TR) *reinterpret_cast<double2 *>(U + v * N + n) = un[v];
                 }
                 if (!STAGE_TR && P.colloc) {
@@ -701,7 +705,7 @@ __device__ __forceinline__ void trace_pass(const KParams &P, const double *Unew,
         const int64_t e = P.elem_first + g * E + el;
         double *dst = P.tr_out + (e * 2 + side) * (NV * NFP) + k;
 #pragma unroll
-        for (int v = 0; v < NV; v++) dst[v * NFP] = Unew[v * N + n];
+        for (int v = 0; v < NV; v++) __stcs(dst + v * NFP, Unew[v * N + n]);
     }
 }
 
