@@ -269,14 +269,22 @@ int32_t validate_desc(const flou_b200_desc *d)
     if (d->equation != FLOU_B200_EQ_EULER && d->equation != FLOU_B200_EQ_LINEAR_ADVECTION)
         return fail(FLOU_B200_EINVAL, "unknown equation");
     if (d->nv != nv_expected) return fail(FLOU_B200_EINVAL, "nv does not match the equation");
-    if (d->divop != FLOU_B200_OP_STRONG && d->divop != FLOU_B200_OP_SPLIT)
+    if (d->divop != FLOU_B200_OP_STRONG && d->divop != FLOU_B200_OP_SPLIT && d->divop != FLOU_B200_OP_HYBRID)
         return fail(FLOU_B200_EINVAL, "unknown divergence operator");
+    if (d->divop == FLOU_B200_OP_HYBRID) {
+        // OpDivergence.jl:452-612; vars_cons2entropy exists for the Euler equations only
+        if (d->equation != FLOU_B200_EQ_EULER)
+            return fail(FLOU_B200_EINVAL, "HybridDivOperator needs the Euler equations");
+        if (d->flags & (FLOU_B200_FLAG_FUSED | FLOU_B200_FLAG_NODE_KERNEL))
+            return fail(FLOU_B200_EINVAL, "HybridDivOperator exists in the line-per-thread kernel only");
+        if (!(d->blend >= 0.0)) return fail(FLOU_B200_EINVAL, "HybridDivOperator blend must be >= 0");
+    }
     if (d->numflux < 0 || d->numflux > FLOU_B200_FLUX_MATRIXDISSIPATION)
         return fail(FLOU_B200_EINVAL, "unknown numerical flux");
     if (d->equation == FLOU_B200_EQ_LINEAR_ADVECTION &&
         (d->numflux != FLOU_B200_FLUX_STDAVERAGE && d->numflux != FLOU_B200_FLUX_LXF))
         return fail(FLOU_B200_EINVAL, "linear advection supports StdAverage and LxF fluxes only");
-    if (d->divop == FLOU_B200_OP_SPLIT && d->tpflux != FLOU_B200_FLUX_STDAVERAGE &&
+    if (d->divop != FLOU_B200_OP_STRONG && d->tpflux != FLOU_B200_FLUX_STDAVERAGE &&
         d->tpflux != FLOU_B200_FLUX_CHANDRASEKHAR)
         return fail(FLOU_B200_EINVAL, "the two-point flux must be StdAverage or ChandrasekharAverage");
     if (d->equation == FLOU_B200_EQ_LINEAR_ADVECTION && d->divop == FLOU_B200_OP_SPLIT &&
@@ -513,6 +521,7 @@ int32_t flou_b200_device_count(void)
 static int vol_kind(int32_t divop, int32_t tpflux)
 {
     if (divop == FLOU_B200_OP_STRONG) return VOL_STRONG;
+    if (divop == FLOU_B200_OP_HYBRID) return VOL_HYBRID;
     return tpflux == FLOU_B200_FLUX_CHANDRASEKHAR ? VOL_SPLIT_CHA : VOL_SPLIT_STD;
 }
 
@@ -520,8 +529,8 @@ int32_t flou_b200_supported(int32_t nd, int32_t np, int32_t equation, int32_t di
                             int32_t tpflux, int32_t geometry)
 {
     if (equation != FLOU_B200_EQ_LINEAR_ADVECTION && equation != FLOU_B200_EQ_EULER) return 0;
-    if (divop != FLOU_B200_OP_STRONG && divop != FLOU_B200_OP_SPLIT) return 0;
-    if (divop == FLOU_B200_OP_SPLIT && tpflux != FLOU_B200_FLUX_STDAVERAGE &&
+    if (divop != FLOU_B200_OP_STRONG && divop != FLOU_B200_OP_SPLIT && divop != FLOU_B200_OP_HYBRID) return 0;
+    if (divop != FLOU_B200_OP_STRONG && tpflux != FLOU_B200_FLUX_STDAVERAGE &&
         tpflux != FLOU_B200_FLUX_CHANDRASEKHAR) return 0;
     return get_stage_launcher(nd, np, equation, vol_kind(divop, tpflux),
                               geometry == FLOU_B200_GEOM_CARTESIAN) != nullptr;
@@ -558,6 +567,8 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     const int nd = d->nd, np = d->np;
     if (!d->Ds || !d->Dsharp || !d->lminus || !d->lplus || !d->dgminus || !d->dgplus)
         return fail(FLOU_B200_EINVAL, "operator tables missing");
+    if (d->divop == FLOU_B200_OP_HYBRID && (!d->D || !d->weights))
+        return fail(FLOU_B200_EINVAL, "HybridDivOperator needs std.D and the 1-D weights");
     if (d->geometry == FLOU_B200_GEOM_GENERAL && (!d->jac || !d->metric || !d->fjac || !d->frames))
         return fail(FLOU_B200_EINVAL, "general geometry tables missing");
     if (!flou_b200_supported(nd, np, d->equation, d->divop, d->tpflux, d->geometry))
@@ -568,6 +579,19 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     if (flou_b200_device_count() <= d->device || d->device < 0)
         return fail(FLOU_B200_ECUDA, "no usable CUDA device (this library has no CPU path)");
     CUDA_TRY(cudaSetDevice(d->device));
+    {
+        // L2 <- HBM fetch granularity.  The face-flux kernel reads the y-face node layers of u as
+        // 40..64-byte runs (np doubles); with the default 64-byte granularity every run that
+        // straddles a 64-byte boundary pulls 128 bytes (ncu at cfg4: 20.5 GB read for 12.6 GB of
+        // traces).  FLOU_B200_L2_FETCH=32|64|128 overrides the device default (a hint; ignored
+        // where the device does not support it).
+        if (const char *s = std::getenv("FLOU_B200_L2_FETCH")) {
+            const int g = std::atoi(s);
+            if (g == 32 || g == 64 || g == 128) {
+                if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g) != cudaSuccess) cudaGetLastError();
+            }
+        }
+    }
 
     Plan pl;
     if (int32_t rc = build_plan(d, cart, pl)) return rc;
@@ -598,8 +622,12 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     // ---- kernel parameters
     KParams &P = h->base;
     std::memset(&P, 0, sizeof(P));
-    const double *Dvol = d->divop == FLOU_B200_OP_STRONG ? d->Ds : d->Dsharp;
+    const bool hybrid = d->divop == FLOU_B200_OP_HYBRID;
+    const double *Dvol = d->divop == FLOU_B200_OP_STRONG ? d->Ds : (hybrid ? d->D : d->Dsharp);
     for (int i = 0; i < np * np; i++) P.Dvol[i] = Dvol[i];
+    P.tpflux = d->tpflux;
+    P.blend = hybrid ? d->blend : 0.0;
+    for (int i = 0; i < np; i++) P.w1d[i] = d->weights ? d->weights[i] : 0.0;
     bool colloc = true;
     for (int i = 0; i < np; i++) {
         P.lm[i] = d->lminus[i]; P.lp[i] = d->lplus[i];
@@ -619,6 +647,12 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
             if (std::fabs(Dvol[j + np * j]) > 1e-12 * dmax) P.diag_mask |= 1 << j;
     }
     h->colloc = colloc;
+    if (hybrid && !colloc) {
+        // the reference moves everything to the surface term on Gauss nodes
+        // (_hybrid_nb_surface_contribution!, OpDivergence.jl:647-779): not on this path
+        flou_b200_destroy(h);
+        return fail(FLOU_B200_EUNSUPPORTED, "HybridDivOperator needs nodes with boundaries (GLL)");
+    }
     if (colloc) {
         // GLL: l(-1) = e_1 and l(+1) = e_np up to the reference's monomial round-off
         // (O(1e-16) off-entries); the lifting weights away from the end nodes are dropped
@@ -667,7 +701,8 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         const int64_t groups = (h->ne_local + h->stage->line_e - 1) / std::max(1, h->stage->line_e);
-        if (h->nranks == 1 && groups < sms && !(d->flags & (FLOU_B200_FLAG_NODE_KERNEL | FLOU_B200_FLAG_LINE_KERNEL)))
+        if (h->nranks == 1 && groups < sms && !hybrid &&
+            !(d->flags & (FLOU_B200_FLAG_NODE_KERNEL | FLOU_B200_FLAG_LINE_KERNEL)))
             h->split_faces = false;
     }
     h->line_kernel = h->split_faces && !(d->flags & FLOU_B200_FLAG_NODE_KERNEL);

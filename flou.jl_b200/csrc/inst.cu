@@ -198,20 +198,35 @@ static constexpr StageLauncher make()
 #endif
 }
 
+// operators that exist in the line-per-thread formulation only (HybridDivOperator): two-kernel
+// stage, no fused / node-per-thread kernels
+template <class C>
+static cudaError_t lines_only_prepare() { return line_prepare<C>(); }
+template <class C>
+static constexpr StageLauncher make_lines()
+{
+    return StageLauncher{nullptr, nullptr, &do_launch_lines<C>, &do_launch_faces<C>, &lines_only_prepare<C>,
+                         &line_resident_ctas<C>, LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES,
+                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES};
+}
+
 #define ND FLOU_ND
 #define NP FLOU_NP
 
 // [eq][vol][cart]
-static const StageLauncher table[2][3][2] = {
+static const StageLauncher table[2][4][2] = {
     {   // linear advection: strong, split (StdAverage two-point flux); no Chandrasekhar
         {make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, true>>()},
+        {StageLauncher{}, StageLauncher{}},
         {StageLauncher{}, StageLauncher{}},
     },
     {   // Euler
         {make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, true>>()},
         {make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
+        // HybridDivOperator: Cartesian sub-grids only (general sub-grid geometry: row f2b, not built)
+        {StageLauncher{}, make_lines<KCfg<ND, NP, EQ_EULER, VOL_HYBRID, true>>()},
     },
 };
 
@@ -238,7 +253,7 @@ static const EmitLauncher emit_euler = {&emit_launch<ND + 2>};
 const StageLauncher *CAT(stage_table_, FLOU_ND, FLOU_NP)(int eq, int vol, int cart)
 {
     const StageLauncher *l = &table[eq][vol][cart ? 1 : 0];
-    return l->launch ? l : nullptr;
+    return (l->launch || l->launch_lines) ? l : nullptr;
 }
 
 const EmitLauncher *CAT(emit_table_, FLOU_ND, FLOU_NP)(int nv)

@@ -28,6 +28,7 @@
 #pragma once
 #include <type_traits>
 #include "stage_kernel.cuh"
+#include "face_kernel.cuh"     // rot2face_c / rot2phys_c: sub-grid frames of the hybrid operator
 
 namespace flou {
 
@@ -108,13 +109,15 @@ struct LCfg {
     static constexpr int NFP = ipow_c(NP, ND - 1);
     static constexpr int NFACES = 2 * ND;
     static constexpr int NLINES = ND * NFP;
-    static constexpr bool SPLIT = (VOL != VOL_STRONG);
+    static constexpr bool HYBRID = (VOL == VOL_HYBRID);
+    static constexpr bool SPLIT = (VOL == VOL_SPLIT_STD || VOL == VOL_SPLIT_CHA);
+    static_assert(!HYBRID || (EQ == EQ_EULER && CART), "HybridDivOperator: Euler on Cartesian sub-grids only");
     // Cartesian split form: the constant metric factor is applied when the partial sums are added
     static constexpr bool FOLD = CART && SPLIT;
     // node data in shared memory: Chandrasekhar (rho, v/2, beta); StdAverage (Q, v, p);
-    // strong form: the ND contravariant fluxes; advection: q
+    // strong form: the ND contravariant fluxes; hybrid: the conservative state; advection: q
     static constexpr int NAUX = (EQ == EQ_ADV) ? (SPLIT ? 1 : ND)
-                              : (VOL == VOL_SPLIT_CHA ? ND + 2 : (VOL == VOL_SPLIT_STD ? NV + ND + 1 : ND * NV));
+                              : (VOL == VOL_SPLIT_CHA ? ND + 2 : (VOL == VOL_SPLIT_STD ? NV + ND + 1 : (HYBRID ? NV : ND * NV)));
     static constexpr int NPART = ND * NV;
     static constexpr int NUB = WS ? 3 : 2;                // state buffers
     static constexpr int NAB = WS ? 2 : 1;                // node-data buffers
@@ -145,7 +148,7 @@ struct LCfg {
 #ifdef FLOU_LINE_MINB
         FLOU_LINE_MINB;
 #else
-        (NP * (NAUX + NV) > 64) ? 1 : 2;
+        (HYBRID || NP * (NAUX + NV) > 64) ? 1 : 2;
 #endif
 };
 
@@ -157,13 +160,13 @@ struct LCfg {
 template <int ND, bool FAST>
 __device__ __forceinline__ void tp_cha_axis(double r1, const double *hv1, double b1,
                                             double r2, const double *hv2, double b2,
-                                            double inv_gm1, double *F, bool &redo)
+                                            double inv_gm1, double *F, int &redo)
 {
     const double rs = r1 + r2, bs = b1 + b2;
     const double irb = fast_rcp(rs * bs);
     const double irs = irb * bs, ibs = irb * rs;
     double Fr, Fb;
-    if (FAST) redo |= logmean_F2_series(r1, r2, irs, b1, b2, ibs, Fr, Fb);
+    if (FAST) logmean_F2_series(r1, r2, irs, b1, b2, ibs, Fr, Fb, redo);
     else logmean_F2(r1, r2, irs, b1, b2, ibs, Fr, Fb);
     const double rho = 0.5 * rs * fast_rcp(Fr);
     const double p = rs * ibs * 0.5;
@@ -185,13 +188,13 @@ __device__ __forceinline__ void tp_cha_axis(double r1, const double *hv1, double
 template <int ND, bool FAST>
 __device__ __forceinline__ void tp_cha_n(double r1, const double *hv1, double b1,
                                          double r2, const double *hv2, double b2,
-                                         double inv_gm1, const double *n, double *F, bool &redo)
+                                         double inv_gm1, const double *n, double *F, int &redo)
 {
     const double rs = r1 + r2, bs = b1 + b2;
     const double irb = fast_rcp(rs * bs);
     const double irs = irb * bs, ibs = irb * rs;
     double Fr, Fb;
-    if (FAST) redo |= logmean_F2_series(r1, r2, irs, b1, b2, ibs, Fr, Fb);
+    if (FAST) logmean_F2_series(r1, r2, irs, b1, b2, ibs, Fr, Fb, redo);
     else logmean_F2(r1, r2, irs, b1, b2, ibs, Fr, Fb);
     const double rho = 0.5 * rs * fast_rcp(Fr);
     const double p = rs * ibs * 0.5;
@@ -234,7 +237,7 @@ template <class C, bool FAST, int J, int L>
 __device__ __forceinline__ void cha_pair_rec(const KParams &P, const double (&r)[C::NP], const double (&hv)[C::NP][C::ND],
                                              const double (&b)[C::NP],
                                              const double (&mt)[C::CART ? 1 : C::NP][C::CART ? 1 : C::ND],
-                                             double (&a_)[C::NP][C::NV], bool &redo)
+                                             double (&a_)[C::NP][C::NV], int &redo)
 {
     constexpr int ND = C::ND, NP = C::NP, NV = C::NV;
     if constexpr (L < NP) {
@@ -268,7 +271,7 @@ __device__ __forceinline__ bool cha_pairs(const KParams &P, const double (&r)[C:
                                           double (&a_)[C::NP][C::NV])
 {
     constexpr int ND = C::ND, NP = C::NP, NV = C::NV;
-    bool redo = false;
+    int redo = 0;        // running maximum of the series arguments (high words)
     // the diagonal of D# is analytically zero on GLL nodes; when the host found entries that are
     // not round-off (diag_mask), the line goes to the exact path, which applies them
     if (FAST) {
@@ -288,7 +291,93 @@ __device__ __forceinline__ bool cha_pairs(const KParams &P, const double (&r)[C:
         }
     }
     cha_pair_rec<C, FAST, 0, 1>(P, r, hv, b, mt, a_, redo);
-    return redo;
+    return FAST && series_out_of_range(redo);
+}
+
+// HybridDivOperator, volume term of ONE line in direction D (_vol_hybrid_tensorproduct!,
+// OpDivergence.jl:557-612) on a Cartesian sub-grid (frames PhysicalRegions.jl:72-148: n = e_D,
+// sub-cell face Jacobian = the element's metric factor of direction D):
+//   Fbar[ii] = sum_{il < ii <= ik} 2 w[il] D[il,ik] F#(Q_il, Q_ik)       telescopic split form
+//   Fv       = rotate2phys(F*(rotate2face(Q_{ii-1}), rotate2face(Q_ii))) * Js     sub-cell FV flux
+//   b        = (W_ii - W_{ii-1}) . (Fbar[ii] - Fv),   delta = max((sqrt(b^2+c) - b)/sqrt(b^2+c), 1/2)
+//   Fbar[ii] = (1 - delta) Fv + delta Fbar[ii];       dQ_ii += (Fbar[ii] - Fbar[ii+1]) / w[ii]
+// Each pair flux is evaluated once and added to every sub-cell interface between its two nodes.
+template <class C, int D>
+__device__ __forceinline__ void hybrid_line(const KParams &P, const double (&Q)[C::NP][C::NV],
+                                            double (&acc)[C::NP][C::NV])
+{
+    constexpr int ND = C::ND, NP = C::NP, NV = C::NV, EQ = C::EQ;
+    const double g = P.fp.gamma;
+    const double js = P.cmet[D];
+    double vel[NP][ND], hv[NP][ND], q[NP], pr[NP], beta[NP], W[NP][NV];
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        NodeAux<ND> A;
+        node_aux<ND>(Q[j], g, A);
+        double m2 = 0.0, q_ = 0.0;
+#pragma unroll
+        for (int c = 0; c < ND; c++) {
+            vel[j][c] = A.vel[c]; hv[j][c] = 0.5 * A.vel[c];
+            q_ += A.vel[c] * A.vel[c];
+            m2 += Q[j][1 + c] * Q[j][1 + c];
+        }
+        q[j] = q_; pr[j] = A.p; beta[j] = A.beta;
+        // vars_cons2entropy (FlouCommon/Euler.jl:273-307), entropy :202-206
+        const double s = log(A.p) - g * log(Q[j][0]);
+        W[j][0] = (g - s) / (g - 1.0) - m2 / Q[j][0] / (2.0 * A.p);
+#pragma unroll
+        for (int c = 0; c < ND; c++) W[j][1 + c] = Q[j][1 + c] / A.p;
+        W[j][ND + 1] = -Q[j][0] / A.p;
+    }
+    double n[ND];
+#pragma unroll
+    for (int c = 0; c < ND; c++) n[c] = (c == D) ? js : 0.0;
+
+    double Fb[NP + 1][NV];
+#pragma unroll
+    for (int ii = 0; ii <= NP; ii++)
+#pragma unroll
+        for (int v = 0; v < NV; v++) Fb[ii][v] = 0.0;
+#pragma unroll
+    for (int il = 0; il < NP - 1; il++)
+#pragma unroll
+        for (int ik = il + 1; ik < NP; ik++) {
+            double F[NV];
+            if (P.tpflux == FX_CHA)
+                tp_chandrasekhar<ND>(Q[il][0], hv[il], q[il], beta[il], Q[ik][0], hv[ik], q[ik], beta[ik],
+                                     P.fp.inv_gm1, n, F);
+            else
+                tp_stdavg<ND>(Q[il], vel[il], pr[il], Q[ik], vel[ik], pr[ik], n, F);
+            const double c = 2.0 * P.w1d[il] * P.Dvol[il + NP * ik];
+#pragma unroll
+            for (int ii = il + 1; ii <= ik; ii++)
+#pragma unroll
+                for (int v = 0; v < NV; v++) Fb[ii][v] = fma(c, F[v], Fb[ii][v]);
+        }
+#pragma unroll
+    for (int ii = 1; ii < NP; ii++) {
+        double Rl[NV], Rr[NV], Fn[NV], Fv[NV];
+        rot2face_c<ND, EQ, 2 * D + 1>(Q[ii - 1], Rl);
+        rot2face_c<ND, EQ, 2 * D + 1>(Q[ii], Rr);
+        euler_numflux<ND>(P.fp, Rl, Rr, Fn);
+        rot2phys_c<ND, EQ, 2 * D + 1>(Fn, Fv);
+        double b = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            Fv[v] *= js;
+            b += (W[ii][v] - W[ii - 1][v]) * (Fb[ii][v] - Fv[v]);
+        }
+        double delta = sqrt(b * b + P.blend);                 // _hybrid_compute_delta (Fisher)
+        delta = (delta - b) / delta;
+        delta = fmax(delta, 0.5);
+#pragma unroll
+        for (int v = 0; v < NV; v++) Fb[ii][v] = (1.0 - delta) * Fv[v] + delta * Fb[ii][v];
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[j][v] = (Fb[j][v] - Fb[j + 1][v]) / P.w1d[j];
+    }
 }
 
 // One line task: volume term of the line's NP nodes in direction d plus the lift of the two face
@@ -324,7 +413,16 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
 #pragma unroll
             for (int v = 0; v < NV; v++) acc[j][v] = 0.0;
 
-        if (!SPLIT) {
+        if constexpr (C::HYBRID) {
+            double Qj[NP][NV];
+#pragma unroll
+            for (int j = 0; j < NP; j++)
+#pragma unroll
+                for (int v = 0; v < NV; v++) Qj[j][v] = sA[v * N + base + j * stride];
+            if (d == 0) hybrid_line<C, 0>(P, Qj, acc);
+            else if (ND >= 2 && d == 1) hybrid_line<C, (ND >= 2 ? 1 : 0)>(P, Qj, acc);
+            else if (ND >= 3) hybrid_line<C, (ND >= 3 ? 2 : 0)>(P, Qj, acc);
+        } else if (!SPLIT) {
             // strong form: dQ[line] -= Ds * F~[line, d]
 #pragma unroll
             for (int v = 0; v < NV; v++) {
@@ -468,6 +566,14 @@ __device__ __forceinline__ void node_data(const KParams &P, const double (&Q)[C:
     constexpr int ND = C::ND, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
     constexpr bool CART = C::CART, SPLIT = C::SPLIT;
     double met[(CART || SPLIT) ? 1 : ND * ND];
+    if constexpr (C::HYBRID) {
+        NodeAux<ND> A;
+        node_aux<ND>(Q, P.fp.gamma, A);
+        if (!(Q[0] > 0.0) || !(A.p > 0.0)) atomicOr(P.status, 1);
+#pragma unroll
+        for (int v = 0; v < NV; v++) ax[v] = Q[v];
+        return;
+    }
     if (!CART && !SPLIT) {
 #pragma unroll
         for (int m = 0; m < ND * ND; m++) met[m] = __ldg(P.metric + dof + P.ndof * m);

@@ -22,7 +22,9 @@
 namespace flou {
 
 enum : int { EQ_ADV = FLOU_B200_EQ_LINEAR_ADVECTION, EQ_EULER = FLOU_B200_EQ_EULER };
-enum : int { VOL_STRONG = 0, VOL_SPLIT_STD = 1, VOL_SPLIT_CHA = 2 };
+// VOL_HYBRID: HybridDivOperator (telescopic split form blended with sub-cell finite volumes,
+// OpDivergence.jl:452-612); line kernel only, two-point flux selected at run time (KParams::tpflux)
+enum : int { VOL_STRONG = 0, VOL_SPLIT_STD = 1, VOL_SPLIT_CHA = 2, VOL_HYBRID = 3 };
 enum : int { FX_STD = FLOU_B200_FLUX_STDAVERAGE, FX_LXF = FLOU_B200_FLUX_LXF,
              FX_CHA = FLOU_B200_FLUX_CHANDRASEKHAR, FX_SCA = FLOU_B200_FLUX_SCALARDISSIPATION,
              FX_MAT = FLOU_B200_FLUX_MATRIXDISSIPATION };
@@ -71,16 +73,24 @@ __device__ __forceinline__ void logmean_F2(double a1, double a2, double ia, doub
     }
 }
 
-// Branch-free variant for the line kernel: series only; the return value says whether either
-// argument pair lies outside the series range (the caller then redoes its work with logmean_F2).
-__device__ __forceinline__ bool logmean_F2_series(double a1, double a2, double ia, double b1, double b2,
-                                                  double ib, double &Fa, double &Fb)
+// Branch-free variant for the line kernel: series only.  `umax` accumulates (as an integer
+// maximum of the high words, exact for non-negative doubles and one ALU instruction per value
+// instead of a DSETP/FSEL/SEL triple) the largest u = f^2 met so far; series_out_of_range(umax)
+// says whether some argument pair lies outside the series range, in which case the caller redoes
+// its work with logmean_F2.  The high-word test is conservative by < 2^-20 relative: values that
+// close below the threshold take the exact path, which applies the reference's own test.
+__device__ __forceinline__ void logmean_F2_series(double a1, double a2, double ia, double b1, double b2,
+                                                  double ib, double &Fa, double &Fb, int &umax)
 {
     const double fa = (a1 - a2) * ia, fb = (b1 - b2) * ib;
     const double ua = fa * fa, ub = fb * fb;
     Fa = 1.0 + ua * (1.0 / 3.0 + ua * (1.0 / 5.0 + ua * (1.0 / 7.0)));
     Fb = 1.0 + ub * (1.0 / 3.0 + ub * (1.0 / 5.0 + ub * (1.0 / 7.0)));
-    return (ua >= 0.01) | (ub >= 0.01);
+    umax = max(umax, max(__double2hiint(ua), __double2hiint(ub)));
+}
+__device__ __forceinline__ bool series_out_of_range(int umax)
+{
+    return umax >= 0x3F847AE1;      // high word of 0.01 = 0x3F847AE147AE147B
 }
 
 static __device__ __noinline__ double log_ratio_slow(double al, double ar) { return log(al / ar); }

@@ -92,6 +92,10 @@ struct KParams {
     double cfjac[3];            // face jac by direction
     double rcmet[3];            // 1/cmet (line kernel: lift pre-division in the folded split form)
     int diag_mask;              // bit j: |Dvol[j,j]| is not round-off (line kernel, split form)
+    // HybridDivOperator (VOL_HYBRID): Dvol = std.D, 1-D quadrature weights, op.blend, op.tpflux
+    double w1d[8];
+    double blend;
+    int tpflux;
     int prefetch_groups;        // line kernel: CTAs resident on the device (L2 prefetch distance)
     // general geometry, device SoA
     const double *jac;          // [dof]

@@ -8,7 +8,7 @@ from ._lib import DomainError, FlouB200Error, LIB_PATH, device_count, lib
 from .disc import EquationConfig, MultielementDisc, nccl_unique_id, rhs
 from .equations import (ChandrasekharAverage, EulerEquation, EulerInflowBC, EulerOutflowBC,
                         EulerSlipBC, GenericBC, LinearAdvection, LxF, MatrixDissipation,
-                        ScalarDissipation, SplitDivOperator, StdAverage, StrongDivOperator,
+                        HybridDivOperator, ScalarDissipation, SplitDivOperator, StdAverage, StrongDivOperator,
                         gaussian_bump, normal_shockwave, nvariables, soundvelocity, spatialdim,
                         vars_prim2cons)
 from .gmshmesh import RawMesh, UnstructuredMesh, read_msh, refine, write_msh

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("FLOU_B200_LIB") or os.path.join(_HERE, "libflou_b200.
 OK, EINVAL, ECUDA, ENCCL, EDOMAIN, EUNSUPPORTED = range(6)
 
 EQ_LINEAR_ADVECTION, EQ_EULER = 0, 1
-OP_STRONG, OP_SPLIT = 0, 1
+OP_STRONG, OP_SPLIT, OP_HYBRID = 0, 1, 2
 FLUX_STDAVERAGE, FLUX_LXF, FLUX_CHANDRASEKHAR, FLUX_SCALARDISSIPATION, FLUX_MATRIXDISSIPATION = range(5)
 BC_INFLOW, BC_OUTFLOW, BC_SLIP, BC_TABLE = range(4)
 GEOM_CARTESIAN, GEOM_GENERAL = 0, 1
@@ -50,7 +50,7 @@ class Desc(C.Structure):
         ("bc_faces", C.c_void_p), ("bc_state", C.c_void_p), ("bc_table", C.c_void_p),
         ("elem_begin", C.c_int64), ("elem_end", C.c_int64),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("part_offsets", C.c_void_p),
-        ("device", C.c_int32), ("flags", C.c_int32),
+        ("device", C.c_int32), ("flags", C.c_int32), ("blend", C.c_double),
     ]
 
 

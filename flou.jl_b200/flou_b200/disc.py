@@ -41,6 +41,12 @@ class MultielementDisc:
         if op.kind == L.OP_SPLIT and not std.basis.hasboundaries:
             raise ValueError("SplitDivOperator on Gauss nodes (the reference's sub-grid surface "
                              "path, OpDivergence.jl:301-437) is not on the B200 hot path yet")
+        if op.kind == L.OP_HYBRID:
+            if equation.kind != L.EQ_EULER:
+                raise ValueError("HybridDivOperator needs entropy variables: Euler equations only")
+            if not std.basis.hasboundaries:
+                raise ValueError("HybridDivOperator on Gauss nodes (the reference's all-surface path, "
+                                 "OpDivergence.jl:647-779) is not on the B200 hot path")
         nd, npn, nv = mesh.nd, std.np, equation.nv
         self.nd, self.np, self.nv = nd, npn, nv
         self.npts, self.nfp = npn ** nd, npn ** (nd - 1)
@@ -81,6 +87,7 @@ class MultielementDisc:
         d.equation = equation.kind
         d.divop = op.kind
         d.tpflux = op.tpflux.kind if op.tpflux is not None else L.FLUX_STDAVERAGE
+        d.blend = float(getattr(op, "blend", 0.0))
         nf_ = op.numflux
         d.numflux = nf_.kind
         d.numflux_avg = getattr(getattr(nf_, "avg", None), "kind", L.FLUX_STDAVERAGE)

@@ -7,6 +7,7 @@ Same names and argument meaning as the reference so user scripts read alike:
   ChandrasekharAverage, ScalarDissipation, MatrixDissipation
                                    src/FlouSpatial/Equations/Euler.jl:167,228-231,303-306
   StrongDivOperator, SplitDivOperator   src/FlouSpatial/Equations/OpDivergence.jl:105,184-194
+  HybridDivOperator                src/FlouSpatial/Equations/OpDivergence.jl:452-477
   EulerInflowBC/OutflowBC/SlipBC   src/FlouSpatial/Equations/Euler.jl:69-94
   GenericBC                        src/FlouSpatial/FlouSpatial.jl:85-91
 These objects only carry parameters; all arithmetic happens in the CUDA library.
@@ -144,6 +145,30 @@ class SplitDivOperator:
             raise ValueError("the two-point flux must be StdAverage or ChandrasekharAverage")
         self.tpflux, self.numflux = tpflux, numflux
         self.kind = L.OP_SPLIT
+
+
+class HybridDivOperator:
+    """HybridDivOperator([tpflux=numflux.avg], numflux, blend)  (OpDivergence.jl:452-477):
+    split form in telescopic (flux-differencing) form, blended sub-cell interface by sub-cell
+    interface with finite-volume fluxes.  As in both of the reference's convenience constructors
+    `fvflux = numflux`; a different `fvflux` (raw four-field constructor) is not offered."""
+
+    def __init__(self, *args):
+        if len(args) == 2:
+            numflux, blend = args
+            if not hasattr(numflux, "avg"):
+                raise TypeError("HybridDivOperator(numflux, blend) needs a flux with an `.avg` "
+                                "(the reference reads numflux.avg)")
+            tpflux = numflux.avg
+        elif len(args) == 3:
+            tpflux, numflux, blend = args
+        else:
+            raise TypeError("HybridDivOperator([tpflux], numflux, blend)")
+        if not isinstance(tpflux, (StdAverage, ChandrasekharAverage)):
+            raise ValueError("the two-point flux must be StdAverage or ChandrasekharAverage")
+        self.tpflux, self.fvflux, self.numflux = tpflux, numflux, numflux
+        self.blend = float(blend)
+        self.kind = L.OP_HYBRID
 
 
 # ------------------------------------------------------------------ boundary conditions

@@ -14,7 +14,8 @@ module FlouB200
 using Flou
 using Flou.FlouCommon: AbstractSpatialDiscretization, EquationConfig, CartesianMesh,
     LinearAdvection, EulerEquation, nvariables, spatialdim, nelements, nfaces
-using Flou.FlouSpatial: MultielementDisc, StrongDivOperator, SplitDivOperator, StdAverage, LxF,
+using Flou.FlouSpatial: MultielementDisc, StrongDivOperator, SplitDivOperator, HybridDivOperator,
+    StdAverage, LxF,
     ChandrasekharAverage, ScalarDissipation, MatrixDissipation, EulerInflowBC, EulerOutflowBC,
     EulerSlipBC, GenericBC, ndofs
 import Flou.FlouCommon: rhs!
@@ -43,6 +44,7 @@ struct Desc
     elem_begin::Int64; elem_end::Int64
     rank::Int32; nranks::Int32; part_offsets::Ptr{Int64}
     device::Int32; flags::Int32
+    blend::Float64
 end
 
 fluxkind(::StdAverage) = Int32(0)
@@ -116,13 +118,16 @@ function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,R
     a = equation isa LinearAdvection ? ntuple(i -> i <= ND ? Float64(equation.a[i]) : 0.0, 3) : (0.0, 0.0, 0.0)
     dx = cart ? ntuple(i -> i <= ND ? Float64(mesh.Δx[i]) : 0.0, 3) : (0.0, 0.0, 0.0)
     ne = nelements(mesh)
+    if op isa HybridDivOperator && op.fvflux !== op.numflux
+        throw(ArgumentError("flou_b200: HybridDivOperator needs fvflux === numflux (both convenience constructors)"))
+    end
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve faceinds facepos eleminds elempos orientation D Ds Dsharp lm lp dgm dgp w1d jac metric fjac frames kinds offsets bcfaces state table begin
         desc = Desc(
             Int32(sizeof(Desc)), Int32(ND), Int32(nv), Int32(size(D, 1)),
             equation isa EulerEquation ? Int32(1) : Int32(0),
-            op isa SplitDivOperator ? Int32(1) : Int32(0),
-            op isa SplitDivOperator ? fluxkind(op.tpflux) : Int32(0),
+            op isa HybridDivOperator ? Int32(2) : (op isa SplitDivOperator ? Int32(1) : Int32(0)),
+            op isa Union{SplitDivOperator,HybridDivOperator} ? fluxkind(op.tpflux) : Int32(0),
             fluxkind(op.numflux), avgkind(op.numflux), cart ? Int32(0) : Int32(1),
             intensity(op.numflux), equation isa EulerEquation ? Float64(equation.γ) : 0.0, a, dx,
             Int64(ne), Int64(nfaces(mesh)),
@@ -133,7 +138,8 @@ function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,R
             cart ? C_NULL : pointer(fjac), cart ? C_NULL : pointer(frames),
             Int32(length(bcs)), pointer(kinds), pointer(offsets), pointer(bcfaces),
             pointer(state), pointer(table),
-            Int64(0), Int64(ne), Int32(0), Int32(1), C_NULL, Int32(device), Int32(0))
+            Int64(0), Int64(ne), Int32(0), Int32(1), C_NULL, Int32(device), Int32(0),
+            op isa HybridDivOperator ? Float64(op.blend) : 0.0)
         check(ccall((:flou_b200_create, lib), Int32, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle))
     end
     b = B200Disc{ND,RT,typeof(disc)}(disc, handle[])

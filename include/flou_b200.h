@@ -49,6 +49,10 @@ extern "C" {
 /* divergence operators: src/FlouSpatial/Equations/OpDivergence.jl:105 (Strong), :184 (Split) */
 #define FLOU_B200_OP_STRONG 0
 #define FLOU_B200_OP_SPLIT  1
+/* HybridDivOperator(tpflux, numflux, blend) (OpDivergence.jl:452-477, volume term :557-612):
+ * telescopic split form blended with sub-cell finite-volume fluxes (fvflux = numflux, as both
+ * convenience constructors set it).  Euler, GLL nodes, Cartesian sub-grids. */
+#define FLOU_B200_OP_HYBRID 2
 
 /* numerical-flux structs: src/FlouSpatial/Interfaces.jl:16-23,
  * src/FlouSpatial/Equations/Euler.jl:167,228-231,303-306 */
@@ -84,7 +88,7 @@ typedef struct flou_b200_desc {
     int32_t np;               /* nodes per direction (p+1), 2..8                             */
     int32_t equation;         /* FLOU_B200_EQ_*                                              */
     int32_t divop;            /* FLOU_B200_OP_*        (disc.operators[1])                   */
-    int32_t tpflux;           /* SplitDivOperator.tpflux: STDAVERAGE | CHANDRASEKHAR         */
+    int32_t tpflux;           /* Split-/HybridDivOperator.tpflux: STDAVERAGE | CHANDRASEKHAR */
     int32_t numflux;          /* operator.numflux kind                                       */
     int32_t numflux_avg;      /* numflux.avg for LxF / Scalar- / MatrixDissipation           */
     int32_t geometry;         /* FLOU_B200_GEOM_*                                            */
@@ -103,7 +107,7 @@ typedef struct flou_b200_desc {
     const uint8_t *orientation; /* nf   : mesh.faces.orientation                             */
 
     /* 1-D operators of the standard region (StdSegment.jl:76-89), np x np column-major */
-    const double *D;          /* std.D   (unused by the kernels, kept for completeness)      */
+    const double *D;          /* std.D   (HybridDivOperator; otherwise unused)               */
     const double *Ds;         /* std.Ds  = D - B                                             */
     const double *Dsharp;     /* std.D♯  = 2D - B                                            */
     const double *lminus;     /* std.l[1]                                                    */
@@ -136,6 +140,7 @@ typedef struct flou_b200_desc {
 
     int32_t device;           /* CUDA device ordinal                                         */
     int32_t flags;            /* FLOU_B200_FLAG_* */
+    double blend;             /* HybridDivOperator.blend (OpDivergence.jl:464)               */
 } flou_b200_desc;
 
 #define FLOU_B200_FLAG_NO_GRAPH 1  /* launch stages directly instead of replaying a CUDA graph */

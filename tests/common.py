@@ -61,7 +61,8 @@ class Case:
 
     def __init__(self, nd, n, npn, nodes="GLL", eq="euler", op="split", tp=None, nf="mat",
                  avg="cha", intensity=1.0, periodic="all", bcs=None, general=False,
-                 perturb_amp=0.0, gamma=1.4, a=(2.0, -1.0, 0.5)):
+                 perturb_amp=0.0, gamma=1.4, a=(2.0, -1.0, 0.5), blend=1.0):
+        self.blend = blend
         self.nd, self.n, self.np, self.nodes = nd, tuple(n), npn, nodes
         self.eq, self.op, self.tp, self.nf, self.avg = eq, op, tp, nf, avg
         self.intensity, self.gamma, self.a = intensity, gamma, tuple(a[:nd])
@@ -78,6 +79,7 @@ class Case:
 
     def __repr__(self):
         return (f"{self.nd}D n={self.n} np={self.np} {self.nodes} {self.eq} {self.op}"
+                f"{'(blend=%g)' % self.blend if self.op == 'hybrid' else ''}"
                 f"{'/' + self.tp if self.tp else ''} {self.nf}({self.avg}) "
                 f"{'general' if self.general else 'cart'} per={len(self.periodic)}")
 
@@ -103,10 +105,10 @@ class Case:
         return O.Problem(
             mesh, self.nodes, self.np,
             O.EQ_ADVECTION if self.eq == "adv" else O.EQ_EULER,
-            O.OP_STRONG if self.op == "strong" else O.OP_SPLIT,
+            {"strong": O.OP_STRONG, "split": O.OP_SPLIT, "hybrid": O.OP_HYBRID}[self.op],
             _FLUX_O[self.nf], tpflux=_FLUX_O[self.tp] if self.tp else None,
             numflux_avg=_FLUX_O[self.avg], intensity=self.intensity, gamma=g, a=self.a,
-            bcs=bcs, cartesian=not self.general)
+            bcs=bcs, cartesian=not self.general, blend=self.blend if self.op == "hybrid" else 0.0)
 
     # ---------------------------------------------------------------- product side
     def product(self, rank=0, nranks=1, device=0, use_graph=True, create=True, kernel="line"):
@@ -130,6 +132,9 @@ class Case:
               "mat": F.MatrixDissipation(avg, self.intensity)}[self.nf]
         if self.op == "strong":
             op = F.StrongDivOperator(nf)
+        elif self.op == "hybrid":
+            tp = {"std": F.StdAverage(), "cha": F.ChandrasekharAverage()}[self.tp or self.avg]
+            op = F.HybridDivOperator(tp, nf, self.blend)
         elif self.tp:
             op = F.SplitDivOperator({"std": F.StdAverage(), "cha": F.ChandrasekharAverage()}[self.tp], nf)
         elif self.nf in ("std", "cha"):

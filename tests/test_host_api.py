@@ -119,3 +119,25 @@ def test_coords_follow_the_reference_node_order():
     assert x.shape == (18, 2)
     assert np.allclose(x[:3, 0], [0.0, 0.5, 1.0]) and np.allclose(x[:3, 1], 0.0)   # x fastest
     assert np.allclose(x[9:12, 0], [1.0, 1.5, 2.0])                                 # element 2
+
+
+def test_hybrid_operator_constructors_and_descriptor():
+    """HybridDivOperator([tpflux], numflux, blend) (OpDivergence.jl:452-477): tpflux defaults to
+    numflux.avg, fvflux = numflux; refused on Gauss nodes and for linear advection."""
+    nf = F.MatrixDissipation(F.ChandrasekharAverage(), 1.0)
+    op = F.HybridDivOperator(nf, 0.25)
+    assert isinstance(op.tpflux, F.ChandrasekharAverage) and op.fvflux is nf and op.numflux is nf
+    assert isinstance(F.HybridDivOperator(F.StdAverage(), nf, 1.0).tpflux, F.StdAverage)
+    with pytest.raises(TypeError):
+        F.HybridDivOperator(F.StdAverage(), 1.0)          # no `.avg` to read the two-point flux from
+    with pytest.raises(ValueError):
+        F.HybridDivOperator(F.LxF(F.StdAverage(), 1.0), nf, 1.0)
+    mesh = F.CartesianMesh(2, (0, 0), (1, 1), (3, 3)).apply_periodicBCs(("1", "2"), ("3", "4"))
+    eq = F.EulerEquation(2, 1.4)
+    d = F.MultielementDisc(mesh, _std(2), eq, op, {}, create=False)._desc
+    assert (d.divop, d.tpflux, d.numflux, d.blend) == (
+        L.OP_HYBRID, L.FLUX_CHANDRASEKHAR, L.FLUX_MATRIXDISSIPATION, 0.25)
+    with pytest.raises(ValueError):
+        F.MultielementDisc(mesh, _std(2, nodes="GL"), eq, op, {}, create=False)
+    with pytest.raises(ValueError):
+        F.MultielementDisc(mesh, _std(2, nv=1), F.LinearAdvection(1.0, 1.0), op, {}, create=False)

@@ -161,3 +161,35 @@ def test_max_dt_follows_the_reference_rule(case):
         p = (case.gamma - 1) * (E - 0.5 * rho * np.sum(vel ** 2, axis=1))
         want = np.min(cfl * dx / (np.sqrt(np.sum(vel ** 2, axis=1)) + np.sqrt(case.gamma * p / rho)))
     assert abs(orc.max_dt(Q, cfl) / want - 1) <= 1e-13
+
+
+# ------------------------------------------------------------------ HybridDivOperator (row f2)
+def _hybrid_case(nd, n, npn, blend, **kw):
+    from common import Case
+    return Case(nd, n, npn, op="hybrid", nf="mat", avg="cha", blend=blend, **kw)
+
+
+@pytest.mark.parametrize("nd,n,npn", [(1, (7,), 4), (2, (4, 3), 5), (3, (2, 3, 2), 4)])
+def test_hybrid_tends_to_split_form_for_large_blend(nd, n, npn):
+    """delta = max((sqrt(b^2+c) - b)/sqrt(b^2+c), 1/2) -> 1 as c -> inf, and the telescopic form
+    with delta = 1 IS the split form (OpDivergence.jl:442-450): pins the sub-cell flux assembly
+    2 w[il] D[il,ik] F#(l,k) and the flux differencing against the independently pinned
+    SplitDivOperator."""
+    from common import Case, random_state, relerr
+    hy = _hybrid_case(nd, n, npn, 1e40).oracle()
+    sp = Case(nd, n, npn, op="split", nf="mat", avg="cha").oracle()
+    Q = random_state(hy.ndof, nd, "euler")
+    assert relerr(hy.rhs(Q), sp.rhs(Q)) <= 1e-12
+
+
+@pytest.mark.parametrize("nd,n,npn", [(2, (4, 3), 4), (3, (2, 2, 3), 3)])
+def test_hybrid_conservation_and_free_stream(nd, n, npn):
+    from common import random_state
+    pb = _hybrid_case(nd, n, npn, 1.0).oracle()
+    Q = random_state(pb.ndof, nd, "euler")
+    dQ = pb.rhs(Q)
+    w = pb.jac * np.tile(pb.weights, pb.ne)
+    total = np.abs(w @ dQ)
+    assert np.all(total <= 1e-12 * np.abs(w) @ np.abs(dQ))
+    Qc = np.tile(Q[:1], (pb.ndof, 1))
+    assert np.max(np.abs(pb.rhs(np.asfortranarray(Qc)))) <= 1e-11

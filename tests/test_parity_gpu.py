@@ -196,6 +196,87 @@ def test_sod_tube_kat_on_gpu(gpu):
     dg.close()
 
 
+# ------------------------------------------------------------------ row f2: HybridDivOperator
+HYBRID_CASES = [
+    Case(1, (10,), 4, op="hybrid", nf="mat", avg="cha", blend=1.0),
+    Case(2, (5, 4), 6, op="hybrid", nf="mat", avg="cha", blend=1.0),          # Shockwave2D's operator
+    Case(2, (4, 5), 4, op="hybrid", tp="std", nf="lxf", avg="std", blend=1e-3),
+    Case(2, (4, 3), 5, op="hybrid", tp="cha", nf="sca", avg="cha", blend=0.05),
+    Case(3, (3, 2, 3), 4, op="hybrid", nf="mat", avg="cha", blend=1.0),
+    Case(3, (2, 3, 2), 3, op="hybrid", tp="std", nf="cha", avg="cha", blend=0.2),
+    Case(2, (5, 4), 4, op="hybrid", nf="mat", avg="cha", blend=1.0, periodic=[("3", "4")],
+         bcs={"1": ("inflow", [1.1, 0.33, 0.02, 2.6]), "2": ("outflow", None)}),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", HYBRID_CASES, ids=repr)
+@pytest.mark.parametrize("state", ["random", "smooth"])
+def test_hybrid_rhs_matches_oracle(gpu, case, state):
+    """HybridDivOperator (OpDivergence.jl:452-612) on the device vs the oracle restatement that
+    reproduces the reference's Shockwave2D value; RHS and the state after a few RK steps."""
+    import flou_b200 as F
+    import oracle as O
+    orc = case.oracle()
+    disc, eq = case.product()
+    Q = (random_state(orc.ndof, case.nd, case.eq, amp=case.amp) if state == "random"
+         else smooth_state(orc.coords, case.nd, case.eq))
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert np.all(np.isfinite(dQ))
+    assert relerr(dQ, orc.rhs(Q)) <= RHS_TOL
+    u = Q.copy(order="F")
+    sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), 4e-4, dt=1e-4)
+    assert relerr(sol.u[-1], orc.lsrk2n(Q, O.ORK256, 1e-4, 4)) <= 1e-10
+    disc.close()
+
+
+@pytest.mark.gpu
+def test_shockwave_2d_kat_on_gpu(gpu):
+    """The reference's only 2-D known-answer test (test/runtests.jl:40-44, setup
+    test/tests.jl:136-185) through the CUDA path: 11x3 elements, GLL(6),
+    HybridDivOperator(MatrixDissipation(ChandrasekharAverage(), 1.0), 1.0), y-periodic, GenericBC
+    in x, ORK256, dt = 1e-2, tf = 1: maximum(u(tf)) to the reference's rtol 1e-7."""
+    import flou_b200 as F
+    eq = F.EulerEquation(2, 1.4)
+    basis = F.LagrangeBasis("GLL", 6)
+    std = F.StdQuad(basis, F.DGSEMrec(basis), eq.nv)
+    mesh = F.CartesianMesh(2, (-1, 0), (1, 1), (11, 3))
+    mesh.apply_periodicBCs(("3", "4"))
+    rho0, M0, p0 = 1.0, 2.0, 1.0
+    u0 = M0 * F.soundvelocity(rho0, p0, eq)
+    rho1, u1, p1 = F.normal_shockwave(rho0, u0, p0, eq)
+    Q0 = F.vars_prim2cons((rho0, u0, 0.0, p0), eq)
+    Q1 = F.vars_prim2cons((rho1, u1, 0.0, p1), eq)
+
+    def Qext(_, xy, __, ___, ____):
+        return Q0 if xy[0] < 0 else Q1
+    bcs = {"1": F.GenericBC(Qext), "2": F.GenericBC(Qext)}
+    op = F.HybridDivOperator(F.MatrixDissipation(F.ChandrasekharAverage(), 1.0), 1.0)
+    dg = F.MultielementDisc(mesh, std, eq, op, bcs)
+    Q = dg.new_state()
+    for i, xy in enumerate(dg.coords()):
+        Q[i] = Qext((), xy, (), 0.0, eq)
+    sol, _ = F.timeintegrate(Q, dg, eq, F.ORK256(williamson_condition=False), 1.0,
+                             dt=1e-2, adaptive=False, alias_u0=True)
+    assert abs(sol.u[-1].max() / 12.977466260673845 - 1) <= 1e-7
+    assert abs(sol.u[-1].min()) < 1e-9
+    dg.close()
+
+
+@pytest.mark.gpu
+def test_hybrid_unsupported_combinations_raise(gpu):
+    """No silent fallback: Gauss nodes, advection, curved sub-grids and the fused / node kernels
+    are refused for the hybrid operator."""
+    import flou_b200 as F
+    with pytest.raises(ValueError):
+        Case(2, (3, 3), 4, nodes="GL", op="hybrid").product()
+    with pytest.raises(ValueError):
+        Case(2, (3, 3), 4, op="hybrid", perturb_amp=0.05).product()
+    with pytest.raises(ValueError):
+        Case(2, (3, 3), 4, op="hybrid").product(kernel="fused")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [
     Case(1, (9,), 4), Case(2, (5, 4), 5), Case(3, (3, 2, 3), 4), Case(3, (2, 2, 2), 5, perturb_amp=0.08),
