@@ -20,6 +20,7 @@
 #include "flou_b200.h"
 #include "launch.h"
 #include "cfl_kernel.cuh"
+#include "monitor_kernel.cuh"
 
 using namespace flou;
 
@@ -366,6 +367,12 @@ struct flou_b200_handle {
     unsigned long long *dt_bits = nullptr;
     double gamma = 0.0, anorm = 0.0;
     int equation = 0;
+    // monitors / Zhang-Shu limiter (row f3)
+    double *w_nodes = nullptr;           // tensor-product quadrature weights of one element [npts]
+    double *mon_partial = nullptr;       // per-block partial sums + the result in the last slot
+    int mon_blocks = 0;
+    bool stage_limiter = false;          // advance(): limiter after every RK stage (stage_limiter!)
+    double limiter_minval = 0.0;
     // two-kernel path
     bool split_faces = true;
     bool line_kernel = true;             // element kernel of the two-kernel stage: line per thread
@@ -483,6 +490,28 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
     return FLOU_B200_OK;
 }
 
+// zhang_shu_limiter (Equations/Euler.jl:616-660) on a device state, in place; the x-face traces
+// of that state are stale afterwards
+int32_t launch_zhang_shu(flou_b200_handle *h, double *u, double minval)
+{
+    const int threads = 256, warps_per_block = threads / 32;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int64_t want = (h->ne_local + warps_per_block - 1) / warps_per_block;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * 8));
+    const double *jac = h->base.jac;     // nullptr on Cartesian meshes
+    switch (h->nv) {
+    case 3: zhang_shu_kernel<3><<<grid, threads, 0, h->stream>>>(u, h->ndof, h->ne_local, h->npts, h->gamma, minval, h->w_nodes, jac, h->base.cjac); break;
+    case 4: zhang_shu_kernel<4><<<grid, threads, 0, h->stream>>>(u, h->ndof, h->ne_local, h->npts, h->gamma, minval, h->w_nodes, jac, h->base.cjac); break;
+    case 5: zhang_shu_kernel<5><<<grid, threads, 0, h->stream>>>(u, h->ndof, h->ne_local, h->npts, h->gamma, minval, h->w_nodes, jac, h->base.cjac); break;
+    default: return fail(FLOU_B200_EINVAL, "the Zhang-Shu limiter is defined for the Euler equations");
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    h->traces_valid = false;
+    return FLOU_B200_OK;
+}
+
 int32_t run_steps_direct(flou_b200_handle *h, int nstages, const double *A, const double *B,
                          double dt, int64_t nsteps)
 {
@@ -492,6 +521,12 @@ int32_t run_steps_direct(flou_b200_handle *h, int nstages, const double *A, cons
                                         h->u[h->cur], h->u[h->cur ^ 1]);
             if (rc) return rc;
             h->cur ^= 1;
+            if (h->stage_limiter) {
+                // OrdinaryDiffEq's `stage_limiter!(u, integrator, p, t)` after every stage update
+                // (examples/src/3D_Euler.jl:76-80)
+                const int32_t rl = launch_zhang_shu(h, h->u[h->cur], h->limiter_minval);
+                if (rl) return rl;
+            }
         }
     return FLOU_B200_OK;
 }
@@ -579,20 +614,6 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     if (flou_b200_device_count() <= d->device || d->device < 0)
         return fail(FLOU_B200_ECUDA, "no usable CUDA device (this library has no CPU path)");
     CUDA_TRY(cudaSetDevice(d->device));
-    {
-        // L2 <- HBM fetch granularity.  The face-flux kernel reads the y-face node layers of u as
-        // 40..64-byte runs (np doubles); with the default 64-byte granularity every run that
-        // straddles a 64-byte boundary pulls 128 bytes (ncu at cfg4: 20.5 GB read for 12.6 GB of
-        // traces).  FLOU_B200_L2_FETCH=32|64|128 overrides the device default (a hint; ignored
-        // where the device does not support it).
-        if (const char *s = std::getenv("FLOU_B200_L2_FETCH")) {
-            const int g = std::atoi(s);
-            if (g == 32 || g == 64 || g == 128) {
-                if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g) != cudaSuccess) cudaGetLastError();
-            }
-        }
-    }
-
     Plan pl;
     if (int32_t rc = build_plan(d, cart, pl)) return rc;
 
@@ -791,6 +812,11 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         for (int c = 0; c < nd; c++) a2 += d->a[c] * d->a[c];
         h->anorm = std::sqrt(a2);
         H_TRY(cudaMalloc((void **)&h->dt_bits, sizeof(unsigned long long)));
+        H_TRY(upload(&h->w_nodes, w));
+        int sms_ = 148;
+        cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, h->device);
+        h->mon_blocks = sms_ * 4;
+        H_TRY(cudaMalloc((void **)&h->mon_partial, sizeof(double) * (size_t)(h->mon_blocks + 1)));
     }
     H_TRY(upload(&h->send_list, send_list));
     H_TRY(upload(&h->interior_list, interior));
@@ -848,7 +874,7 @@ int32_t flou_b200_destroy(flou_b200_handle *h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void *ptrs[] = {h->u[0], h->u[1], h->tr[0], h->tr[1], h->tr_all, h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
                     h->frames, h->faces, h->econn, h->Fn, h->elem_dx, h->dt_bits, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
-                    h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list};
+                    h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list, h->w_nodes, h->mon_partial};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev_emit) cudaEventDestroy(h->ev_emit);
@@ -865,6 +891,7 @@ int32_t flou_b200_upload_state(flou_b200_handle *h, const double *Q)
 {
     if (!h || !Q) return fail(FLOU_B200_EINVAL, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));     // a new state: flags start over
     CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, sizeof(double) * (size_t)h->ndof * h->nv,
                              cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -912,6 +939,64 @@ int32_t flou_b200_max_dt(flou_b200_handle *h, const double *Q, double cfl, doubl
     CUDA_TRY(cudaMemcpyAsync(&out, h->dt_bits, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     *dt = out;
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_monitor(flou_b200_handle *h, int32_t kind, const double *Q, double *value)
+{
+    if (!h || !value) return fail(FLOU_B200_EINVAL, "null argument");
+    if (h->equation != FLOU_B200_EQ_EULER)
+        return fail(FLOU_B200_EINVAL, "monitors are defined for the Euler equations (list_monitors)");
+    if (kind != FLOU_B200_MONITOR_KINETIC_ENERGY && kind != FLOU_B200_MONITOR_ENTROPY)
+        return fail(FLOU_B200_EINVAL, "unknown monitor");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (Q) {
+        CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, sizeof(double) * (size_t)h->ndof * h->nv,
+                                 cudaMemcpyHostToDevice, h->stream));
+        h->traces_valid = false;
+    }
+    const int threads = 256;
+    const int64_t want = (h->ndof + threads - 1) / threads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, h->mon_blocks));
+    double *out = h->mon_partial + h->mon_blocks;
+    monitor_kernel<<<grid, threads, 0, h->stream>>>(h->u[h->cur], h->ndof, h->npts, h->nd, kind, h->gamma,
+                                                    h->w_nodes, h->base.jac, h->base.cjac, h->mon_partial);
+    CUDA_TRY(cudaGetLastError());
+    monitor_reduce_kernel<<<1, 256, 0, h->stream>>>(h->mon_partial, grid, out);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    if (h->nranks > 1) {
+        if (!h->comm) return fail(FLOU_B200_EINVAL, "partitioned handle used before flou_b200_comm_init");
+        NCCL_TRY(g_nccl.AllReduce(out, out, 1, ncclFloat64, 0 /* ncclSum */, h->comm, h->stream));
+    }
+    double v = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(&v, out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *value = v;
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_zhang_shu(flou_b200_handle *h, double *Q, double minval)
+{
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    if (h->equation != FLOU_B200_EQ_EULER)
+        return fail(FLOU_B200_EINVAL, "the Zhang-Shu limiter is defined for the Euler equations (list_limiters)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * (size_t)h->ndof * h->nv;
+    if (Q) CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (int32_t rc = launch_zhang_shu(h, h->u[h->cur], minval)) return rc;
+    if (Q) CUDA_TRY(cudaMemcpyAsync(Q, h->u[h->cur], bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_set_stage_limiter(flou_b200_handle *h, int32_t enable, double minval)
+{
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    if (enable && h->equation != FLOU_B200_EQ_EULER)
+        return fail(FLOU_B200_EINVAL, "the Zhang-Shu limiter is defined for the Euler equations (list_limiters)");
+    h->stage_limiter = enable != 0;
+    h->limiter_minval = enable ? minval : 0.0;
     return FLOU_B200_OK;
 }
 
@@ -977,6 +1062,7 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
         key.push_back((double)nstages); key.push_back(dt);
         key.insert(key.end(), A, A + nstages);
         key.insert(key.end(), B, B + nstages);
+        key.push_back(h->stage_limiter ? 1.0 : 0.0); key.push_back(h->limiter_minval);
         const int gi = h->cur;           // two steps bring u back to the buffer they started in
         if (!h->graph[gi] || key != h->graph_key[gi]) {
             if (h->graph[gi]) cudaGraphExecDestroy(h->graph[gi]);
@@ -984,8 +1070,8 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
             cudaGraph_t g = nullptr;
             const int cur0 = h->cur;
             const int64_t l0 = h->launches;
-            // Gauss nodes: every captured pass starts with its own trace emit
-            if (!h->colloc) h->traces_valid = false;
+            // Gauss nodes / stage limiter: every captured pass starts with its own trace emit
+            if (!h->colloc || h->stage_limiter) h->traces_valid = false;
             CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             const int32_t rc = run_steps_direct(h, nstages, A, B, dt, 2);
             cudaError_t e = cudaStreamEndCapture(h->stream, &g);
@@ -1003,7 +1089,7 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
             CUDA_TRY(cudaGraphLaunch(h->graph[gi], h->stream));
             h->launches += h->graph_launches_per_replay;
             done += 2;
-            h->traces_valid = h->colloc;
+            h->traces_valid = h->colloc && !h->stage_limiter;
         }
     }
     return run_steps_direct(h, nstages, A, B, dt, nsteps - done);

@@ -86,7 +86,11 @@ __device__ __forceinline__ void logmean_F2_series(double a1, double a2, double i
     const double ua = fa * fa, ub = fb * fb;
     Fa = 1.0 + ua * (1.0 / 3.0 + ua * (1.0 / 5.0 + ua * (1.0 / 7.0)));
     Fb = 1.0 + ub * (1.0 / 3.0 + ub * (1.0 / 5.0 + ub * (1.0 / 7.0)));
+#ifdef FLOU_REDO_FP      // A/B: the earlier floating-point test (DSETP/FSEL/SEL per value)
+    if ((ua >= 0.01) | (ub >= 0.01)) umax = 0x7FFFFFFF;
+#else
     umax = max(umax, max(__double2hiint(ua), __double2hiint(ub)));
+#endif
 }
 __device__ __forceinline__ bool series_out_of_range(int umax)
 {

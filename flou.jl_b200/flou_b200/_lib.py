@@ -17,6 +17,7 @@ OP_STRONG, OP_SPLIT, OP_HYBRID = 0, 1, 2
 FLUX_STDAVERAGE, FLUX_LXF, FLUX_CHANDRASEKHAR, FLUX_SCALARDISSIPATION, FLUX_MATRIXDISSIPATION = range(5)
 BC_INFLOW, BC_OUTFLOW, BC_SLIP, BC_TABLE = range(4)
 GEOM_CARTESIAN, GEOM_GENERAL = 0, 1
+MONITOR_KINETIC_ENERGY, MONITOR_ENTROPY = 0, 1
 FLAG_NO_GRAPH = 1
 FLAG_FUSED = 2
 FLAG_NODE_KERNEL = 4
@@ -67,6 +68,9 @@ SYMBOLS = {
                                             C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                             C.c_int64]),
     "flou_b200_max_dt": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double)]),
+    "flou_b200_monitor": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double)]),
+    "flou_b200_zhang_shu": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_double]),
+    "flou_b200_set_stage_limiter": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double]),
     "flou_b200_synchronize": (C.c_int32, [C.c_void_p]),
     "flou_b200_status": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     "flou_b200_last_error": (C.c_char_p, []),

@@ -24,8 +24,13 @@ class _LowStorageRK2N:
         if williamson_condition:
             raise ValueError("williamson_condition=true (ArrayFuse path) is not supported; the "
                              "reference always passes williamson_condition=false")
-        if stage_limiter is not None or step_limiter is not None:
-            raise ValueError("stage/step limiters are outside the B200 hot path")
+        if step_limiter is not None:
+            raise ValueError("step limiters are outside the B200 hot path (the reference uses stage_limiter!)")
+        # ORK256(stage_limiter! = get_limiter_callback(dg, eq, :zhang_shu, minval)) as in
+        # examples/src/3D_Euler.jl:76-80; applied on the device after every stage
+        if stage_limiter is not None and not hasattr(stage_limiter, "minval"):
+            raise ValueError("stage_limiter must come from get_limiter_callback(disc, eq, 'zhang_shu', minval)")
+        self.stage_limiter = stage_limiter
 
     @property
     def nstages(self):
@@ -53,9 +58,16 @@ def _tab(solver):
             np.array(solver.c, dtype=np.float64))
 
 
+def _set_limiter(disc, solver):
+    lim = getattr(solver, "stage_limiter", None)
+    L.check(L.lib().flou_b200_set_stage_limiter(disc.handle, 1 if lim is not None else 0,
+                                                lim.minval if lim is not None else 0.0))
+
+
 def advance(disc, solver, dt, nsteps, t0=0.0):
     """Device-resident fast path: nsteps RK steps on the uploaded state (asynchronous)."""
     A, B, c = _tab(solver)
+    _set_limiter(disc, solver)
     L.check(L.lib().flou_b200_lsrk2n_advance(disc.handle, solver.nstages, _ptr(A), _ptr(B), _ptr(c),
                                              float(dt), float(t0), int(nsteps)))
 
@@ -80,11 +92,14 @@ def timeintegrate(Q0, disc, equation, solver, tfinal, *, dt, adaptive=False, ali
                   save_start=True):
     """Returns (sol, exetime) like the reference; `Q0` is overwritten when alias_u0=True.
 
-    Only fixed-step integration (`adaptive=false`) without callbacks is on the hot path."""
+    Fixed-step integration (`adaptive=false`).  `callback`: a list from `make_callback_list` of
+    monitor / CFL callbacks (flou_b200.monitors); they are evaluated on the device between steps
+    (the save callback, FlouBiz output, is not on this path)."""
     if adaptive:
         raise ValueError("adaptive=true is not supported (the reference always uses adaptive=false)")
     if callback is not None:
-        raise ValueError("callbacks are outside the B200 hot path")
+        return _timeintegrate_callbacks(Q0, disc, equation, solver, tfinal, dt=dt, alias_u0=alias_u0,
+                                        callback=callback, t0=t0, save_start=save_start)
     if equation is not disc.equation:
         raise ValueError("`equation` is not the one the discretisation was built with")
     Q = _state(Q0, disc.ndofs, disc.nv, writable=alias_u0)
@@ -95,6 +110,7 @@ def timeintegrate(Q0, disc, equation, solver, tfinal, *, dt, adaptive=False, ali
     if nsteps is None:
         nsteps = int(round((tfinal - t0) / dt))
     A, B, c = _tab(solver)
+    _set_limiter(disc, solver)
     tic = _time.perf_counter()
     try:
         L.check(L.lib().flou_b200_timeintegrate(disc.handle, _ptr(Q), solver.nstages, _ptr(A),
@@ -105,3 +121,54 @@ def timeintegrate(Q0, disc, equation, solver, tfinal, *, dt, adaptive=False, ali
         print("ERROR: Simulation crashed!")
         return None, _time.perf_counter() - tic
     return Solution(u0, Q, t0, t0 + nsteps * dt), _time.perf_counter() - tic
+
+
+class _Integrator:
+    """The fields of OrdinaryDiffEq's integrator the reference's callbacks read."""
+
+    def __init__(self, disc, equation, t, dt):
+        self.disc, self.equation, self.t, self.dt, self.iter = disc, equation, t, dt, 0
+
+
+def _timeintegrate_callbacks(Q0, disc, equation, solver, tfinal, *, dt, alias_u0, callback, t0,
+                             save_start):
+    """Step-by-step loop with device-side callbacks (FlouTime.jl:56-152): the state is uploaded
+    once and downloaded once; each callback costs one small reduction kernel."""
+    from .monitors import _Callback
+    cbs = list(callback) if isinstance(callback, (list, tuple)) else [callback]
+    for cb in cbs:
+        if not isinstance(cb, _Callback):
+            raise ValueError("only callbacks from flou_b200.monitors (monitor, CFL) run on the B200 path")
+    if equation is not disc.equation:
+        raise ValueError("`equation` is not the one the discretisation was built with")
+    Q = _state(Q0, disc.ndofs, disc.nv, writable=alias_u0)
+    u0 = Q.copy(order="F") if (save_start or not alias_u0) else None
+    if not alias_u0:
+        Q = u0.copy(order="F")
+    A, B, c = _tab(solver)
+    _set_limiter(disc, solver)
+    tic = _time.perf_counter()
+    disc.upload(Q)
+    integ = _Integrator(disc, equation, float(t0), float(dt))
+    for cb in cbs:
+        if cb.initialize:
+            cb.affect(integ)
+    try:
+        while integ.t < tfinal - 1e-14 * max(1.0, abs(tfinal)):
+            h = min(integ.dt, tfinal - integ.t)       # the last step lands on tfinal (tstops)
+            L.check(L.lib().flou_b200_lsrk2n_advance(disc.handle, solver.nstages, _ptr(A), _ptr(B),
+                                                     _ptr(c), h, integ.t, 1))
+            integ.t += h
+            integ.iter += 1
+            for cb in cbs:
+                if cb.selected(integ.iter):
+                    cb.affect(integ)
+        disc.download(Q)
+        if disc.status() & 1:
+            raise L.DomainError("non-positive density/pressure or NaN (Simulation crashed!)")
+    except L.DomainError:
+        print("ERROR: Simulation crashed!")
+        return None, _time.perf_counter() - tic
+    sol = Solution(u0, Q, t0, integ.t)
+    sol.iterations = integ.iter
+    return sol, _time.perf_counter() - tic

@@ -190,8 +190,26 @@ int32_t flou_b200_timeintegrate(flou_b200_handle *h, double *Q, int32_t nstages,
  * an uploaded one; an ncclAllReduce(min) joins the ranks of a partitioned run.  Row f1. */
 int32_t flou_b200_max_dt(flou_b200_handle *h, const double *Q, double cfl, double *dt);
 
+/* ---- monitors and limiters ------------------------------------------ */
+/* get_monitor(disc, eq, :kinetic_energy | :entropy) (src/FlouSpatial/Equations/Euler.jl:541-593):
+ * sum over the elements of integrate(f(Q_i), geom) with f = kinetic_energy
+ * (FlouCommon/Euler.jl:162-175) or math_entropy (:213-217), as a device reduction over the
+ * device-resident state (Q == NULL) or an uploaded one; ncclAllReduce(sum) across ranks. */
+#define FLOU_B200_MONITOR_KINETIC_ENERGY 0
+#define FLOU_B200_MONITOR_ENTROPY        1
+int32_t flou_b200_monitor(flou_b200_handle *h, int32_t kind, const double *Q, double *value);
+/* get_limiter(disc, eq, :zhang_shu, minval) (Equations/Euler.jl:597-660): positivity limiter of
+ * Zhang & Shu, element by element.  Q == NULL: the device-resident state, in place; otherwise Q
+ * (host, owned rows) is uploaded, limited and written back. */
+int32_t flou_b200_zhang_shu(flou_b200_handle *h, double *Q, double minval);
+/* ORK256(stage_limiter! = get_limiter_callback(dg, eq, :zhang_shu, minval)) as in
+ * examples/src/3D_Euler.jl:76-80: flou_b200_lsrk2n_advance / _timeintegrate apply the limiter to
+ * the state after every RK stage, on the device. */
+int32_t flou_b200_set_stage_limiter(flou_b200_handle *h, int32_t enable, double minval);
+
 int32_t flou_b200_synchronize(flou_b200_handle *h);
-/* sticky device flags: bit 0 = non-positive density/pressure or NaN seen */
+/* sticky device flags: bit 0 = non-positive density/pressure or NaN seen since the last
+ * flou_b200_upload_state / flou_b200_timeintegrate (both clear them) */
 int32_t flou_b200_status(flou_b200_handle *h, int32_t *flags);
 const char *flou_b200_last_error(void);
 

@@ -217,6 +217,78 @@ class Problem:
         vol = np.ascontiguousarray((self.jac * np.tile(self.weights, self.ne)).reshape(self.ne, -1).sum(axis=1))
         return float(lib().oracle_max_dt(C.byref(self.c), _ptr(Q), _ptr(vol), float(cfl)))
 
+    # ---- monitors and limiter; plain numpy, element by element in the
+    # reference's order.  No reference test evaluates them: parity unpinned, checked by properties
+    # (tests/test_oracle_properties.py).
+    def _jw(self):
+        return (self.jac * np.tile(self.weights, self.ne)).reshape(self.ne, self.npts)
+
+    def _pressure(self, Q):
+        """pressure(Q, eq) (FlouCommon/Euler.jl:142-155)."""
+        g, nd = self.c.gamma, self.nd
+        m2 = np.sum(Q[..., 1:1 + nd] ** 2, axis=-1)
+        return (g - 1) * (Q[..., nd + 1] - m2 / (2 * Q[..., 0]))
+
+    def monitor(self, Q, name):
+        """kinetic_energy_monitor / entropy_monitor (src/FlouSpatial/Equations/Euler.jl:559-593):
+        s += integrate(f.(Qe.dofs), geom_e) over the elements, integrate = Jw' * f
+        (PhysicalRegions.jl:366-368)."""
+        Q = np.asarray(Q, dtype=np.float64)
+        g, nd = self.c.gamma, self.nd
+        Jw = self._jw()
+        Qe = Q.reshape(self.ne, self.npts, self.nv)
+        s = 0.0
+        for e in range(self.ne):
+            q = Qe[e]
+            if name in ("kinetic_energy", "energy"):
+                f = np.sum(q[:, 1:1 + nd] ** 2, axis=1) / (2 * q[:, 0])         # Euler.jl:162-175
+            elif name == "entropy":
+                ent = np.log(self._pressure(q)) - g * np.log(q[:, 0])           # entropy :202-206
+                f = -q[:, 0] * ent / (g - 1)                                     # math_entropy :213-217
+            else:
+                raise ValueError(f"Unknown monitor '{name}'.")
+            s += float(Jw[e] @ f)
+        return s
+
+    def zhang_shu(self, Q, minval):
+        """zhang_shu_limiter (src/FlouSpatial/Equations/Euler.jl:616-660), returns the limited
+        copy.  Element mean = integrate(Qe.dofs, geom)/geom.volume, volume = sum(Jw)
+        (PhysicalRegions.jl:402-405)."""
+        Q = np.array(Q, dtype=np.float64, order="F", copy=True)
+        Jw = self._jw()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for e in range(self.ne):
+                rows = slice(e * self.npts, (e + 1) * self.npts)
+                q = Q[rows]                              # view: (npts, nv)
+                vol = float(np.sum(Jw[e]))
+                qbar = (Jw[e] @ q) / vol
+                m = min(minval, qbar[0])
+                rmin = float(np.min(q[:, 0]))
+                theta = abs(np.float64(qbar[0] - m) / np.float64(qbar[0] - rmin))
+                if theta <= 1.0:
+                    q[:, 0] = theta * (q[:, 0] - qbar[0]) + qbar[0]
+                p = self._pressure(q)
+                pbar = float(Jw[e] @ p) / vol
+                m = min(minval, pbar)
+                pmin = float(np.min(p))
+                theta = abs(np.float64(pbar - m) / np.float64(pbar - pmin))
+                if theta <= 1.0:
+                    q[:, :] = theta * (q - qbar) + qbar
+        return Q
+
+    def lsrk2n_limited(self, Q, tableau, dt, nsteps, minval):
+        """The 2N recurrence with `stage_limiter!` = Zhang-Shu after every stage
+        (OrdinaryDiffEq LowStorageRK2N; usage examples/src/3D_Euler.jl:76-80)."""
+        u = np.array(Q, dtype=np.float64, order="F", copy=True)
+        tmp = np.zeros_like(u, order="F")
+        A, B = tableau["A"], tableau["B"]
+        for _ in range(nsteps):
+            for s in range(len(B)):
+                k = self.rhs(u)
+                tmp = dt * k if s == 0 else A[s] * tmp + dt * k
+                u = self.zhang_shu(u + B[s] * tmp, minval)
+        return u
+
     def lsrk2n(self, Q, tableau, dt, nsteps, t0=0.0):
         u = np.array(Q, dtype=np.float64, order="F", copy=True)
         k = np.zeros_like(u, order="F")

@@ -160,3 +160,16 @@ class Case:
 def relerr(a, b):
     """inf-norm error relative to max|b|."""
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def troubled_state(ndof, nd, gamma=1.4, seed=SEED, frac=0.05):
+    """A random admissible state in which a few nodes are pushed below the Zhang-Shu floor:
+    tiny (some negative) densities, and energies that give tiny or negative pressures."""
+    rng = np.random.default_rng(seed + 1)
+    Q = random_state(ndof, nd, "euler", gamma=gamma, seed=seed, amp=0.3)
+    bad_r = rng.random(ndof) < frac
+    Q[bad_r, 0] = rng.uniform(-2e-3, 5e-3, int(bad_r.sum()))
+    bad_p = rng.random(ndof) < frac
+    kin = 0.5 * np.sum(Q[:, 1:1 + nd] ** 2, axis=1) / Q[:, 0]
+    Q[bad_p, nd + 1] = kin[bad_p] + rng.uniform(-1e-3, 5e-3, int(bad_p.sum())) / (gamma - 1)
+    return np.asfortranarray(Q)

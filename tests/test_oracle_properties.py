@@ -193,3 +193,54 @@ def test_hybrid_conservation_and_free_stream(nd, n, npn):
     assert np.all(total <= 1e-12 * np.abs(w) @ np.abs(dQ))
     Qc = np.tile(Q[:1], (pb.ndof, 1))
     assert np.max(np.abs(pb.rhs(np.asfortranarray(Qc)))) <= 1e-11
+
+
+# ------------------------------------------------------------------ monitors / limiter (row f3)
+@pytest.mark.parametrize("nd,n,npn,general", [(1, (6,), 4, False), (2, (4, 3), 5, False),
+                                               (3, (2, 3, 2), 4, False), (2, (3, 3), 4, True)])
+def test_monitors_of_a_uniform_state(nd, n, npn, general):
+    """integrate() of a constant is the constant times the domain volume (Euler.jl:559-593)."""
+    from common import Case, box
+    pb = Case(nd, n, npn, perturb_amp=0.08 if general else 0.0).oracle()
+    g = 1.4
+    prim = [1.3] + [0.4, -0.2, 0.1][:nd] + [0.9]
+    Q0 = O.vars_prim2cons(prim, g)
+    Q = np.asfortranarray(np.tile(Q0, (pb.ndof, 1)))
+    start, finish = box(nd)
+    vol = float(np.prod(np.array(finish) - np.array(start)))
+    if general:       # perturbed vertices move the outer boundary too
+        vol = float(np.sum(pb.jac * np.tile(pb.weights, pb.ne)))
+    ke = 0.5 * prim[0] * sum(v * v for v in prim[1:1 + nd])
+    assert abs(pb.monitor(Q, "kinetic_energy") / (vol * ke) - 1) <= 1e-12
+    s = np.log(prim[-1]) - g * np.log(prim[0])
+    assert abs(pb.monitor(Q, "entropy") / (vol * (-prim[0] * s / (g - 1))) - 1) <= 1e-12
+    with pytest.raises(ValueError):
+        pb.monitor(Q, "enstrophy")
+
+
+@pytest.mark.parametrize("nd,n,npn,general", [(1, (8,), 4, False), (2, (4, 4), 5, False),
+                                               (3, (3, 2, 2), 4, False), (3, (2, 2, 2), 3, True)])
+def test_zhang_shu_properties(nd, n, npn, general):
+    """Zhang-Shu limiter (Euler.jl:616-660): identity on states above the floor, conservative
+    (element means unchanged), and after limiting rho >= floor and p >= floor in every element
+    whose means are above the floor."""
+    from common import Case, random_state, troubled_state
+    pb = Case(nd, n, npn, perturb_amp=0.08 if general else 0.0).oracle()
+    minval = 1e-2
+    good = random_state(pb.ndof, nd, "euler", amp=0.3)
+    assert np.array_equal(pb.zhang_shu(good, minval), good)
+    Q = troubled_state(pb.ndof, nd)
+    L = pb.zhang_shu(Q, minval)
+    Jw = (pb.jac * np.tile(pb.weights, pb.ne)).reshape(pb.ne, pb.npts)
+    mean = lambda X: np.einsum("ei,eiv->ev", Jw, X.reshape(pb.ne, pb.npts, -1)) / Jw.sum(axis=1)[:, None]
+    assert np.max(np.abs(mean(L) - mean(Q))) <= 1e-13 * np.max(np.abs(mean(Q)))
+    assert not np.array_equal(L, Q)
+    rho = L[:, 0].reshape(pb.ne, pb.npts)
+    ok = mean(Q)[:, 0] > minval
+    assert np.all(rho[ok].min(axis=1) >= minval * (1 - 1e-9))
+    p = pb._pressure(L).reshape(pb.ne, pb.npts)
+    pm = np.einsum("ei,ei->e", Jw, p) / Jw.sum(axis=1)
+    okp = ok & (pm > minval)
+    assert np.all(p[okp].min(axis=1) >= minval * (1 - 1e-6))
+    # a second application leaves an already limited state essentially alone
+    assert np.max(np.abs(pb.zhang_shu(L, minval) - L)) <= 1e-9 * np.max(np.abs(L))
