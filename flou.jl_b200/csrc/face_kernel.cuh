@@ -39,8 +39,20 @@ __device__ __forceinline__ void load_trace(const KParams &P, int kind, int elem_
     }
 }
 
+// The kernel waits on two dependent DRAM round trips (face record, then traces): occupancy pays
+// more than the spills it costs.  cfg4s, 3-D Euler p=4: 5 CTAs/SM (95 registers) 0.658 ms,
+// 6 (80) 0.610, 7 (72) 0.583, 8 (64) 0.591.
+
+// FLOU_FACE_PREFETCH: faces ahead whose record is pulled into L2 (cfg4s: 0.585 -> 0.556 ms for
+// 2048..8192, nothing at 32768).  Prefetching the traces of a face further ahead as well
+// (cp.async.bulk.prefetch.L2 per run) was slower, 0.67 ms: with the record prefetch the kernel moves
+// 3.3 GB at ~5.9 TB/s, i.e. it is bound by DRAM traffic, of which the 40-byte runs of y-face node
+// layers waste a third.
+#ifndef FLOU_FACE_PREFETCH
+#define FLOU_FACE_PREFETCH 4096
+#endif
 #ifndef FLOU_FACE_MIN_BLOCKS
-#define FLOU_FACE_MIN_BLOCKS 5
+#define FLOU_FACE_MIN_BLOCKS 7
 #endif
 
 // Rotation to / from the frame of a Cartesian face whose master-side local face is the
@@ -170,6 +182,12 @@ face_flux_kernel(const __grid_constant__ KParams P)
     if (t >= (int64_t)P.face_count * NFP) return;
     const int fl = (int)(t / NFP), i = (int)(t - (int64_t)fl * NFP);
     const int f = P.face_first + fl;
+#if FLOU_FACE_PREFETCH > 0
+    // the record of a face a later CTA will work on: pulled into L2 now, so that the first of the
+    // two dependent round trips of that thread (record, then traces) is an L2 hit
+    if (i == 0 && fl + FLOU_FACE_PREFETCH < P.face_count)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.faces + f + FLOU_FACE_PREFETCH));
+#endif
     const FaceRec rec = P.faces[f];
     // faces keep Flou's global order, in which the master's local face changes rarely: the switch
     // is warp-uniform almost everywhere

@@ -64,8 +64,38 @@ __device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gmem_sr
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
+// Wait for the phase with the given parity.  A failed try_wait comes back within a few cycles on
+// sm_100a, so a plain retry loop spins at ~4 cycles per iteration and takes issue slots from the
+// compute warps of the same scheduler (ncu: 157 retries per wait of the line threads on freeP).
+// FLOU_MBAR_WAIT selects the back-off: 0 = plain retry, 1 = try_wait with a suspend-time hint
+// (measured: no effect), 2 = nanosleep between tries (default; element kernel -1.3 %).
+#ifndef FLOU_MBAR_WAIT
+#define FLOU_MBAR_WAIT 2
+#endif
+#ifndef FLOU_MBAR_NS
+#define FLOU_MBAR_NS 40
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
+#if FLOU_MBAR_WAIT == 1
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"((unsigned)FLOU_MBAR_NS) : "memory");
+#elif FLOU_MBAR_WAIT == 2
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "WAIT_%=:\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"((unsigned)FLOU_MBAR_NS) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -73,6 +103,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 
 struct ETPick { int e, t; };
