@@ -28,6 +28,8 @@ def main():
         (Case(3, (4, 4, 2 * world), 4, eq="euler", op="split", nf="mat", avg="cha"), 6),
         (Case(2, (5, 3 * world), 5, eq="euler", op="split", nf="mat", avg="cha"), 6),
         (Case(2, (6, 2 * world + 1), 4, nodes="GL", eq="adv", op="strong", nf="lxf", avg="std"), 6),
+        # row f2: HybridDivOperator (line kernel only) across a partition
+        (Case(2, (4, 3 * world), 4, eq="euler", op="hybrid", nf="mat", avg="cha", blend=1.0), 4),
         (Case(3, (3, 3, world), 3, eq="euler", op="split", nf="mat", avg="cha", periodic=[("5", "6")],
               bcs={"1": ("inflow", [1.0, 0.4, 0.0, 0.1, 2.7]), "2": ("outflow", None),
                    "3": ("slip", None), "4": ("slip", None)}), 4),
@@ -46,11 +48,17 @@ def main():
         dQ = disc.new_state()
         F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
         dtn = F.get_max_dt(Q, disc, eq, 0.4)       # ncclAllReduce(min) over the ranks (row f1)
+        # row f3: monitors are ncclAllReduce(sum) over the ranks; the limiter is element-local
+        mon = lim = None
+        if case.eq == "euler":
+            mon = tuple(F.get_monitor(disc, eq, name)(Q, disc, eq) for name in ("kinetic_energy", "entropy"))
+            lim = Q.copy(order="F")
+            F.get_limiter(disc, eq, "zhang_shu", 0.95)(lim, disc, eq)
         u = Q.copy(order="F")
         sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), nsteps * 1e-3, dt=1e-3)
         assert sol is not None
         parts = [None] * world
-        dist.all_gather_object(parts, (dQ, sol.u[-1], dtn))
+        dist.all_gather_object(parts, (dQ, sol.u[-1], dtn, mon, lim))
         if rank == 0:
             dQ1 = full.new_state()
             F.rhs(dQ1, Qg, F.EquationConfig(full, eq1), 0.0)
@@ -61,6 +69,15 @@ def main():
             dt1 = F.get_max_dt(Qg, full, eq1, 0.4)
             same = (np.array_equal(dQn, dQ1) and np.array_equal(un, u1)
                     and all(p[2] == dt1 for p in parts))
+            if case.eq == "euler":
+                # the partial sums are added in a different order: 1e-13, identical on all ranks
+                for j, name in enumerate(("kinetic_energy", "entropy")):
+                    m1 = F.get_monitor(full, eq1, name)(Qg, full, eq1)
+                    same = same and all(p[3] == parts[0][3] for p in parts) and abs(parts[0][3][j] / m1 - 1) <= 1e-13
+                l1 = Qg.copy(order="F")
+                F.get_limiter(full, eq1, "zhang_shu", 0.95)(l1, full, eq1)
+                same = same and np.array_equal(np.concatenate([p[4] for p in parts], axis=0), l1) \
+                    and not np.array_equal(l1, Qg)
             print(f"[multigpu] {case!r}: ranks={world} bitwise_equal={same} "
                   f"max|d rhs|={np.max(np.abs(dQn - dQ1)):.3e} max|d u|={np.max(np.abs(un - u1)):.3e}",
                   flush=True)
