@@ -1125,7 +1125,7 @@ int32_t flou_b200_kernel_info(flou_b200_handle *h, int32_t *grid_ctas, int32_t *
 {
     if (!h) return fail(FLOU_B200_EINVAL, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (grid_ctas) *grid_ctas = h->stage->resident();
+    if (grid_ctas) *grid_ctas = (h->line_kernel && h->stage->line_resident) ? h->stage->line_resident() : h->stage->resident();
     if (threads) *threads = h->line_kernel ? h->stage->line_t : h->stage->threads;
     if (smem_bytes) *smem_bytes = (int32_t)(h->line_kernel ? h->stage->line_smem : h->stage->smem);
     if (elems_per_cta_iter) *elems_per_cta_iter = h->line_kernel ? h->stage->line_e : h->stage->epb;

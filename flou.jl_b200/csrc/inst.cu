@@ -190,11 +190,11 @@ static constexpr StageLauncher make()
 #ifdef FLOU_WS
     return StageLauncher{&ws_launch<C>, &do_launch_elements<C>, &do_launch_lines<C>, &do_launch_faces<C>, &ws_prepare<C>,
                          &ws_resident_ctas<C>, C::EPB, WSCfg<C>::THREADS, WSCfg<C>::SMEM_BYTES,
-                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES};
+                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES, &line_resident_ctas<C>};
 #else
     return StageLauncher{&do_launch<C>, &do_launch_elements<C>, &do_launch_lines<C>, &do_launch_faces<C>, &do_prepare<C>,
                          &resident_ctas<C>, C::EPB, C::THREADS, C::SMEM_BYTES,
-                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES};
+                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES, &line_resident_ctas<C>};
 #endif
 }
 
@@ -207,7 +207,7 @@ static constexpr StageLauncher make_lines()
 {
     return StageLauncher{nullptr, nullptr, &do_launch_lines<C>, &do_launch_faces<C>, &lines_only_prepare<C>,
                          &line_resident_ctas<C>, LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES,
-                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES};
+                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES, &line_resident_ctas<C>};
 }
 
 #define ND FLOU_ND

@@ -16,6 +16,7 @@ struct StageLauncher {
     size_t smem;
     int line_e, line_t;         // line kernel: elements and threads per CTA
     size_t line_smem;
+    int (*line_resident)();     // persistent grid of the line kernel
 };
 
 struct EmitLauncher {
