@@ -668,6 +668,21 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
             if (std::fabs(Dvol[j + np * j]) > 1e-12 * dmax) P.diag_mask |= 1 << j;
     }
     h->colloc = colloc;
+    // split form on nodes without boundaries (Gauss): entropy-projected surface term
+    // (_splitdiv_nb_surface_contribution!, OpDivergence.jl:300-437), line kernels only
+    const bool split_nb = d->divop == FLOU_B200_OP_SPLIT && !colloc;
+    if (split_nb) {
+        const char *why = nullptr;
+        if (d->equation != FLOU_B200_EQ_EULER) why = "SplitDivOperator on Gauss nodes needs entropy variables (Euler equations)";
+        else if (!cart) why = "SplitDivOperator on Gauss nodes is built for Cartesian sub-grids only";
+        else if (d->flags & (FLOU_B200_FLAG_FUSED | FLOU_B200_FLAG_NODE_KERNEL))
+            why = "SplitDivOperator on Gauss nodes exists in the line-per-thread kernel only";
+        if (why) { flou_b200_destroy(h); return fail(FLOU_B200_EUNSUPPORTED, why); }
+        // the instances built for such nodes (dispatch indices 4 / 5, inst.cu)
+        h->stage = get_stage_launcher(nd, np, d->equation,
+                                      d->tpflux == FLOU_B200_FLUX_CHANDRASEKHAR ? 5 : 4, cart);
+        if (!h->stage) { flou_b200_destroy(h); return fail(FLOU_B200_EUNSUPPORTED, "no kernel compiled for this (nd, np)"); }
+    }
     if (hybrid && !colloc) {
         // the reference moves everything to the surface term on Gauss nodes
         // (_hybrid_nb_surface_contribution!, OpDivergence.jl:647-779): not on this path
@@ -722,7 +737,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         const int64_t groups = (h->ne_local + h->stage->line_e - 1) / std::max(1, h->stage->line_e);
-        if (h->nranks == 1 && groups < sms && !hybrid &&
+        if (h->nranks == 1 && groups < sms && !hybrid && !split_nb &&
             !(d->flags & (FLOU_B200_FLAG_NODE_KERNEL | FLOU_B200_FLAG_LINE_KERNEL)))
             h->split_faces = false;
     }

@@ -82,11 +82,11 @@ static cudaError_t do_launch_elements(const KParams &P, cudaStream_t s)
 // ---- line-per-thread element kernel (default element kernel of the two-kernel stage)
 #ifndef FLOU_LINE_NOWS    // default: warp-specialised variant, TL line threads + one update warp
 template <class C>
-using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, true>;
+using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, true, C::NB>;
 #define FLOU_LINE_KERNEL line_kernel_ws
 #else
 template <class C>
-using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, false>;
+using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, false, C::NB>;
 #define FLOU_LINE_KERNEL line_kernel
 #endif
 
@@ -210,14 +210,22 @@ static constexpr StageLauncher make_lines()
                          LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES, &line_resident_ctas<C>};
 }
 
+// configuration tag of the line-only instances for nodes without boundaries (split form, Gauss)
+template <int ND_, int NP_, int EQ_, int VOL_, bool CART_>
+struct NBCfg : KCfg<ND_, NP_, EQ_, VOL_, CART_> {
+    static constexpr bool NB = true;
+};
+
 #define ND FLOU_ND
 #define NP FLOU_NP
 
-// [eq][vol][cart]
-static const StageLauncher table[2][4][2] = {
+// [eq][vol][cart]; vol 4 / 5 = split form (StdAverage / Chandrasekhar) on nodes without boundaries
+static const StageLauncher table[2][6][2] = {
     {   // linear advection: strong, split (StdAverage two-point flux); no Chandrasekhar
         {make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, true>>()},
+        {StageLauncher{}, StageLauncher{}},
+        {StageLauncher{}, StageLauncher{}},
         {StageLauncher{}, StageLauncher{}},
         {StageLauncher{}, StageLauncher{}},
     },
@@ -227,6 +235,9 @@ static const StageLauncher table[2][4][2] = {
         {make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
         // HybridDivOperator: Cartesian sub-grids only (general sub-grid geometry: row f2b, not built)
         {StageLauncher{}, make_lines<KCfg<ND, NP, EQ_EULER, VOL_HYBRID, true>>()},
+        // split form on Gauss nodes: Cartesian sub-grids only
+        {StageLauncher{}, make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, true>>()},
+        {StageLauncher{}, make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
     },
 };
 

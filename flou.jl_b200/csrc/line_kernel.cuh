@@ -131,10 +131,13 @@ constexpr ETPick pick_et(int nlines, int per_elem_doubles, int max_kb)
 
 // WS = warp-specialised variant (line_kernel_ws.cuh): TL line threads plus one update warp, three
 // state buffers and two node-data buffers.
-template <int ND_, int NP_, int EQ_, int VOL_, bool CART_, bool WS_ = false>
+// NB = nodes without boundaries (Gauss): the split form takes its surface term from entropy-
+// projected end states (splitdiv_nb_line); a separate instance, so that the GLL kernels carry none
+// of that code (inlined into the exact path it cost the GLL instance 35 %: local-memory frame).
+template <int ND_, int NP_, int EQ_, int VOL_, bool CART_, bool WS_ = false, bool NB_ = false>
 struct LCfg {
     static constexpr int ND = ND_, NP = NP_, EQ = EQ_, VOL = VOL_;
-    static constexpr bool CART = CART_, WS = WS_;
+    static constexpr bool CART = CART_, WS = WS_, NB = NB_;
     static constexpr int NV = (EQ == EQ_ADV) ? 1 : ND + 2;
     static constexpr int NPTS = ipow_c(NP, ND);
     static constexpr int NFP = ipow_c(NP, ND - 1);
@@ -411,6 +414,101 @@ __device__ __forceinline__ void hybrid_line(const KParams &P, const double (&Q)[
     }
 }
 
+// Surface term of the split form on nodes WITHOUT boundaries, one line
+// (_flux_splitdiv_nb_tensorproduct! + _surf_splitdiv_nb_tensorproduct!, OpDivergence.jl:389-437):
+//   W_i = vars_cons2entropy(Q_i);  Q(l) = vars_entropy2cons(l' W),  Q(r) = vars_entropy2cons(r' W)
+//   Fl_i = F#(Q_i, Q(l)),  Fr_i = F#(Q_i, Q(r))
+//   Fl_i -= l' Fl + Fn_left,   Fr_i -= r' Fr - Fn_right,   dQ_i += dg_l[i] Fl_i - dg_r[i] Fr_i
+// in the folded Cartesian form of the caller: unit metric along the (permuted) axis 0, face fluxes
+// pre-divided by the metric factor (wl, wr carry sign and 1/metric), components in the order pc.
+template <class C>
+__device__ __forceinline__ void splitdiv_nb_line(const KParams &P, const double *sA, const double *sF,
+                                              int base, int stride, const int (&pc)[C::ND], int task,
+                                              double wl, double wr, double (&acc)[C::NP][C::NV])
+{
+    constexpr int ND = C::ND, NP = C::NP, NV = C::NV, N = C::N, LT = C::LT, VOL = C::VOL;
+    const double g = P.fp.gamma;
+    double rho[NP], vel[NP][ND], pr[NP], Wl[NV], Wr[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) { Wl[v] = 0.0; Wr[v] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        const int node = base + j * stride;
+        if (VOL == VOL_SPLIT_CHA) {          // node data (rho, v/2, beta)
+            rho[j] = sA[node];
+#pragma unroll
+            for (int c = 0; c < ND; c++) vel[j][c] = 2.0 * sA[(1 + pc[c]) * N + node];
+            pr[j] = rho[j] / (2.0 * sA[(ND + 1) * N + node]);
+        } else {                             // node data (Q, v, p)
+            rho[j] = sA[node];
+#pragma unroll
+            for (int c = 0; c < ND; c++) vel[j][c] = sA[(NV + pc[c]) * N + node];
+            pr[j] = sA[(NV + ND) * N + node];
+        }
+        double q = 0.0, W[NV];
+#pragma unroll
+        for (int c = 0; c < ND; c++) q += vel[j][c] * vel[j][c];
+        const double s = log(pr[j]) - g * log(rho[j]);                  // FlouCommon/Euler.jl:202-206
+        W[0] = (g - s) / (g - 1.0) - rho[j] * q / (2.0 * pr[j]);        // :273-307
+#pragma unroll
+        for (int c = 0; c < ND; c++) W[1 + c] = rho[j] * vel[j][c] / pr[j];
+        W[ND + 1] = -rho[j] / pr[j];
+#pragma unroll
+        for (int v = 0; v < NV; v++) { Wl[v] = fma(P.lm[j], W[v], Wl[v]); Wr[v] = fma(P.lp[j], W[v], Wr[v]); }
+    }
+    // vars_entropy2prim (FlouCommon/Euler.jl:309-334) of both projections: e = 0 left, 1 right
+    double re[2], ve[2][ND], pe[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const double *W = e ? Wr : Wl;
+        double q = 0.0;
+#pragma unroll
+        for (int c = 0; c < ND; c++) { ve[e][c] = -W[1 + c] / W[ND + 1]; q += ve[e][c] * ve[e][c]; }
+        const double s = g - (g - 1.0) * (W[0] - W[ND + 1] * q / 2.0);
+        pe[e] = pow(pow(-W[ND + 1], g) * exp(s), 1.0 / (1.0 - g));
+        re[e] = -pe[e] * W[ND + 1];
+    }
+    double Fl[NP][NV], Fr[NP][NV], lFl[NV], rFr[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) { lFl[v] = 0.0; rFr[v] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            double *F = e ? Fr[j] : Fl[j];
+            if (VOL == VOL_SPLIT_CHA) {
+                double h1[ND], h2[ND];
+                int dummy = 0;
+#pragma unroll
+                for (int c = 0; c < ND; c++) { h1[c] = 0.5 * vel[j][c]; h2[c] = 0.5 * ve[e][c]; }
+                tp_cha_axis<ND, false>(rho[j], h1, rho[j] / (2.0 * pr[j]), re[e], h2, re[e] / (2.0 * pe[e]),
+                                       P.fp.inv_gm1, F, dummy);
+            } else {
+                double Q1[NV], Q2[NV], n[ND], q1 = 0.0, q2 = 0.0;
+                Q1[0] = rho[j]; Q2[0] = re[e];
+#pragma unroll
+                for (int c = 0; c < ND; c++) {
+                    Q1[1 + c] = rho[j] * vel[j][c]; Q2[1 + c] = re[e] * ve[e][c];
+                    q1 += vel[j][c] * vel[j][c]; q2 += ve[e][c] * ve[e][c];
+                    n[c] = (c == 0) ? 1.0 : 0.0;
+                }
+                Q1[ND + 1] = pr[j] * P.fp.inv_gm1 + 0.5 * rho[j] * q1;
+                Q2[ND + 1] = pe[e] * P.fp.inv_gm1 + 0.5 * re[e] * q2;
+                tp_stdavg<ND>(Q1, vel[j], pr[j], Q2, ve[e], pe[e], n, F);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) { lFl[v] = fma(P.lm[j], Fl[j][v], lFl[v]); rFr[v] = fma(P.lp[j], Fr[j][v], rFr[v]); }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const double a0 = lFl[v] + wl * sF[v * LT + task], b0 = rFr[v] - wr * sF[(NV + v) * LT + task];
+#pragma unroll
+        for (int j = 0; j < NP; j++)
+            acc[j][v] += P.dgl[j] * (Fl[j][v] - a0) - P.dgr[j] * (Fr[j][v] - b0);
+    }
+}
+
 // One line task: volume term of the line's NP nodes in direction d plus the lift of the two face
 // fluxes at its ends, written as the partial sums of direction d.  FAST (Chandrasekhar only):
 // branch-free pair fluxes; returns true when the line has to be redone with FAST = false.
@@ -555,6 +653,13 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
                     acc[0][v] = fma(-w0, sF[v * LT + task], acc[0][v]);
                     acc[NP - 1][v] = fma(-w1, sF[(NV + v) * LT + task], acc[NP - 1][v]);
                 }
+            } else if (SPLIT && EQ == EQ_EULER) {
+                // split form on nodes without boundaries (Gauss): the surface term couples every
+                // node of the line with the entropy-projected end states
+                // (_splitdiv_nb_surface_contribution!, OpDivergence.jl:300-437).  Cartesian
+                // sub-grids only, NB instances only (the host selects them for such nodes); these
+                // never take the fast Chandrasekhar path, which has no surface code
+                if constexpr (C::NB && CART && !FAST) splitdiv_nb_line<C>(P, sA, sF, base, stride, pc, task, wl, wr, acc);
             } else {
 #pragma unroll
                 for (int j = 0; j < NP; j++) {
@@ -965,7 +1070,7 @@ line_kernel(const __grid_constant__ KParams P)
 
         // ---------------- phase 2: one tensor-product line per thread
         for (int task = tid; task < nl; task += T) {
-            if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA) {
+            if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA && !C::NB) {
                 if (line_task<C, true>(P, sA, sP, sF, task, dof0)) line_task_exact<C>(P, sA, sP, sF, task, dof0);
             } else {
                 line_task<C, false>(P, sA, sP, sF, task, dof0);

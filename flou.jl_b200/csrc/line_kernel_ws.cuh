@@ -177,7 +177,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
         // ---------------- phase 2: one tensor-product line per thread
         const unsigned fb = i > 0 ? freeP : 0u, fpar = (unsigned)((i - 1) & 1);
         for (int task = tid; task < nl; task += TL) {
-            if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA) {
+            if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA && !C::NB) {
                 if (line_task<C, true>(P, A, sP, sF, task, dof0, fb, fpar)) line_task_exact<C>(P, A, sP, sF, task, dof0, fb, fpar);
             } else {
                 line_task<C, false>(P, A, sP, sF, task, dof0, fb, fpar);

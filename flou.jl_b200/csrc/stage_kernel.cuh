@@ -320,6 +320,7 @@ template <int ND_, int NP_, int EQ_, int VOL_, bool CART_>
 struct KCfg {
     static constexpr int ND = ND_, NP = NP_, EQ = EQ_, VOL = VOL_;
     static constexpr bool CART = CART_;
+    static constexpr bool NB = false;                  // line kernels: see LCfg
     static constexpr int NV = (EQ == EQ_ADV) ? 1 : ND + 2;
     static constexpr int NPTS = ipow_c(NP, ND);
     static constexpr int NFP = ipow_c(NP, ND - 1);

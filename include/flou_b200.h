@@ -48,6 +48,8 @@ extern "C" {
 
 /* divergence operators: src/FlouSpatial/Equations/OpDivergence.jl:105 (Strong), :184 (Split) */
 #define FLOU_B200_OP_STRONG 0
+/* SplitDivOperator: on nodes with boundaries (GLL) any geometry; on Gauss nodes the entropy-
+ * projected surface term (OpDivergence.jl:300-437) for the Euler equations on Cartesian meshes */
 #define FLOU_B200_OP_SPLIT  1
 /* HybridDivOperator(tpflux, numflux, blend) (OpDivergence.jl:452-477, volume term :557-612):
  * telescopic split form blended with sub-cell finite-volume fluxes (fvflux = numflux, as both

@@ -64,6 +64,7 @@ class _Problem(C.Structure):
         ("bc_faces", C.c_void_p), ("bc_state", C.c_void_p), ("bc_table", C.c_void_p),
         ("Qf", C.c_void_p * 2), ("Fn", C.c_void_p * 2),
         ("blend", C.c_double), ("w1d", C.c_void_p), ("sub_jac", C.c_double * 3),
+        ("hasboundaries", C.c_int32), ("proj_traces", C.c_int32),
     ]
 
 
@@ -190,8 +191,13 @@ class Problem:
         # HybridDivOperator (oracle only): 1-D weights, Cartesian sub-grid face Jacobians
         k["w1d"] = np.ascontiguousarray(self.ops["w"])
         p.w1d, p.blend = _ptr(k["w1d"]), float(blend)
-        if op == OP_HYBRID:
-            if not (cartesian and self.ops["hasboundaries"]):
+        p.hasboundaries = 1 if self.ops["hasboundaries"] else 0
+        split_nb = op == OP_SPLIT and not self.ops["hasboundaries"]
+        if split_nb and not (cartesian and equation == EQ_EULER):
+            raise ValueError("the oracle's split form on Gauss nodes (entropy-projected surface term) "
+                             "covers the Euler equations on Cartesian meshes")
+        if op == OP_HYBRID or split_nb:
+            if op == OP_HYBRID and not (cartesian and self.ops["hasboundaries"]):
                 raise ValueError("the oracle's HybridDivOperator covers GLL nodes on Cartesian meshes")
             dx = mesh.dx
             sub = [1.0] if nd == 1 else [dx[1] / 2, dx[0] / 2] if nd == 2 else \

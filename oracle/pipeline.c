@@ -11,6 +11,8 @@
  *   _volumeflux!             src/FlouSpatial/Equations/OpDivergence.jl:28-37
  *   StrongDivOperator        OpDivergence.jl:105-173
  *   SplitDivOperator         OpDivergence.jl:184-299
+ *   SplitDivOperator, nodes  OpDivergence.jl:284-437 (_splitdiv_nb_surface_contribution!: Gauss
+ *     without boundaries     nodes, entropy-projected end states; Cartesian sub-grid frames)
  *   HybridDivOperator        OpDivergence.jl:452-612, 781-801 (GLL nodes, Cartesian sub-grid
  *                            frames PhysicalRegions.jl:72-148); ORACLE ONLY -- it exists to
  *                            pin the 2-D machinery against the reference's Shockwave2D KAT
@@ -90,6 +92,13 @@ typedef struct {
     double blend;             /* op.blend */
     const double *w1d;        /* 1-D weights of the standard region */
     double sub_jac[3];        /* Cartesian sub-grid face Jacobians by direction */
+    /* std |> basis |> hasboundaries (GLL/CGL: 1, GL: 0): selects the surface term of the split form */
+    int32_t hasboundaries;
+    /* TEST DEVICE, not the reference's behaviour: face traces of the Gauss-node split form from the
+     * entropy-projected end states instead of l'Q.  With it the scheme is exactly entropy
+     * conservative, which is how tests/test_oracle_properties.py pins the restatement of the
+     * projection terms; the reference interpolates the conservative variables (Interfaces.jl:93-109). */
+    int32_t proj_traces;
 } oracle_problem;
 
 static inline int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
@@ -134,6 +143,19 @@ static inline void cons2entropy(const double *Q, int nd, double g, double *W)
     W[0] = (g - s) / (g - 1) - m2 / rho / (2 * p);
     for (int d = 0; d < nd; d++) W[1 + d] = Q[1 + d] / p;
     W[nd + 1] = -rho / p;
+}
+
+/* vars_entropy2cons = vars_prim2cons(vars_entropy2prim(W))   FlouCommon/Euler.jl:309-339, 255-271 */
+static inline void entropy2cons(const double *W, int nd, double g, double *Q)
+{
+    double wn = W[nd + 1], vel[3], q = 0;
+    for (int d = 0; d < nd; d++) { vel[d] = -W[1 + d] / wn; q += vel[d] * vel[d]; }
+    double s = g - (g - 1) * (W[0] - wn * q / 2);
+    double p = pow(pow(-wn, g) * exp(s), 1 / (1 - g));
+    double rho = -p * wn;
+    Q[0] = rho;
+    for (int d = 0; d < nd; d++) Q[1 + d] = rho * vel[d];
+    Q[nd + 1] = p / (g - 1) + rho * q / 2;
 }
 
 /* volumeflux: F[c][v], c = physical direction   FlouCommon/Euler.jl:54-114 */
@@ -524,6 +546,19 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
                     QL[fl + k + nfd * v] = sl;
                     QR[fr + k + nfd * v] = sr;
                 }
+                if (P->proj_traces && P->equation == EQ_EULER) {
+                    double Wl[MAXV], Wr[MAXV], Qa[MAXV], Qb[MAXV];
+                    for (int v = 0; v < nv; v++) { Wl[v] = 0; Wr[v] = 0; }
+                    for (int ii = 0; ii < np; ii++) {
+                        double Qi[MAXV], Wi[MAXV];
+                        for (int v = 0; v < nv; v++) Qi[v] = Q[e * npts + base + ii * stride + ndof * v];
+                        cons2entropy(Qi, nd, P->gamma, Wi);
+                        for (int v = 0; v < nv; v++) { Wl[v] += P->lm[ii] * Wi[v]; Wr[v] += P->lp[ii] * Wi[v]; }
+                    }
+                    entropy2cons(Wl, nd, P->gamma, Qa);
+                    entropy2cons(Wr, nd, P->gamma, Qb);
+                    for (int v = 0; v < nv; v++) { QL[fl + k + nfd * v] = Qa[v]; QR[fr + k + nfd * v] = Qb[v]; }
+                }
             }
         }
     }
@@ -715,7 +750,9 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
         }
     }
 
-    /* surface_contribution!   OpDivergence.jl:42-100 */
+    /* surface_contribution!   OpDivergence.jl:42-100; split form on nodes without boundaries:
+     * _splitdiv_nb_surface_contribution!   OpDivergence.jl:300-437 */
+    const int split_nb = (P->op == OP_SPLIT && !P->hasboundaries);
     #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < ne; e++) {
         const int64_t *faces = P->faceinds + e * 2 * nd, *sides = P->facepos + e * 2 * nd;
@@ -723,7 +760,40 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
             const double *FL = sides[2 * d] == 1 ? Fn0 : Fn1;
             const double *FR = sides[2 * d + 1] == 1 ? Fn0 : Fn1;
             int64_t fl = (faces[2 * d] - 1) * nfp, fr = (faces[2 * d + 1] - 1) * nfp;
-            for (int k = 0; k < nlines; k++) {
+            for (int k = 0; k < nlines && split_nb; k++) {
+                /* _flux_splitdiv_nb_tensorproduct! + _surf_splitdiv_nb_tensorproduct! for one row;
+                 * Cartesian sub-grid: frames[dir][*].n = e_dir, Js = sub_jac[dir] */
+                int base, stride;
+                line_of(nd, np, d, k, &base, &stride);
+                const double *Ja = P->metric + (int64_t)e * npts * nd * nd;
+                double nl[3] = {0, 0, 0}, Wl[MAXV], Wr[MAXV], Qa[MAXV], Qb[MAXV];
+                double Fl[MAXNP][MAXV], Fr[MAXNP][MAXV], lFl[MAXV], rFr[MAXV];
+                nl[d] = P->sub_jac[d];                    /* nl = nr on a Cartesian sub-grid */
+                for (int v = 0; v < nv; v++) { Wl[v] = 0; Wr[v] = 0; lFl[v] = 0; rFr[v] = 0; }
+                for (int ii = 0; ii < np; ii++) {
+                    double Qi[MAXV], Wi[MAXV];
+                    for (int v = 0; v < nv; v++) Qi[v] = Q[e * npts + base + ii * stride + ndof * v];
+                    cons2entropy(Qi, nd, P->gamma, Wi);
+                    for (int v = 0; v < nv; v++) { Wl[v] += P->lm[ii] * Wi[v]; Wr[v] += P->lp[ii] * Wi[v]; }
+                }
+                entropy2cons(Wl, nd, P->gamma, Qa);
+                entropy2cons(Wr, nd, P->gamma, Qb);
+                for (int ii = 0; ii < np; ii++) {
+                    int i = base + ii * stride;
+                    double Qi[MAXV];
+                    for (int v = 0; v < nv; v++) Qi[v] = Q[e * npts + i + ndof * v];
+                    twopointflux(P, Qi, Qa, Ja + i * nd * nd + nd * d, nl, Fl[ii]);
+                    twopointflux(P, Qi, Qb, Ja + i * nd * nd + nd * d, nl, Fr[ii]);
+                    for (int v = 0; v < nv; v++) { lFl[v] += P->lm[ii] * Fl[ii][v]; rFr[v] += P->lp[ii] * Fr[ii][v]; }
+                }
+                for (int ii = 0; ii < np; ii++)
+                    for (int v = 0; v < nv; v++) {
+                        double a = Fl[ii][v] - (lFl[v] + FL[fl + k + nfd * v]);
+                        double b = Fr[ii][v] - (rFr[v] - FR[fr + k + nfd * v]);
+                        dQ[e * npts + base + ii * stride + ndof * v] += P->dgl[ii] * a - P->dgr[ii] * b;
+                    }
+            }
+            for (int k = 0; k < nlines && !split_nb; k++) {
                 int base, stride;
                 line_of(nd, np, d, k, &base, &stride);
                 for (int ii = 0; ii < np; ii++)

@@ -81,9 +81,12 @@ def test_generic_bc_is_tabulated_at_face_nodes():
 def test_out_of_scope_features_raise_instead_of_falling_back():
     mesh = F.CartesianMesh(2, (0, 0), (1, 1), (2, 2)).apply_periodicBCs(("1", "2"), ("3", "4"))
     eq = F.EulerEquation(2, 1.4)
-    with pytest.raises(ValueError):        # Gauss-node split form = sub-grid path (next row f4)
-        F.MultielementDisc(mesh, _std(2, nodes="GL"), eq, F.SplitDivOperator(
-            F.MatrixDissipation(F.ChandrasekharAverage(), 1.0)), {}, create=False)
+    # Gauss-node split form (row f4): Euler only -- the reference has no entropy variables for advection
+    F.MultielementDisc(mesh, _std(2, nodes="GL"), eq, F.SplitDivOperator(
+        F.MatrixDissipation(F.ChandrasekharAverage(), 1.0)), {}, create=False)
+    with pytest.raises(ValueError):
+        F.MultielementDisc(mesh, _std(2, nodes="GL", nv=1), F.LinearAdvection(1.0, 0.5),
+                           F.SplitDivOperator(F.StdAverage(), F.LxF(F.StdAverage(), 1.0)), {}, create=False)
     with pytest.raises(ValueError):        # source terms
         F.MultielementDisc(mesh, _std(2), eq, F.StrongDivOperator(F.StdAverage()), {},
                            source=lambda *a: None, create=False)

@@ -196,6 +196,49 @@ def test_sod_tube_kat_on_gpu(gpu):
     dg.close()
 
 
+# ------------------------------------------------------------------ row f4: split form on Gauss nodes
+GAUSS_SPLIT_CASES = [
+    Case(1, (9,), 4, nodes="GL", op="split", nf="mat", avg="cha"),
+    Case(2, (4, 5), 4, nodes="GL", op="split", nf="cha", avg="cha"),
+    Case(2, (3, 4), 5, nodes="GL", op="split", tp="std", nf="lxf", avg="std"),
+    Case(3, (2, 3, 2), 3, nodes="GL", op="split", nf="mat", avg="cha"),
+    Case(3, (2, 2, 2), 4, nodes="GL", op="split", tp="std", nf="sca", avg="cha"),
+    Case(2, (4, 3), 4, nodes="GL", op="split", nf="mat", avg="cha", periodic=[("3", "4")],
+         bcs={"1": ("inflow", [1.1, 0.33, 0.02, 2.6]), "2": ("outflow", None)}),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GAUSS_SPLIT_CASES, ids=repr)
+@pytest.mark.parametrize("state", ["random", "smooth"])
+def test_gauss_node_split_form_matches_oracle(gpu, case, state):
+    """SplitDivOperator on Gauss nodes: the entropy-projected surface term
+    (_splitdiv_nb_surface_contribution!, OpDivergence.jl:300-437) in the line kernel vs the oracle
+    (pinned by its exact entropy balance, tests/test_oracle_properties.py)."""
+    import flou_b200 as F
+    import oracle as O
+    orc = case.oracle()
+    disc, eq = case.product()
+    Q = (random_state(orc.ndof, case.nd, case.eq, amp=case.amp) if state == "random"
+         else smooth_state(orc.coords, case.nd, case.eq))
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert np.all(np.isfinite(dQ))
+    assert relerr(dQ, orc.rhs(Q)) <= RHS_TOL
+    u = Q.copy(order="F")
+    sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), 4e-4, dt=1e-4)
+    assert relerr(sol.u[-1], orc.lsrk2n(Q, O.ORK256, 1e-4, 4)) <= 1e-10
+    disc.close()
+
+
+@pytest.mark.gpu
+def test_gauss_node_split_form_unsupported_combinations_raise(gpu):
+    with pytest.raises(ValueError):
+        Case(2, (3, 3), 4, nodes="GL", op="split", perturb_amp=0.05).product()     # curved sub-grids
+    with pytest.raises(ValueError):
+        Case(2, (3, 3), 4, nodes="GL", op="split").product(kernel="fused")
+
+
 # ------------------------------------------------------------------ row f2: HybridDivOperator
 HYBRID_CASES = [
     Case(1, (10,), 4, op="hybrid", nf="mat", avg="cha", blend=1.0),
