@@ -44,6 +44,9 @@ WORKLOADS = {
                  desc="3D Euler Taylor-Green vortex 128^3 p=4 GLL SplitDiv(Chandrasekhar)+MatrixDissipation ORK256"),
     "cfg4s": dict(nd=3, n=(64, 64, 64), np=5, eq="euler", dt=2e-4,
                   desc="3D Euler Taylor-Green vortex 64^3 p=4 GLL SplitDiv(Chandrasekhar)+MatrixDissipation ORK256"),
+    "cfg5b": dict(nd=2, n=(73 * 1024,), np=6, eq="euler", dt=5e-6, unstructured=32,
+                  desc="2D Euler on the reference's 2D_cylinder quad mesh (73 quads) refined 32x32 (74 752 quads), "
+                       "p=5 GLL, SplitDiv(Chandrasekhar)+MatrixDissipation, slip walls + inflow/outflow, ORK256"),
     "cfg5": dict(nd=2, n=(73 * 64,), np=6, eq="euler", dt=2e-5, unstructured=8,
                  desc="2D Euler on the reference's 2D_cylinder quad mesh (73 quads) refined 8x8, p=5 GLL, "
                       "SplitDiv(Chandrasekhar)+MatrixDissipation, slip walls + inflow/outflow, ORK256"),
