@@ -162,6 +162,44 @@ function Flou.FlouCommon.get_max_dt(q::Matrix{Float64}, disc::B200Disc, ::Any, c
     return dt[]
 end
 
+# get_monitor(disc, equation, name) (FlouSpatial/Equations/Euler.jl:541-557): the returned closure
+# has the reference's signature (_Q, disc, equation); `_Q === nothing` reads the device state.
+# (The reference lists :kinetic_energy but dispatches on :energy: both are accepted.)
+function Flou.FlouCommon.get_monitor(disc::B200Disc, ::EulerEquation, name::Symbol, _=nothing)
+    kind = name in (:kinetic_energy, :energy) ? Int32(0) :
+           name == :entropy ? Int32(1) : error("Unknown monitor '$(name)'.")
+    return (_Q, d, _eq) -> begin
+        v = Ref{Float64}(0.0)
+        check(ccall((:flou_b200_monitor, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ref{Float64}),
+                    d.handle, kind, _Q === nothing ? Ptr{Float64}(C_NULL) : pointer(_Q), v))
+        v[]
+    end
+end
+
+# get_limiter(disc, equation, :zhang_shu, minval) (Euler.jl:597-660): limits _Q in place
+function Flou.FlouCommon.get_limiter(disc::B200Disc, ::EulerEquation, name::Symbol, minval=nothing)
+    name == :zhang_shu || error("Unknown limiter '$(name)'.")
+    minval === nothing && throw(ArgumentError(
+        "The minimum value must be specified when using the limiter of Zhang & Shu."))
+    return (_Q, d, _eq) -> begin
+        check(ccall((:flou_b200_zhang_shu, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64),
+                    d.handle, _Q === nothing ? Ptr{Float64}(C_NULL) : pointer(_Q), Float64(minval)))
+        nothing
+    end
+end
+
+# ORK256(stage_limiter! = get_limiter_callback(dg, eq, :zhang_shu, minval)) as in
+# examples/src/3D_Euler.jl:76-80: the fused RK loop applies the limiter after every stage
+struct B200StageLimiter
+    minval::Float64
+end
+stage_limiter(disc::B200Disc, equation, name::Symbol, minval) =
+    (name == :zhang_shu || error("Unknown limiter '$(name)'."); B200StageLimiter(Float64(minval)))
+function set_stage_limiter!(disc::B200Disc, lim::Union{B200StageLimiter,Nothing})
+    check(ccall((:flou_b200_set_stage_limiter, lib), Int32, (Ptr{Cvoid}, Int32, Float64),
+                disc.handle, lim === nothing ? Int32(0) : Int32(1), lim === nothing ? 0.0 : lim.minval))
+end
+
 # 2N tableaus straight from the OrdinaryDiffEq solver objects' caches
 function tableau(solver::Union{ORK256,CarpenterKennedy2N54})
     tab = OrdinaryDiffEq.alg_cache(solver, zeros(1), zeros(1), Float64, Float64, Float64,
@@ -176,8 +214,10 @@ end
 # timeintegrate(Q0, disc, equation, solver, tfinal; adaptive=false, dt, alias_u0=true)
 function timeintegrate(Q0::Matrix{Float64}, disc::B200Disc, equation,
                        solver::Union{ORK256,CarpenterKennedy2N54}, tfinal;
-                       dt, adaptive=false, alias_u0=true, kwargs...)
+                       dt, adaptive=false, alias_u0=true,
+                       stage_limiter::Union{B200StageLimiter,Nothing}=nothing, kwargs...)
     adaptive && throw(ArgumentError("adaptive=true is not supported on the B200 path"))
+    set_stage_limiter!(disc, stage_limiter)
     A, B, c = tableau(solver)
     Q = alias_u0 ? Q0 : copy(Q0)
     nsteps = round(Int64, tfinal / dt)

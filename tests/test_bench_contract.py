@@ -1,0 +1,40 @@
+"""bench.py contract on CPU: the reference arm (`--impl reference`, the oracle port timed on the
+host cores) prints exactly one JSON line with the keys the driver reads; the b200 arm refuses to
+run without a GPU instead of falling back to the CPU."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, timeout=600):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args],
+                          capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = _run("--impl", "reference", "--workload", "cfg1", "--steps", "1", "--warmup", "0")
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("DOF-updates/sec")
+    for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["value"] > 0 and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    out = _run("--workload", "cfg1", "--steps", "1", "--warmup", "0", "--no-cpu-baseline", "--no-e2e")
+    assert out.returncode != 0
+    assert "no usable CUDA device" in (out.stderr + out.stdout) or "CUDA" in (out.stderr + out.stdout)
