@@ -64,6 +64,7 @@ class _Problem(C.Structure):
         ("bc_faces", C.c_void_p), ("bc_state", C.c_void_p), ("bc_table", C.c_void_p),
         ("Qf", C.c_void_p * 2), ("Fn", C.c_void_p * 2),
         ("blend", C.c_double), ("w1d", C.c_void_p), ("sub_jac", C.c_double * 3),
+        ("sub_frames", C.c_void_p), ("sub_fjac", C.c_void_p),
         ("hasboundaries", C.c_int32), ("proj_traces", C.c_int32),
     ]
 
@@ -193,17 +194,23 @@ class Problem:
         p.w1d, p.blend = _ptr(k["w1d"]), float(blend)
         p.hasboundaries = 1 if self.ops["hasboundaries"] else 0
         split_nb = op == OP_SPLIT and not self.ops["hasboundaries"]
-        if split_nb and not (cartesian and equation == EQ_EULER):
-            raise ValueError("the oracle's split form on Gauss nodes (entropy-projected surface term) "
-                             "covers the Euler equations on Cartesian meshes")
+        if split_nb and equation != EQ_EULER:
+            raise ValueError("the split form on Gauss nodes (entropy-projected surface term) needs the "
+                             "Euler equations")
+        if op == OP_HYBRID and not self.ops["hasboundaries"]:
+            raise ValueError("the oracle's HybridDivOperator covers nodes with boundaries (GLL)")
         if op == OP_HYBRID or split_nb:
-            if op == OP_HYBRID and not (cartesian and self.ops["hasboundaries"]):
-                raise ValueError("the oracle's HybridDivOperator covers GLL nodes on Cartesian meshes")
-            dx = mesh.dx
-            sub = [1.0] if nd == 1 else [dx[1] / 2, dx[0] / 2] if nd == 2 else \
-                [dx[1] * dx[2] / 4, dx[0] * dx[2] / 4, dx[0] * dx[1] / 4]
-            for d_, v_ in enumerate(sub):
-                p.sub_jac[d_] = v_
+            # geometry.subgrids (PhysicalRegions.jl:28-292): Cartesian constants or, on general
+            # meshes, frames / Jacobians from the mapping at the complementary-grid points
+            fr, fj = geometry.subgrid_geometry(mesh, self.ops["xi"], self.ops["w"], cartesian)
+            k["sub_frames"], k["sub_fjac"] = np.ascontiguousarray(fr), np.ascontiguousarray(fj)
+            p.sub_frames, p.sub_fjac = _ptr(k["sub_frames"]), _ptr(k["sub_fjac"])
+            if cartesian:
+                dx = mesh.dx
+                sub = [1.0] if nd == 1 else [dx[1] / 2, dx[0] / 2] if nd == 2 else \
+                    [dx[1] * dx[2] / 4, dx[0] * dx[2] / 4, dx[0] * dx[1] / 4]
+                for d_, v_ in enumerate(sub):
+                    p.sub_jac[d_] = v_
         p.Qf[0], p.Qf[1] = _ptr(k["Qf0"]), _ptr(k["Qf1"])
         p.Fn[0], p.Fn[1] = _ptr(k["Fn0"]), _ptr(k["Fn1"])
 

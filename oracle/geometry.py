@@ -7,6 +7,8 @@ Restatement of Flou.jl's element metrics and face frames.
 * unstructured element metric             PhysicalRegions.jl:438-472
 * Cartesian face frames 1/2/3-D           PhysicalRegions.jl:541-696
 * unstructured face frames 2-D / 3-D      PhysicalRegions.jl:797-871 / 873-971
+* sub-grid points, frames, Jacobians      StdSegment.jl:60-74, StdQuad.jl:56-58,126-137,
+                                          PhysicalRegions.jl:72-148 (Cartesian), 179-292 (general)
 * tensor-product node order               StdQuad.jl:46-50, StdHex.jl:48-54 (x fastest)
 
 Arrays returned (all float64, C-contiguous):
@@ -225,3 +227,99 @@ def face_geometry(mesh, xi1d, cartesian=True, want_coords=True):
                 frames[f * nfp + i, 1] = t
                 frames[f * nfp + i, 2] = b
     return fcoords, fjac, frames
+
+
+# ------------------------------------------------------------------- sub-grid
+def subgrid_points_1d(w):
+    """Complementary-grid points of one direction (StdSegment.jl:60-74): cumulative sums of the
+    weights from both ends, averaged, ends forced to -1 / +1."""
+    n = len(w)
+    c1 = np.zeros(n + 1)
+    c1[0] = -1.0
+    for i in range(n):
+        c1[i + 1] = c1[i] + w[i]
+    c2 = np.zeros(n + 1)
+    c2[n] = 1.0
+    for i in range(n - 1, -1, -1):
+        c2[i] = c2[i + 1] - w[i]
+    c = (c1 + c2) / 2
+    c[0], c[n] = -1.0, 1.0
+    return c
+
+
+def _line_base_xi(nd, n, d, k, xi1d):
+    """Reference coordinates (other than direction d) of tensor-product line k of direction d
+    (tpdofs order: StdQuad.jl:116-124, StdHex.jl:135-145)."""
+    out = np.zeros(nd)
+    if nd == 2:
+        out[1 - d] = xi1d[k]
+    elif nd == 3:
+        a, b = k % n, k // n
+        if d == 0:
+            out[1], out[2] = xi1d[a], xi1d[b]
+        elif d == 1:
+            out[0], out[2] = xi1d[a], xi1d[b]
+        else:
+            out[0], out[1] = xi1d[a], xi1d[b]
+    return out
+
+
+def subgrid_geometry(mesh, xi1d, w1d, cartesian=True):
+    """geometry.subgrids[e].frames[dir][is], .jac[dir][is] re-indexed by (element, direction,
+    line, position along the line): frames (ne, nd, nlines, np+1, 3, nd) rows n, t, b and
+    jac (ne, nd, nlines, np+1).  Sub-grid point `ii` of a line sits at xi_c[ii] along the line's
+    direction and at the line's own nodes otherwise (tpdofs_subgrid)."""
+    nd, n = mesh.nd, len(xi1d)
+    nlines = n ** (nd - 1)
+    ne = mesh.nelements
+    xic = subgrid_points_1d(w1d)
+    frames = np.zeros((ne, nd, nlines, n + 1, 3, nd))
+    jac = np.zeros((ne, nd, nlines, n + 1))
+    for e in range(ne):
+        if cartesian:
+            dx = mesh.dx
+            for d in range(nd):
+                if nd == 1:
+                    frames[e, d, :, :, 0, 0] = 1.0
+                    jac[e, d] = 1.0
+                elif nd == 2:
+                    frames[e, d, :, :, 0, d] = 1.0
+                    frames[e, d, :, :, 1, 1 - d] = 1.0 if d == 0 else -1.0
+                    jac[e, d] = dx[1 - d] / 2
+                else:
+                    frames[e, d, :, :, 0, d] = 1.0
+                    frames[e, d, :, :, 1, (d + 1) % 3] = 1.0
+                    frames[e, d, :, :, 2, (d + 2) % 3] = 1.0
+                    jac[e, d] = np.prod(dx) / dx[d] / 4
+            continue
+        nodes = [mesh.nodes[i - 1] for i in mesh.enodes[e]]
+        for d in range(nd):
+            for k in range(nlines):
+                base = _line_base_xi(nd, n, d, k, xi1d)
+                for ii in range(n + 1):
+                    xi = base.copy()
+                    xi[d] = xic[ii]
+                    main = map_basis(xi, nodes)
+                    dual = map_dual_basis(main)
+                    if nd == 1:
+                        s = np.sign(map_jacobian(main))
+                        frames[e, d, k, ii, 0] = s * dual[0]
+                        jac[e, d, k, ii] = 1.0
+                        continue
+                    if nd == 2:
+                        s = np.sign(map_jacobian(main))
+                        nvec = s * dual[d]
+                        # vertical faces: t = s normalize(main[2]); horizontal: t = -s normalize(main[1])
+                        t = s * _normalize(main[1]) if d == 0 else -s * _normalize(main[0])
+                        b = np.zeros(2)
+                    else:
+                        nvec = dual[d]
+                        t = _normalize(main[(d + 1) % 3])
+                        b = None
+                    j = np.sqrt(np.dot(nvec, nvec))
+                    nvec = nvec / j
+                    if nd == 3:
+                        b = _normalize(np.cross(nvec, t))
+                    frames[e, d, k, ii, 0], frames[e, d, k, ii, 1], frames[e, d, k, ii, 2] = nvec, t, b
+                    jac[e, d, k, ii] = j
+    return frames, jac

@@ -91,7 +91,12 @@ typedef struct {
     /* HybridDivOperator only */
     double blend;             /* op.blend */
     const double *w1d;        /* 1-D weights of the standard region */
-    double sub_jac[3];        /* Cartesian sub-grid face Jacobians by direction */
+    double sub_jac[3];        /* Cartesian sub-grid face Jacobians by direction (kept for reference) */
+    /* geometry.subgrids by (element, direction, line, position along the line):
+     * sub_frames[(((e*nd + d)*nlines + k)*(np+1) + ii)*3*nd + r*nd + c], rows r = n, t, b;
+     * sub_fjac[((e*nd + d)*nlines + k)*(np+1) + ii]   (PhysicalRegions.jl:72-292) */
+    const double *sub_frames;
+    const double *sub_fjac;
     /* std |> basis |> hasboundaries (GLL/CGL: 1, GL: 0): selects the surface term of the split form */
     int32_t hasboundaries;
     /* TEST DEVICE, not the reference's behaviour: face traces of the Gauss-node split form from the
@@ -606,12 +611,8 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
                         line_of(nd, np, d, k, &base, &stride);
                         double Fb[MAXNP + 1][MAXV];
                         memset(Fb, 0, sizeof Fb);
-                        /* Cartesian sub-grid frame of direction d: PhysicalRegions.jl:72-148 */
-                        double fr[9];
-                        memset(fr, 0, sizeof fr);
-                        fr[d] = 1.0;
-                        if (nd == 2) fr[nd + (1 - d)] = (d == 0) ? 1.0 : -1.0;
-                        if (nd == 3) { fr[nd + (d + 1) % 3] = 1.0; fr[2 * nd + (d + 2) % 3] = 1.0; }
+                        /* sub-grid frames / Jacobians of this line: PhysicalRegions.jl:72-292 */
+                        const int64_t sg0 = (((int64_t)e * nd + d) * nlines + k) * (np + 1);
                         for (int ii = 1; ii < np; ii++) {          /* Julia ii = 2..npts */
                             for (int ik = ii; ik < np; ik++) {
                                 int kk = base + ik * stride;
@@ -634,11 +635,12 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
                                 Qa[v] = Q[e * npts + il + ndof * v];
                                 Qb[v] = Q[e * npts + i + ndof * v];
                             }
+                            const double *fr = P->sub_frames + (sg0 + ii) * 3 * nd;
                             rotate2face(P, Qa, fr, Qln);
                             rotate2face(P, Qb, fr, Qrn);
                             numericalflux(P, Qln, Qrn, fr, Fn_);
                             rotate2phys(P, Fn_, fr, Fv);
-                            for (int v = 0; v < nv; v++) Fv[v] *= P->sub_jac[d];
+                            for (int v = 0; v < nv; v++) Fv[v] *= P->sub_fjac[sg0 + ii];
                             double Wl[MAXV], Wr[MAXV], b = 0;
                             cons2entropy(Qa, nd, P->gamma, Wl);
                             cons2entropy(Qb, nd, P->gamma, Wr);
@@ -761,14 +763,17 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
             const double *FR = sides[2 * d + 1] == 1 ? Fn0 : Fn1;
             int64_t fl = (faces[2 * d] - 1) * nfp, fr = (faces[2 * d + 1] - 1) * nfp;
             for (int k = 0; k < nlines && split_nb; k++) {
-                /* _flux_splitdiv_nb_tensorproduct! + _surf_splitdiv_nb_tensorproduct! for one row;
-                 * Cartesian sub-grid: frames[dir][*].n = e_dir, Js = sub_jac[dir] */
+                /* _flux_splitdiv_nb_tensorproduct! + _surf_splitdiv_nb_tensorproduct! for one row */
                 int base, stride;
                 line_of(nd, np, d, k, &base, &stride);
                 const double *Ja = P->metric + (int64_t)e * npts * nd * nd;
-                double nl[3] = {0, 0, 0}, Wl[MAXV], Wr[MAXV], Qa[MAXV], Qb[MAXV];
+                double nl[3] = {0, 0, 0}, nr[3] = {0, 0, 0}, Wl[MAXV], Wr[MAXV], Qa[MAXV], Qb[MAXV];
                 double Fl[MAXNP][MAXV], Fr[MAXNP][MAXV], lFl[MAXV], rFr[MAXV];
-                nl[d] = P->sub_jac[d];                    /* nl = nr on a Cartesian sub-grid */
+                const int64_t sg0 = (((int64_t)e * nd + d) * nlines + k) * (np + 1);
+                for (int c = 0; c < nd; c++) {            /* frames[dir][i1].n * Js[dir][i1], i2 */
+                    nl[c] = P->sub_frames[sg0 * 3 * nd + c] * P->sub_fjac[sg0];
+                    nr[c] = P->sub_frames[(sg0 + np) * 3 * nd + c] * P->sub_fjac[sg0 + np];
+                }
                 for (int v = 0; v < nv; v++) { Wl[v] = 0; Wr[v] = 0; lFl[v] = 0; rFr[v] = 0; }
                 for (int ii = 0; ii < np; ii++) {
                     double Qi[MAXV], Wi[MAXV];
@@ -783,7 +788,7 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
                     double Qi[MAXV];
                     for (int v = 0; v < nv; v++) Qi[v] = Q[e * npts + i + ndof * v];
                     twopointflux(P, Qi, Qa, Ja + i * nd * nd + nd * d, nl, Fl[ii]);
-                    twopointflux(P, Qi, Qb, Ja + i * nd * nd + nd * d, nl, Fr[ii]);
+                    twopointflux(P, Qi, Qb, Ja + i * nd * nd + nd * d, nr, Fr[ii]);
                     for (int v = 0; v < nv; v++) { lFl[v] += P->lm[ii] * Fl[ii][v]; rFr[v] += P->lp[ii] * Fr[ii][v]; }
                 }
                 for (int ii = 0; ii < np; ii++)

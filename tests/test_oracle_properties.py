@@ -286,3 +286,87 @@ def test_gauss_node_split_form_differs_from_plain_lifting():
     Q = random_state(orc.ndof, 2, "euler", amp=case.amp)
     W = _entropy_vars(Q, 2, case.gamma)
     assert _integral(orc, np.sum(W * orc.rhs(Q), axis=1)) < 0          # matrix dissipation: dissipative
+
+
+# ------------------------------------------------------------------ sub-grid geometry on general meshes
+# (PhysicalRegions.jl:179-292; oracle only so far -- groundwork for the hybrid operator and the
+# Gauss-node split form on curved meshes, row f2/f4)
+def _rotated_problem(nd_n_np, theta, **kw):
+    """A periodic Cartesian 2-D mesh rotated by theta, assembled through the general-geometry path."""
+    from oracle import connectivity as ocn
+    n, npn = nd_n_np
+    mesh = ocn.cartesian_mesh([0.0, 0.0], [1.0, 1.5], n)
+    c, s = np.cos(theta), np.sin(theta)
+    R = np.array([[c, -s], [s, c]])
+    mesh.nodes = [R @ np.asarray(x, dtype=float) for x in mesh.nodes]
+    ocn.apply_periodic_bcs(mesh, ("1", "2"), ("3", "4"))
+    return O.Problem(mesh, kw.pop("nodes", "GLL"), npn, O.EQ_EULER, kw.pop("op"), O.FLUX_MATRIXDISS,
+                     numflux_avg=O.FLUX_CHANDRASEKHAR, intensity=1.0, gamma=1.4, cartesian=False, **kw), R
+
+
+@pytest.mark.parametrize("opkw", [dict(op=O.OP_HYBRID, blend=0.3), dict(op=O.OP_SPLIT, nodes="GL")],
+                         ids=["hybrid", "gauss-split"])
+def test_general_subgrid_path_equals_cartesian_path_on_a_cartesian_mesh(opkw):
+    """The frames / Jacobians computed from the mapping at the complementary-grid points reproduce
+    the Cartesian constants: same RHS through either path."""
+    kw = dict(opkw)
+    nodes = kw.pop("nodes", "GLL")
+    op = kw.pop("op")
+    case = Case(2, (4, 3), 4, nodes=nodes, op="hybrid" if op == O.OP_HYBRID else "split", nf="mat", avg="cha",
+                blend=kw.get("blend", 1.0))
+    cart = case.oracle()
+    case.general = True
+    gen = case.oracle()
+    Q = random_state(cart.ndof, 2, "euler", amp=case.amp)
+    a, b = cart.rhs(Q), gen.rhs(Q)
+    assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(a))
+
+
+@pytest.mark.parametrize("opkw", [dict(op=O.OP_HYBRID, blend=0.3), dict(op=O.OP_SPLIT, nodes="GL")],
+                         ids=["hybrid", "gauss-split"])
+def test_rotation_invariance_with_general_subgrid_frames(opkw):
+    """Rotating the mesh and the velocities rotates the RHS: exercises normals AND tangents of the
+    sub-grid frames away from the coordinate axes."""
+    p0, _ = _rotated_problem(((4, 3), 4), 0.0, **dict(opkw))
+    p1, R = _rotated_problem(((4, 3), 4), 0.7, **dict(opkw))
+    Q = random_state(p0.ndof, 2, "euler", amp=0.15)
+    Qr = Q.copy(order="F")
+    Qr[:, 1:3] = Q[:, 1:3] @ R.T
+    d0, d1 = p0.rhs(Q), p1.rhs(Qr)
+    want = d0.copy(order="F")
+    want[:, 1:3] = d0[:, 1:3] @ R.T
+    assert np.max(np.abs(d1 - want)) <= 1e-11 * np.max(np.abs(want))
+
+
+def _interior_perturbed_problem(nd, n, npn, which):
+    """Periodic box whose INTERIOR vertices are perturbed (the periodic boundary faces stay
+    congruent, so the mesh is watertight), general-geometry path."""
+    from oracle import connectivity as ocn
+    start, finish = [0.0] * nd, [1.0 + 0.5 * d for d in range(nd)]
+    mesh = ocn.cartesian_mesh(start, finish, n)
+    rng = np.random.default_rng(11)
+    h = min(mesh.dx)
+    nodes = []
+    for x in mesh.nodes:
+        x = np.asarray(x, dtype=float)
+        inside = all(start[c] + 1e-9 < x[c] < finish[c] - 1e-9 for c in range(nd))
+        nodes.append(x + (0.12 * h * rng.uniform(-1, 1, nd) if inside else 0.0))
+    mesh.nodes = nodes
+    ocn.apply_periodic_bcs(mesh, *[(str(2 * d + 1), str(2 * d + 2)) for d in range(nd)])
+    kw = dict(blend=0.5) if which == "hybrid" else {}
+    return O.Problem(mesh, "GLL" if which == "hybrid" else "GL", npn, O.EQ_EULER,
+                     O.OP_HYBRID if which == "hybrid" else O.OP_SPLIT, O.FLUX_MATRIXDISS,
+                     numflux_avg=O.FLUX_CHANDRASEKHAR, intensity=1.0, gamma=1.4, cartesian=False, **kw)
+
+
+@pytest.mark.parametrize("nd,n,npn", [(2, (4, 3), 4), (3, (3, 3, 3), 3)])
+@pytest.mark.parametrize("which", ["hybrid", "gauss-split"])
+def test_curved_mesh_free_stream_and_conservation(nd, n, npn, which):
+    orc = _interior_perturbed_problem(nd, n, npn, which)
+    assert np.ptp(orc.jac) > 1e-3 * np.mean(orc.jac)          # the elements really are distorted
+    Q = random_state(orc.ndof, nd, "euler", amp=0.15)
+    dQ = orc.rhs(Q)
+    for v in range(orc.nv):
+        assert abs(_integral(orc, dQ[:, v])) < 1e-12 * _integral(orc, np.abs(dQ[:, v])) + 1e-13
+    Qc = np.asfortranarray(np.tile(Q[:1], (orc.ndof, 1)))
+    assert np.max(np.abs(orc.rhs(Qc))) < 1e-10
