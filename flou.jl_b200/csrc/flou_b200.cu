@@ -337,6 +337,7 @@ struct flou_b200_handle {
     Conn *conn = nullptr;
     int *faceid = nullptr;
     double *jac = nullptr, *metric = nullptr, *fjac = nullptr, *frames = nullptr;
+    double *sub_frames = nullptr, *sub_jac = nullptr;     // sub-grid tables of the owned elements
     int *bc_kind = nullptr;
     double *bc_state = nullptr, *bc_table = nullptr;
     int *status = nullptr;
@@ -674,7 +675,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     if (split_nb) {
         const char *why = nullptr;
         if (d->equation != FLOU_B200_EQ_EULER) why = "SplitDivOperator on Gauss nodes needs entropy variables (Euler equations)";
-        else if (!cart) why = "SplitDivOperator on Gauss nodes is built for Cartesian sub-grids only";
+        else if (!cart && (!d->sub_frames || !d->sub_jac)) why = "SplitDivOperator on Gauss nodes: sub-grid tables (sub_frames, sub_jac) missing";
         else if (d->flags & (FLOU_B200_FLAG_FUSED | FLOU_B200_FLAG_NODE_KERNEL))
             why = "SplitDivOperator on Gauss nodes exists in the line-per-thread kernel only";
         if (why) { flou_b200_destroy(h); return fail(FLOU_B200_EUNSUPPORTED, why); }
@@ -682,6 +683,10 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         h->stage = get_stage_launcher(nd, np, d->equation,
                                       d->tpflux == FLOU_B200_FLUX_CHANDRASEKHAR ? 5 : 4, cart);
         if (!h->stage) { flou_b200_destroy(h); return fail(FLOU_B200_EUNSUPPORTED, "no kernel compiled for this (nd, np)"); }
+    }
+    if (hybrid && !cart && (!d->sub_frames || !d->sub_jac)) {
+        flou_b200_destroy(h);
+        return fail(FLOU_B200_EINVAL, "HybridDivOperator on a general mesh: sub-grid tables (sub_frames, sub_jac) missing");
     }
     if (hybrid && !colloc) {
         // the reference moves everything to the surface term on Gauss nodes
@@ -769,6 +774,16 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         H_TRY(upload(&h->metric, met));
         H_TRY(upload(&h->fjac, fj));
         H_TRY(upload(&h->frames, fr));
+        if ((hybrid || split_nb) && d->sub_frames && d->sub_jac) {
+            // geometry.subgrids of the owned elements, layout of the descriptor kept
+            const size_t per_elem = (size_t)nd * h->nfp * (np + 1);
+            std::vector<double> sf(d->sub_frames + (size_t)d->elem_begin * per_elem * 3 * nd,
+                                   d->sub_frames + (size_t)d->elem_end * per_elem * 3 * nd);
+            std::vector<double> sj(d->sub_jac + (size_t)d->elem_begin * per_elem,
+                                   d->sub_jac + (size_t)d->elem_end * per_elem);
+            H_TRY(upload(&h->sub_frames, sf));
+            H_TRY(upload(&h->sub_jac, sj));
+        }
         H_TRY(upload(&h->faceid, faceid));
         P.nfacedofs = nfd;
     }
@@ -869,6 +884,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     H_TRY(h->stage->prepare());
 #undef H_TRY
     P.jac = h->jac; P.metric = h->metric; P.fjac = h->fjac; P.frames = h->frames;
+    P.sub_frames = h->sub_frames; P.sub_jac = h->sub_jac;
     P.faceid = h->faceid; P.conn = h->conn;
     P.faces = h->faces; P.econn = h->econn; P.Fn = h->Fn; P.split_faces = h->split_faces ? 1 : 0;
     P.bc_kind = h->bc_kind; P.bc_state = h->bc_state; P.bc_table = h->bc_table;
@@ -889,7 +905,8 @@ int32_t flou_b200_destroy(flou_b200_handle *h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void *ptrs[] = {h->u[0], h->u[1], h->tr[0], h->tr[1], h->tr_all, h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
                     h->frames, h->faces, h->econn, h->Fn, h->elem_dx, h->dt_bits, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
-                    h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list, h->w_nodes, h->mon_partial};
+                    h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list, h->w_nodes, h->mon_partial,
+                    h->sub_frames, h->sub_jac};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev_emit) cudaEventDestroy(h->ev_emit);

@@ -233,11 +233,11 @@ static const StageLauncher table[2][6][2] = {
         {make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, true>>()},
         {make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
-        // HybridDivOperator: Cartesian sub-grids only (general sub-grid geometry: row f2b, not built)
-        {StageLauncher{}, make_lines<KCfg<ND, NP, EQ_EULER, VOL_HYBRID, true>>()},
-        // split form on Gauss nodes: Cartesian sub-grids only
-        {StageLauncher{}, make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, true>>()},
-        {StageLauncher{}, make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
+        // HybridDivOperator (general geometry reads the sub-grid tables)
+        {make_lines<KCfg<ND, NP, EQ_EULER, VOL_HYBRID, false>>(), make_lines<KCfg<ND, NP, EQ_EULER, VOL_HYBRID, true>>()},
+        // split form on Gauss nodes
+        {make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, false>>(), make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, true>>()},
+        {make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, false>>(), make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
     },
 };
 

@@ -145,7 +145,7 @@ struct LCfg {
     static constexpr int NLINES = ND * NFP;
     static constexpr bool HYBRID = (VOL == VOL_HYBRID);
     static constexpr bool SPLIT = (VOL == VOL_SPLIT_STD || VOL == VOL_SPLIT_CHA);
-    static_assert(!HYBRID || (EQ == EQ_EULER && CART), "HybridDivOperator: Euler on Cartesian sub-grids only");
+    static_assert(!HYBRID || EQ == EQ_EULER, "HybridDivOperator: Euler equations only");
     // Cartesian split form: the constant metric factor is applied when the partial sums are added
     static constexpr bool FOLD = CART && SPLIT;
     // node data in shared memory: Chandrasekhar (rho, v/2, beta); StdAverage (Q, v, p);
@@ -338,12 +338,23 @@ __device__ __forceinline__ bool cha_pairs(const KParams &P, const double (&r)[C:
 // Each pair flux is evaluated once and added to every sub-cell interface between its two nodes.
 template <class C, int D>
 __device__ __forceinline__ void hybrid_line(const KParams &P, const double (&Q)[C::NP][C::NV],
+                                            int64_t gnode0, int stride, int64_t sub0,
                                             double (&acc)[C::NP][C::NV])
 {
     constexpr int ND = C::ND, NP = C::NP, NV = C::NV, EQ = C::EQ;
+    constexpr bool CART = C::CART;
     const double g = P.fp.gamma;
-    const double js = P.cmet[D];
+    const double js = CART ? P.cmet[D] : 0.0;
     double vel[NP][ND], hv[NP][ND], q[NP], pr[NP], beta[NP], W[NP][NV];
+    // metric vector of direction D at the line's nodes, Ja[:, D] (general geometry; constant
+    // cmet[D] e_D on Cartesian meshes, PhysicalRegions.jl:370-408)
+    double mt[CART ? 1 : NP][CART ? 1 : ND];
+    if (!CART) {
+#pragma unroll
+        for (int j = 0; j < NP; j++)
+#pragma unroll
+            for (int c = 0; c < ND; c++) mt[CART ? 0 : j][CART ? 0 : c] = __ldg(P.metric + gnode0 + j * stride + P.ndof * (c + ND * D));
+    }
 #pragma unroll
     for (int j = 0; j < NP; j++) {
         NodeAux<ND> A;
@@ -363,9 +374,6 @@ __device__ __forceinline__ void hybrid_line(const KParams &P, const double (&Q)[
         for (int c = 0; c < ND; c++) W[j][1 + c] = Q[j][1 + c] / A.p;
         W[j][ND + 1] = -Q[j][0] / A.p;
     }
-    double n[ND];
-#pragma unroll
-    for (int c = 0; c < ND; c++) n[c] = (c == D) ? js : 0.0;
 
     double Fb[NP + 1][NV];
 #pragma unroll
@@ -376,7 +384,10 @@ __device__ __forceinline__ void hybrid_line(const KParams &P, const double (&Q)[
     for (int il = 0; il < NP - 1; il++)
 #pragma unroll
         for (int ik = il + 1; ik < NP; ik++) {
-            double F[NV];
+            double F[NV], n[ND];
+#pragma unroll
+            for (int c = 0; c < ND; c++)
+                n[c] = CART ? ((c == D) ? js : 0.0) : 0.5 * (mt[CART ? 0 : il][CART ? 0 : c] + mt[CART ? 0 : ik][CART ? 0 : c]);
             if (P.tpflux == FX_CHA)
                 tp_chandrasekhar<ND>(Q[il][0], hv[il], q[il], beta[il], Q[ik][0], hv[ik], q[ik], beta[ik],
                                      P.fp.inv_gm1, n, F);
@@ -390,15 +401,27 @@ __device__ __forceinline__ void hybrid_line(const KParams &P, const double (&Q)[
         }
 #pragma unroll
     for (int ii = 1; ii < NP; ii++) {
-        double Rl[NV], Rr[NV], Fn[NV], Fv[NV];
-        rot2face_c<ND, EQ, 2 * D + 1>(Q[ii - 1], Rl);
-        rot2face_c<ND, EQ, 2 * D + 1>(Q[ii], Rr);
-        euler_numflux<ND>(P.fp, Rl, Rr, Fn);
-        rot2phys_c<ND, EQ, 2 * D + 1>(Fn, Fv);
+        double Rl[NV], Rr[NV], Fn[NV], Fv[NV], jsi = js;
+        if (CART) {
+            rot2face_c<ND, EQ, 2 * D + 1>(Q[ii - 1], Rl);
+            rot2face_c<ND, EQ, 2 * D + 1>(Q[ii], Rr);
+            euler_numflux<ND>(P.fp, Rl, Rr, Fn);
+            rot2phys_c<ND, EQ, 2 * D + 1>(Fn, Fv);
+        } else {
+            // frame and Jacobian of sub-cell interface ii of this line (PhysicalRegions.jl:179-292)
+            double fr[3 * ND];
+#pragma unroll
+            for (int c = 0; c < 3 * ND; c++) fr[c] = (c < ND * ND || ND == 3) ? __ldg(P.sub_frames + (sub0 + ii) * (3 * ND) + c) : 0.0;
+            jsi = __ldg(P.sub_jac + sub0 + ii);
+            rotate2face<ND, EQ>(Q[ii - 1], fr, Rl);
+            rotate2face<ND, EQ>(Q[ii], fr, Rr);
+            euler_numflux<ND>(P.fp, Rl, Rr, Fn);
+            rotate2phys<ND, EQ>(Fn, fr, Fv);
+        }
         double b = 0.0;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-            Fv[v] *= js;
+            Fv[v] *= jsi;
             b += (W[ii][v] - W[ii - 1][v]) * (Fb[ii][v] - Fv[v]);
         }
         double delta = sqrt(b * b + P.blend);                 // _hybrid_compute_delta (Fisher)
@@ -424,10 +447,28 @@ __device__ __forceinline__ void hybrid_line(const KParams &P, const double (&Q)[
 template <class C>
 __device__ __forceinline__ void splitdiv_nb_line(const KParams &P, const double *sA, const double *sF,
                                               int base, int stride, const int (&pc)[C::ND], int task,
-                                              double wl, double wr, double (&acc)[C::NP][C::NV])
+                                              double wl, double wr, int d, int64_t gnode0, int64_t sub0,
+                                              double (&acc)[C::NP][C::NV])
 {
     constexpr int ND = C::ND, NP = C::NP, NV = C::NV, N = C::N, LT = C::LT, VOL = C::VOL;
+    constexpr bool CART = C::CART;
     const double g = P.fp.gamma;
+    // general geometry: metric vector Ja[:, d] of the line's nodes and the sub-grid normals times
+    // Jacobians at the two ends of the line (frames[dir][i1].n * Js[dir][i1], OpDivergence.jl:396-399)
+    double mt[CART ? 1 : NP][CART ? 1 : ND], nend[2][ND];
+    if (!CART) {
+#pragma unroll
+        for (int j = 0; j < NP; j++)
+#pragma unroll
+            for (int c = 0; c < ND; c++) mt[CART ? 0 : j][CART ? 0 : c] = __ldg(P.metric + gnode0 + j * stride + P.ndof * (c + ND * d));
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int64_t si = sub0 + (e ? NP : 0);
+            const double js = __ldg(P.sub_jac + si);
+#pragma unroll
+            for (int c = 0; c < ND; c++) nend[e][c] = __ldg(P.sub_frames + si * (3 * ND) + c) * js;
+        }
+    }
     double rho[NP], vel[NP][ND], pr[NP], Wl[NV], Wr[NV];
 #pragma unroll
     for (int v = 0; v < NV; v++) { Wl[v] = 0.0; Wr[v] = 0.0; }
@@ -476,21 +517,29 @@ __device__ __forceinline__ void splitdiv_nb_line(const KParams &P, const double 
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             double *F = e ? Fr[j] : Fl[j];
+            // averaged metric vector: unit axis 0 in the folded Cartesian form, (Ja_i + n_end)/2 else
+            double n[ND];
+#pragma unroll
+            for (int c = 0; c < ND; c++)
+                n[c] = CART ? ((c == 0) ? 1.0 : 0.0) : 0.5 * (mt[CART ? 0 : j][CART ? 0 : c] + nend[e][c]);
             if (VOL == VOL_SPLIT_CHA) {
                 double h1[ND], h2[ND];
                 int dummy = 0;
 #pragma unroll
                 for (int c = 0; c < ND; c++) { h1[c] = 0.5 * vel[j][c]; h2[c] = 0.5 * ve[e][c]; }
-                tp_cha_axis<ND, false>(rho[j], h1, rho[j] / (2.0 * pr[j]), re[e], h2, re[e] / (2.0 * pe[e]),
-                                       P.fp.inv_gm1, F, dummy);
+                if (CART)
+                    tp_cha_axis<ND, false>(rho[j], h1, rho[j] / (2.0 * pr[j]), re[e], h2, re[e] / (2.0 * pe[e]),
+                                           P.fp.inv_gm1, F, dummy);
+                else
+                    tp_cha_n<ND, false>(rho[j], h1, rho[j] / (2.0 * pr[j]), re[e], h2, re[e] / (2.0 * pe[e]),
+                                        P.fp.inv_gm1, n, F, dummy);
             } else {
-                double Q1[NV], Q2[NV], n[ND], q1 = 0.0, q2 = 0.0;
+                double Q1[NV], Q2[NV], q1 = 0.0, q2 = 0.0;
                 Q1[0] = rho[j]; Q2[0] = re[e];
 #pragma unroll
                 for (int c = 0; c < ND; c++) {
                     Q1[1 + c] = rho[j] * vel[j][c]; Q2[1 + c] = re[e] * ve[e][c];
                     q1 += vel[j][c] * vel[j][c]; q2 += ve[e][c] * ve[e][c];
-                    n[c] = (c == 0) ? 1.0 : 0.0;
                 }
                 Q1[ND + 1] = pr[j] * P.fp.inv_gm1 + 0.5 * rho[j] * q1;
                 Q2[ND + 1] = pe[e] * P.fp.inv_gm1 + 0.5 * re[e] * q2;
@@ -548,9 +597,12 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
             for (int j = 0; j < NP; j++)
 #pragma unroll
                 for (int v = 0; v < NV; v++) Qj[j][v] = sA[v * N + base + j * stride];
-            if (d == 0) hybrid_line<C, 0>(P, Qj, acc);
-            else if (ND >= 2 && d == 1) hybrid_line<C, (ND >= 2 ? 1 : 0)>(P, Qj, acc);
-            else if (ND >= 3) hybrid_line<C, (ND >= 3 ? 2 : 0)>(P, Qj, acc);
+            // global node of the line's first node and the line's slot in the sub-grid tables
+            const int64_t gnode0 = dof0 + base;
+            const int64_t sub0 = (((dof0 / NPTS + el) * ND + d) * NFP + k) * (NP + 1);
+            if (d == 0) hybrid_line<C, 0>(P, Qj, gnode0, stride, sub0, acc);
+            else if (ND >= 2 && d == 1) hybrid_line<C, (ND >= 2 ? 1 : 0)>(P, Qj, gnode0, stride, sub0, acc);
+            else if (ND >= 3) hybrid_line<C, (ND >= 3 ? 2 : 0)>(P, Qj, gnode0, stride, sub0, acc);
         } else if (!SPLIT) {
             // strong form: dQ[line] -= Ds * F~[line, d]
 #pragma unroll
@@ -656,10 +708,12 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
             } else if (SPLIT && EQ == EQ_EULER) {
                 // split form on nodes without boundaries (Gauss): the surface term couples every
                 // node of the line with the entropy-projected end states
-                // (_splitdiv_nb_surface_contribution!, OpDivergence.jl:300-437).  Cartesian
-                // sub-grids only, NB instances only (the host selects them for such nodes); these
+                // (_splitdiv_nb_surface_contribution!, OpDivergence.jl:300-437); NB instances only (the host selects them for such nodes); these
                 // never take the fast Chandrasekhar path, which has no surface code
-                if constexpr (C::NB && CART && !FAST) splitdiv_nb_line<C>(P, sA, sF, base, stride, pc, task, wl, wr, acc);
+                if constexpr (C::NB && !FAST) {
+                    const int64_t sub0 = (((dof0 / NPTS + el) * ND + d) * NFP + k) * (NP + 1);
+                    splitdiv_nb_line<C>(P, sA, sF, base, stride, pc, task, wl, wr, d, dof0 + base, sub0, acc);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < NP; j++) {

@@ -96,6 +96,10 @@ struct KParams {
     double w1d[8];
     double blend;
     int tpflux;
+    // sub-grid frames / Jacobians of unstructured elements (hybrid operator, Gauss-node split form):
+    // [(((e*ND + d)*NFP + k)*(NP+1) + ii)*3*ND + r*ND + c] and [((e*ND + d)*NFP + k)*(NP+1) + ii], e local
+    const double *sub_frames;
+    const double *sub_jac;
     int prefetch_groups;        // line kernel: CTAs resident on the device (L2 prefetch distance)
     // general geometry, device SoA
     const double *jac;          // [dof]

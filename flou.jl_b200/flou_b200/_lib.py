@@ -52,6 +52,7 @@ class Desc(C.Structure):
         ("elem_begin", C.c_int64), ("elem_end", C.c_int64),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("part_offsets", C.c_void_p),
         ("device", C.c_int32), ("flags", C.c_int32), ("blend", C.c_double),
+        ("sub_frames", C.c_void_p), ("sub_jac", C.c_void_p),
     ]
 
 

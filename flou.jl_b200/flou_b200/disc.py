@@ -80,6 +80,10 @@ class MultielementDisc:
             jac, metric = G.general_element_geometry(self._verts, std.xi)
             _, fjac, frames = self._face_geometry()
             keep.update(jac=jac, metric=metric, fjac=fjac, frames=frames)
+            if op.kind == L.OP_HYBRID or (op.kind == L.OP_SPLIT and not std.basis.hasboundaries):
+                # requires_subgrid(op, std): geometry.subgrids (PhysicalRegions.jl:179-292)
+                sfr, sjac = G.general_subgrid_geometry(self._verts, std.xi1d, std.w1d)
+                keep.update(sub_frames=sfr, sub_jac=sjac)
 
         # ---- descriptor
         d = self._desc = L.Desc()
@@ -137,6 +141,8 @@ class MultielementDisc:
         if not cart:
             for name in ("jac", "metric", "fjac", "frames"):
                 setattr(d, name, _ptr(keep[name]))
+            if "sub_frames" in keep:
+                d.sub_frames, d.sub_jac = _ptr(keep["sub_frames"]), _ptr(keep["sub_jac"])
         d.nbound = nb
         d.elem_begin, d.elem_end = self.elem_begin, self.elem_end
         d.rank, d.nranks = self.rank, self.nranks
@@ -163,7 +169,7 @@ class MultielementDisc:
         if create:
             L.check(L.lib().flou_b200_create(C.byref(d), C.byref(self._h)))
             # the library copied everything it needs; drop the big host tables
-            for name in ("jac", "metric", "fjac", "frames"):
+            for name in ("jac", "metric", "fjac", "frames", "sub_frames", "sub_jac"):
                 keep.pop(name, None)
 
     def partition_plan(self):

@@ -145,3 +145,68 @@ def general_face_geometry(verts, eleminds, elempos, xif, nd):
         frames[sel, :, 2] = b
     return (fcoords.reshape(-1, nd), fjac.reshape(-1),
             np.ascontiguousarray(frames.reshape(nf * nfp, 3 * nd)))
+
+
+# ------------------------------------------------------------------ sub-grid (HybridDivOperator, Gauss-node split form)
+def subgrid_points_1d(w):
+    """Complementary-grid points of one direction (StdSegment.jl:60-74): cumulative sums of the
+    weights from either end, averaged; end points exactly -1 and +1."""
+    w = np.asarray(w, dtype=np.float64)
+    n = w.size
+    c1 = np.concatenate(([-1.0], -1.0 + np.cumsum(w)))
+    c2 = np.concatenate((1.0 - np.cumsum(w[::-1])[::-1], [1.0]))
+    c = (c1 + c2) / 2
+    c[0], c[n] = -1.0, 1.0
+    return c
+
+
+def general_subgrid_geometry(verts, xi1d, w1d):
+    """geometry.subgrids (PhysicalRegions.jl:179-292) of unstructured elements, indexed by
+    (element, direction, tensor-product line, position along the line):
+      frames (ne, nd, nlines, np+1, 3*nd) rows n, t, b;   jac (ne, nd, nlines, np+1).
+    Point `ii` of line k of direction d sits at xi_c[ii] along d and at the line's own node
+    coordinates otherwise (tpdofs_subgrid, StdQuad.jl:126-137)."""
+    ne, nd = verts.shape[0], verts.shape[2]
+    n = len(xi1d)
+    nlines = n ** (nd - 1)
+    xic = subgrid_points_1d(w1d)
+    frames = np.zeros((ne, nd, nlines, n + 1, 3, nd))
+    fjac = np.zeros((ne, nd, nlines, n + 1))
+    for d in range(nd):
+        # reference points (nlines*(n+1), nd), line-major
+        pts = np.zeros((nlines, n + 1, nd))
+        pts[:, :, d] = xic[None, :]
+        if nd == 2:
+            pts[:, :, 1 - d] = np.asarray(xi1d)[:, None]
+        elif nd == 3:
+            k = np.arange(nlines)
+            a, b = np.asarray(xi1d)[k % n], np.asarray(xi1d)[k // n]
+            o1, o2 = [c for c in range(3) if c != d]
+            pts[:, :, o1], pts[:, :, o2] = a[:, None], b[:, None]
+        main = _main_basis(verts, pts.reshape(-1, nd))            # (ne, P, nd, nd)
+        dual, jac = _dual_and_jac(main)
+        if nd == 1:
+            frames[:, 0, :, :, 0, 0] = (np.sign(jac) * dual[..., 0, 0]).reshape(ne, nlines, n + 1)
+            fjac[:, 0] = 1.0
+            continue
+        if nd == 2:
+            s = np.sign(jac)[..., None]
+            nv = s * dual[..., d, :]
+            tv = main[..., 1, :] if d == 0 else -main[..., 0, :]
+            t = s * tv / np.linalg.norm(tv, axis=-1, keepdims=True)
+            b = np.zeros_like(nv)
+        else:
+            nv = dual[..., d, :]
+            tv = main[..., (d + 1) % 3, :]
+            t = tv / np.linalg.norm(tv, axis=-1, keepdims=True)
+        j = np.linalg.norm(nv, axis=-1)
+        nv = nv / j[..., None]
+        if nd == 3:
+            b = np.cross(nv, t)
+            b = b / np.linalg.norm(b, axis=-1, keepdims=True)
+        shp = (ne, nlines, n + 1)
+        frames[:, d, :, :, 0] = nv.reshape(shp + (nd,))
+        frames[:, d, :, :, 1] = t.reshape(shp + (nd,))
+        frames[:, d, :, :, 2] = b.reshape(shp + (nd,))
+        fjac[:, d] = j.reshape(shp)
+    return np.ascontiguousarray(frames.reshape(ne, nd, nlines, n + 1, 3 * nd)), np.ascontiguousarray(fjac)

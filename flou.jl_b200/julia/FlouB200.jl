@@ -45,6 +45,7 @@ struct Desc
     rank::Int32; nranks::Int32; part_offsets::Ptr{Int64}
     device::Int32; flags::Int32
     blend::Float64
+    sub_frames::Ptr{Float64}; sub_jac::Ptr{Float64}
 end
 
 fluxkind(::StdAverage) = Int32(0)
@@ -139,7 +140,8 @@ function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,R
             Int32(length(bcs)), pointer(kinds), pointer(offsets), pointer(bcfaces),
             pointer(state), pointer(table),
             Int64(0), Int64(ne), Int32(0), Int32(1), C_NULL, Int32(device), Int32(0),
-            op isa HybridDivOperator ? Float64(op.blend) : 0.0)
+            op isa HybridDivOperator ? Float64(op.blend) : 0.0,
+            C_NULL, C_NULL)   # sub-grid tables of curved meshes: geometry.subgrids re-laid by line (see disc.py); Cartesian here
         check(ccall((:flou_b200_create, lib), Int32, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle))
     end
     b = B200Disc{ND,RT,typeof(disc)}(disc, handle[])

@@ -49,11 +49,13 @@ extern "C" {
 /* divergence operators: src/FlouSpatial/Equations/OpDivergence.jl:105 (Strong), :184 (Split) */
 #define FLOU_B200_OP_STRONG 0
 /* SplitDivOperator: on nodes with boundaries (GLL) any geometry; on Gauss nodes the entropy-
- * projected surface term (OpDivergence.jl:300-437) for the Euler equations on Cartesian meshes */
+ * projected surface term (OpDivergence.jl:300-437) for the Euler equations (general geometry
+ * needs the sub_frames / sub_jac tables) */
 #define FLOU_B200_OP_SPLIT  1
 /* HybridDivOperator(tpflux, numflux, blend) (OpDivergence.jl:452-477, volume term :557-612):
  * telescopic split form blended with sub-cell finite-volume fluxes (fvflux = numflux, as both
- * convenience constructors set it).  Euler, GLL nodes, Cartesian sub-grids. */
+ * convenience constructors set it).  Euler, GLL nodes; Cartesian sub-grids or, with the
+ * sub_frames / sub_jac tables, unstructured elements. */
 #define FLOU_B200_OP_HYBRID 2
 
 /* numerical-flux structs: src/FlouSpatial/Interfaces.jl:16-23,
@@ -143,6 +145,13 @@ typedef struct flou_b200_desc {
     int32_t device;           /* CUDA device ordinal                                         */
     int32_t flags;            /* FLOU_B200_FLAG_* */
     double blend;             /* HybridDivOperator.blend (OpDivergence.jl:464)               */
+    /* GEOM_GENERAL with HybridDivOperator or SplitDivOperator on Gauss nodes (NULL otherwise):
+     * geometry.subgrids (PhysicalRegions.jl:179-292) by GLOBAL element, direction, tensor-product
+     * line and position along the line (np+1 sub-cell interfaces, tpdofs_subgrid order):
+     *   sub_frames[((((e*nd + d)*nlines + k)*(np+1) + ii)*3 + r)*nd + c], r = n, t, b
+     *   sub_jac   [ ((e*nd + d)*nlines + k)*(np+1) + ii]                                          */
+    const double *sub_frames;
+    const double *sub_jac;
 } flou_b200_desc;
 
 #define FLOU_B200_FLAG_NO_GRAPH 1  /* launch stages directly instead of replaying a CUDA graph */

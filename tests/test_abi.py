@@ -81,11 +81,11 @@ def test_supported_matrix():
     assert not lib.flou_b200_supported(3, 9, L.EQ_EULER, L.OP_STRONG, 0, 0)
     assert not lib.flou_b200_supported(4, 4, L.EQ_EULER, L.OP_STRONG, 0, 0)
     assert not lib.flou_b200_supported(2, 4, L.EQ_LINEAR_ADVECTION, L.OP_SPLIT, L.FLUX_CHANDRASEKHAR, 0)
-    # HybridDivOperator (row f2): Euler on Cartesian sub-grids, either two-point flux
+    # HybridDivOperator (row f2): Euler, either two-point flux, Cartesian or general sub-grids
     for nd in (1, 2, 3):
         for tp in (L.FLUX_STDAVERAGE, L.FLUX_CHANDRASEKHAR):
             assert lib.flou_b200_supported(nd, 4, L.EQ_EULER, L.OP_HYBRID, tp, L.GEOM_CARTESIAN)
-    assert not lib.flou_b200_supported(2, 4, L.EQ_EULER, L.OP_HYBRID, L.FLUX_CHANDRASEKHAR, L.GEOM_GENERAL)
+    assert lib.flou_b200_supported(2, 4, L.EQ_EULER, L.OP_HYBRID, L.FLUX_CHANDRASEKHAR, L.GEOM_GENERAL)
     assert not lib.flou_b200_supported(2, 4, L.EQ_LINEAR_ADVECTION, L.OP_HYBRID, L.FLUX_STDAVERAGE, 0)
     assert not lib.flou_b200_supported(2, 4, L.EQ_EULER, L.OP_HYBRID, L.FLUX_LXF, 0)
 

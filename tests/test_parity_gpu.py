@@ -205,6 +205,10 @@ GAUSS_SPLIT_CASES = [
     Case(3, (2, 2, 2), 4, nodes="GL", op="split", tp="std", nf="sca", avg="cha"),
     Case(2, (4, 3), 4, nodes="GL", op="split", nf="mat", avg="cha", periodic=[("3", "4")],
          bcs={"1": ("inflow", [1.1, 0.33, 0.02, 2.6]), "2": ("outflow", None)}),
+    # curved sub-grids (PhysicalRegions.jl:179-292): vertex-perturbed meshes
+    Case(2, (4, 3), 4, nodes="GL", op="split", nf="mat", avg="cha", perturb_amp=0.08),
+    Case(2, (3, 3), 5, nodes="GL", op="split", tp="std", nf="lxf", avg="std", perturb_amp=0.1),
+    Case(3, (2, 2, 2), 3, nodes="GL", op="split", nf="mat", avg="cha", perturb_amp=0.06),
 ]
 
 
@@ -234,9 +238,9 @@ def test_gauss_node_split_form_matches_oracle(gpu, case, state):
 @pytest.mark.gpu
 def test_gauss_node_split_form_unsupported_combinations_raise(gpu):
     with pytest.raises(ValueError):
-        Case(2, (3, 3), 4, nodes="GL", op="split", perturb_amp=0.05).product()     # curved sub-grids
-    with pytest.raises(ValueError):
         Case(2, (3, 3), 4, nodes="GL", op="split").product(kernel="fused")
+    with pytest.raises(ValueError):
+        Case(2, (3, 3), 4, nodes="GL", op="split").product(kernel="node")
 
 
 # ------------------------------------------------------------------ row f2: HybridDivOperator
@@ -249,6 +253,10 @@ HYBRID_CASES = [
     Case(3, (2, 3, 2), 3, op="hybrid", tp="std", nf="cha", avg="cha", blend=0.2),
     Case(2, (5, 4), 4, op="hybrid", nf="mat", avg="cha", blend=1.0, periodic=[("3", "4")],
          bcs={"1": ("inflow", [1.1, 0.33, 0.02, 2.6]), "2": ("outflow", None)}),
+    # curved sub-grids (PhysicalRegions.jl:179-292): vertex-perturbed meshes
+    Case(2, (4, 3), 4, op="hybrid", nf="mat", avg="cha", blend=0.3, perturb_amp=0.08),
+    Case(2, (3, 4), 5, op="hybrid", tp="std", nf="lxf", avg="std", blend=1.0, perturb_amp=0.1),
+    Case(3, (2, 2, 2), 3, op="hybrid", nf="mat", avg="cha", blend=0.5, perturb_amp=0.06),
 ]
 
 
@@ -309,13 +317,11 @@ def test_shockwave_2d_kat_on_gpu(gpu):
 
 @pytest.mark.gpu
 def test_hybrid_unsupported_combinations_raise(gpu):
-    """No silent fallback: Gauss nodes, advection, curved sub-grids and the fused / node kernels
-    are refused for the hybrid operator."""
+    """No silent fallback: Gauss nodes and the fused / node kernels are refused for the hybrid
+    operator."""
     import flou_b200 as F
     with pytest.raises(ValueError):
         Case(2, (3, 3), 4, nodes="GL", op="hybrid").product()
-    with pytest.raises(ValueError):
-        Case(2, (3, 3), 4, op="hybrid", perturb_amp=0.05).product()
     with pytest.raises(ValueError):
         Case(2, (3, 3), 4, op="hybrid").product(kernel="fused")
 
