@@ -97,6 +97,27 @@ function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,R
     metric = cart ? Float64[] : collect(reinterpret(Float64, geometry.elements.metric))
     fjac = cart ? Float64[] : geometry.faces.jac
     frames = cart ? Float64[] : collect(reinterpret(Float64, geometry.faces.frames))
+    # geometry.subgrids (PhysicalRegions.jl:179-292) re-laid by (element, direction, tensor-product
+    # line, position along the line) for the hybrid operator / the Gauss-node split form on
+    # unstructured meshes: frames rows n, t, b (C order), then the sub-cell face Jacobians
+    needs_sub = !cart && Flou.FlouSpatial.requires_subgrid(op, std)
+    np1 = size(D, 1) + 1
+    nlines = ND == 1 ? 1 : (ND == 2 ? size(D, 1) : size(D, 1)^2)
+    sub_frames = needs_sub ? zeros(Float64, ND, 3, np1, nlines, ND, nelements(mesh)) : Float64[]
+    sub_jac = needs_sub ? zeros(Float64, np1, nlines, ND, nelements(mesh)) : Float64[]
+    if needs_sub
+        dirs = ND == 1 ? (Val(1),) : (ND == 2 ? (Val(1), Val(2)) : (Val(1), Val(2), Val(3)))
+        for ie in 1:nelements(mesh), (dir, vdir) in enumerate(dirs)
+            sg = geometry.subgrids[ie]
+            for (k, sinds) in enumerate(Flou.FlouSpatial.tpdofs_subgrid(std, vdir)), (ii, is) in enumerate(sinds)
+                fr = sg.frames[dir][is]
+                sub_frames[:, 1, ii, k, dir, ie] .= fr.n
+                sub_frames[:, 2, ii, k, dir, ie] .= fr.t
+                sub_frames[:, 3, ii, k, dir, ie] .= fr.b
+                sub_jac[ii, k, dir, ie] = sg.jac[dir][is]
+            end
+        end
+    end
     # boundary conditions in mesh.bdfaces order (disc.bcs is already ordered by bdmap)
     kinds = Int32[bckind(bc) for bc in bcs]
     offsets = Int64[0; cumsum(length.(mesh.bdfaces))]
@@ -123,7 +144,7 @@ function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,R
         throw(ArgumentError("flou_b200: HybridDivOperator needs fvflux === numflux (both convenience constructors)"))
     end
     handle = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve faceinds facepos eleminds elempos orientation D Ds Dsharp lm lp dgm dgp w1d jac metric fjac frames kinds offsets bcfaces state table begin
+    GC.@preserve faceinds facepos eleminds elempos orientation D Ds Dsharp lm lp dgm dgp w1d jac metric fjac frames sub_frames sub_jac kinds offsets bcfaces state table begin
         desc = Desc(
             Int32(sizeof(Desc)), Int32(ND), Int32(nv), Int32(size(D, 1)),
             equation isa EulerEquation ? Int32(1) : Int32(0),
@@ -141,7 +162,7 @@ function B200Disc(disc::MultielementDisc{ND,RT}, equation; device=0) where {ND,R
             pointer(state), pointer(table),
             Int64(0), Int64(ne), Int32(0), Int32(1), C_NULL, Int32(device), Int32(0),
             op isa HybridDivOperator ? Float64(op.blend) : 0.0,
-            C_NULL, C_NULL)   # sub-grid tables of curved meshes: geometry.subgrids re-laid by line (see disc.py); Cartesian here
+            needs_sub ? pointer(sub_frames) : C_NULL, needs_sub ? pointer(sub_jac) : C_NULL)
         check(ccall((:flou_b200_create, lib), Int32, (Ref{Desc}, Ref{Ptr{Cvoid}}), desc, handle))
     end
     b = B200Disc{ND,RT,typeof(disc)}(disc, handle[])
