@@ -92,6 +92,21 @@ def test_rhs_on_synthetic_unstructured_mesh(gpu, synthetic_msh, npn, nf, avg, op
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("npn,op,nodes", [(5, "hybrid", "GLL"), (4, "split", "GL")])
+def test_subgrid_operators_on_synthetic_unstructured_mesh(gpu, synthetic_msh, npn, op, nodes):
+    """Hybrid operator and Gauss-node split form on the unstructured mesh (rotated element node
+    lists, both face orientations, slip walls / inflow / outflow): curved sub-grid frames from the
+    mapping (PhysicalRegions.jl:179-292) on every element."""
+    names = ["Bottom", "Right", "Top", "Left"]
+    orc, disc, eq = build_pair(synthetic_msh, npn, euler_bcs(names), nf="mat", avg="cha", op=op, nodes=nodes)
+    Q = random_state(orc.ndof, 2, "euler", amp=0.5 if nodes == "GLL" else 0.15)
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert relerr(dQ, orc.rhs(Q)) <= 1e-12
+    disc.close()
+
+
+@pytest.mark.gpu
 def test_config5_state_after_n_steps(gpu, synthetic_msh, tmp_path):
     """p=5 (np=6), EC split form + matrix dissipation, slip walls + inflow/outflow, refined 2x2."""
     import oracle as O

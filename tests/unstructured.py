@@ -50,7 +50,7 @@ def euler_bcs(names, inflow=("Left",), outflow=("Right",), Qinf=(1.0, 0.45, 0.05
 
 
 def build_pair(mshfile, npn, bcs, nf="mat", avg="cha", op="split", nodes="GLL", create=True,
-               refinement=1, rank=0, nranks=1):
+               refinement=1, rank=0, nranks=1, blend=0.5):
     import flou_b200 as F
     omesh = ogm.unstructured_mesh_2d(mshfile)
     obcs = {}
@@ -59,8 +59,10 @@ def build_pair(mshfile, npn, bcs, nf="mat", avg="cha", op="split", nodes="GLL", 
                       "outflow": (O.BC_OUTFLOW, None), "slip": (O.BC_SLIP, None)}[kind]
     FL = {"std": O.FLUX_STDAVG, "lxf": O.FLUX_LXF, "cha": O.FLUX_CHANDRASEKHAR,
           "sca": O.FLUX_SCALARDISS, "mat": O.FLUX_MATRIXDISS}
-    orc = O.Problem(omesh, nodes, npn, O.EQ_EULER, O.OP_STRONG if op == "strong" else O.OP_SPLIT,
-                    FL[nf], numflux_avg=FL[avg], intensity=1.0, gamma=1.4, bcs=obcs, cartesian=False)
+    orc = O.Problem(omesh, nodes, npn, O.EQ_EULER,
+                    {"strong": O.OP_STRONG, "split": O.OP_SPLIT, "hybrid": O.OP_HYBRID}[op],
+                    FL[nf], numflux_avg=FL[avg], intensity=1.0, gamma=1.4, bcs=obcs, cartesian=False,
+                    blend=blend if op == "hybrid" else 0.0)
     mesh = F.UnstructuredMesh(2, mshfile, refinement=refinement)
     eq = F.EulerEquation(2, 1.4)
     basis = F.LagrangeBasis(nodes, npn)
@@ -68,7 +70,8 @@ def build_pair(mshfile, npn, bcs, nf="mat", avg="cha", op="split", nodes="GLL", 
     a = {"std": F.StdAverage(), "cha": F.ChandrasekharAverage()}[avg]
     numflux = {"std": F.StdAverage(), "cha": F.ChandrasekharAverage(), "lxf": F.LxF(a, 1.0),
                "sca": F.ScalarDissipation(a, 1.0), "mat": F.MatrixDissipation(a, 1.0)}[nf]
-    oper = F.StrongDivOperator(numflux) if op == "strong" else F.SplitDivOperator(numflux)
+    oper = (F.StrongDivOperator(numflux) if op == "strong" else
+            F.HybridDivOperator(numflux, blend) if op == "hybrid" else F.SplitDivOperator(numflux))
     pb = {}
     for name, (kind, param) in bcs.items():
         pb[name] = {"inflow": lambda p=param: F.EulerInflowBC(p), "outflow": F.EulerOutflowBC,
