@@ -13,7 +13,7 @@ FLOU_PAIR_LIST
 
 const StageLauncher *get_stage_launcher(int nd, int np, int eq, int vol, int cart)
 {
-    if (eq < 0 || eq > 1 || vol < 0 || vol > 5) return nullptr;
+    if (eq < 0 || eq > 1 || vol < 0 || vol > 6) return nullptr;
 #define X(a, b) if (nd == a && np == b) return stage_table_##a##_##b(eq, vol, cart);
     FLOU_PAIR_LIST
 #undef X

@@ -689,10 +689,12 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         return fail(FLOU_B200_EINVAL, "HybridDivOperator on a general mesh: sub-grid tables (sub_frames, sub_jac) missing");
     }
     if (hybrid && !colloc) {
-        // the reference moves everything to the surface term on Gauss nodes
-        // (_hybrid_nb_surface_contribution!, OpDivergence.jl:647-779): not on this path
-        flou_b200_destroy(h);
-        return fail(FLOU_B200_EUNSUPPORTED, "HybridDivOperator needs nodes with boundaries (GLL)");
+        // nodes without boundaries: everything is a surface contribution
+        // (_hybrid_nb_surface_contribution!, OpDivergence.jl:629-779): instances of dispatch index 6,
+        // which use D# (the GLL form uses D)
+        h->stage = get_stage_launcher(nd, np, d->equation, 6, cart);
+        if (!h->stage) { flou_b200_destroy(h); return fail(FLOU_B200_EUNSUPPORTED, "no kernel compiled for this (nd, np)"); }
+        for (int i = 0; i < np * np; i++) P.Dvol[i] = d->Dsharp[i];
     }
     if (colloc) {
         // GLL: l(-1) = e_1 and l(+1) = e_np up to the reference's monomial round-off

@@ -219,11 +219,13 @@ struct NBCfg : KCfg<ND_, NP_, EQ_, VOL_, CART_> {
 #define ND FLOU_ND
 #define NP FLOU_NP
 
-// [eq][vol][cart]; vol 4 / 5 = split form (StdAverage / Chandrasekhar) on nodes without boundaries
-static const StageLauncher table[2][6][2] = {
+// [eq][vol][cart]; vol 4 / 5 = split form (StdAverage / Chandrasekhar), 6 = hybrid operator on nodes
+// without boundaries
+static const StageLauncher table[2][7][2] = {
     {   // linear advection: strong, split (StdAverage two-point flux); no Chandrasekhar
         {make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, true>>()},
+        {StageLauncher{}, StageLauncher{}},
         {StageLauncher{}, StageLauncher{}},
         {StageLauncher{}, StageLauncher{}},
         {StageLauncher{}, StageLauncher{}},
@@ -238,6 +240,7 @@ static const StageLauncher table[2][6][2] = {
         // split form on Gauss nodes
         {make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, false>>(), make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, true>>()},
         {make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, false>>(), make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
+        {make_lines<NBCfg<ND, NP, EQ_EULER, VOL_HYBRID, false>>(), make_lines<NBCfg<ND, NP, EQ_EULER, VOL_HYBRID, true>>()},
     },
 };
 

@@ -437,6 +437,172 @@ __device__ __forceinline__ void hybrid_line(const KParams &P, const double (&Q)[
     }
 }
 
+// HybridDivOperator on nodes WITHOUT boundaries (Gauss), one line in direction D: everything is a
+// surface contribution (_hybrid_nb_surface_contribution!, OpDivergence.jl:629-779):
+//   F#            diagonal = contravariant flux of the node, off-diagonal = two-point fluxes
+//   Fl_i, Fr_i    two-point fluxes against the entropy-projected end states, minus l'Fl + Fn_left
+//                 and r'Fr - Fn_right (_flux_splitdiv_nb_tensorproduct!)
+//   Fbar[0] = -Fn_left, Fbar[NP] = Fn_right,
+//   Fbar[ii+1] = Fbar[ii] + w_ii (D# F#)_ii - l_ii Fl_ii + r_ii Fr_ii,  blended with the FV flux of
+//                interface ii+1 (the blended value feeds the next step of the recursion),
+//   dQ_ii += (Fbar[ii] - Fbar[ii+1]) / w_ii
+// fnl / fnr: the element-side face fluxes of this line (sign applied).  Dvol = D# here.
+template <class C, int D>
+__device__ __forceinline__ void hybrid_nb_line(const KParams &P, const double (&Q)[C::NP][C::NV],
+                                               const double (&fnl)[C::NV], const double (&fnr)[C::NV],
+                                               int64_t gnode0, int stride, int64_t sub0,
+                                               double (&acc)[C::NP][C::NV])
+{
+    constexpr int ND = C::ND, NP = C::NP, NV = C::NV, EQ = C::EQ;
+    constexpr bool CART = C::CART;
+    const double g = P.fp.gamma;
+    double rho[NP], vel[NP][ND], pr[NP], W[NP][NV], mt[NP][ND], nend[2][ND], Wp[2][NV];
+#pragma unroll
+    for (int j = 0; j < NP; j++)
+#pragma unroll
+        for (int c = 0; c < ND; c++)
+            mt[j][c] = CART ? ((c == D) ? P.cmet[D] : 0.0) : __ldg(P.metric + gnode0 + j * stride + P.ndof * (c + ND * D));
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+#pragma unroll
+        for (int c = 0; c < ND; c++) {
+            if (CART) nend[e][c] = (c == D) ? P.cmet[D] : 0.0;
+            else {
+                const int64_t si = sub0 + (e ? NP : 0);
+                nend[e][c] = __ldg(P.sub_frames + si * (3 * ND) + c) * __ldg(P.sub_jac + si);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) Wp[e][v] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        NodeAux<ND> A;
+        node_aux<ND>(Q[j], g, A);
+        rho[j] = Q[j][0]; pr[j] = A.p;
+        double m2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < ND; c++) { vel[j][c] = A.vel[c]; m2 += Q[j][1 + c] * Q[j][1 + c]; }
+        const double s = log(A.p) - g * log(Q[j][0]);
+        W[j][0] = (g - s) / (g - 1.0) - m2 / Q[j][0] / (2.0 * A.p);
+#pragma unroll
+        for (int c = 0; c < ND; c++) W[j][1 + c] = Q[j][1 + c] / A.p;
+        W[j][ND + 1] = -Q[j][0] / A.p;
+#pragma unroll
+        for (int v = 0; v < NV; v++) { Wp[0][v] = fma(P.lm[j], W[j][v], Wp[0][v]); Wp[1][v] = fma(P.lp[j], W[j][v], Wp[1][v]); }
+    }
+    // two-point flux of two states given as (rho, vel, p), contracted with n
+    auto tp = [&](double r1, const double *v1, double p1, double r2, const double *v2, double p2,
+                  const double *n, double *F) {
+        if (P.tpflux == FX_CHA) {
+            double h1[ND], h2[ND], q1 = 0.0, q2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < ND; c++) { h1[c] = 0.5 * v1[c]; h2[c] = 0.5 * v2[c]; q1 += v1[c] * v1[c]; q2 += v2[c] * v2[c]; }
+            tp_chandrasekhar<ND>(r1, h1, q1, r1 / (2.0 * p1), r2, h2, q2, r2 / (2.0 * p2), P.fp.inv_gm1, n, F);
+        } else {
+            double Q1[NV], Q2[NV], q1 = 0.0, q2 = 0.0;
+            Q1[0] = r1; Q2[0] = r2;
+#pragma unroll
+            for (int c = 0; c < ND; c++) { Q1[1 + c] = r1 * v1[c]; Q2[1 + c] = r2 * v2[c]; q1 += v1[c] * v1[c]; q2 += v2[c] * v2[c]; }
+            Q1[ND + 1] = p1 * P.fp.inv_gm1 + 0.5 * r1 * q1;
+            Q2[ND + 1] = p2 * P.fp.inv_gm1 + 0.5 * r2 * q2;
+            tp_stdavg<ND>(Q1, v1, p1, Q2, v2, p2, n, F);
+        }
+    };
+    // entropy-projected end states: vars_entropy2prim (FlouCommon/Euler.jl:309-334)
+    double re[2], ve[2][ND], pe[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        double q = 0.0;
+#pragma unroll
+        for (int c = 0; c < ND; c++) { ve[e][c] = -Wp[e][1 + c] / Wp[e][ND + 1]; q += ve[e][c] * ve[e][c]; }
+        const double s = g - (g - 1.0) * (Wp[e][0] - Wp[e][ND + 1] * q / 2.0);
+        pe[e] = pow(pow(-Wp[e][ND + 1], g) * exp(s), 1.0 / (1.0 - g));
+        re[e] = -pe[e] * Wp[e][ND + 1];
+    }
+    // (D# F#)_ii for the first NP-1 nodes, and Fl, Fr
+    double DF[NP][NV], Fl[NP][NV], Fr[NP][NV], lFl[NV], rFr[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) { lFl[v] = 0.0; rFr[v] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        double Fc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) DF[i][v] = 0.0;
+        // diagonal: contravariant flux of node i (volumeflux contracted with Ja_i[:, D])
+#pragma unroll
+        for (int c = 0; c < ND; c++) {
+            if (CART && c != D) continue;
+            euler_flux_dir<ND>(Q[i], vel[i], pr[i], c, Fc);
+            const double dii = P.Dvol[i + NP * i] * mt[i][c];
+#pragma unroll
+            for (int v = 0; v < NV; v++) DF[i][v] = fma(dii, Fc[v], DF[i][v]);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            double n[ND];
+#pragma unroll
+            for (int c = 0; c < ND; c++) n[c] = 0.5 * (mt[i][c] + nend[e][c]);
+            tp(rho[i], vel[i], pr[i], re[e], ve[e], pe[e], n, e ? Fr[i] : Fl[i]);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) { lFl[v] = fma(P.lm[i], Fl[i][v], lFl[v]); rFr[v] = fma(P.lp[i], Fr[i][v], rFr[v]); }
+    }
+#pragma unroll
+    for (int i = 0; i < NP - 1; i++)
+#pragma unroll
+        for (int l = i + 1; l < NP; l++) {
+            double n[ND], F[NV];
+#pragma unroll
+            for (int c = 0; c < ND; c++) n[c] = 0.5 * (mt[i][c] + mt[l][c]);
+            tp(rho[i], vel[i], pr[i], rho[l], vel[l], pr[l], n, F);
+            const double dil = P.Dvol[i + NP * l], dli = P.Dvol[l + NP * i];
+#pragma unroll
+            for (int v = 0; v < NV; v++) { DF[i][v] = fma(dil, F[v], DF[i][v]); DF[l][v] = fma(dli, F[v], DF[l][v]); }
+        }
+    double Fb[NP + 1][NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) { Fb[0][v] = -fnl[v]; Fb[NP][v] = fnr[v]; }
+#pragma unroll
+    for (int ii = 0; ii < NP - 1; ii++) {
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+            Fb[ii + 1][v] = Fb[ii][v] + DF[ii][v] * P.w1d[ii] - P.lm[ii] * (Fl[ii][v] - (lFl[v] + fnl[v]))
+                          + P.lp[ii] * (Fr[ii][v] - (rFr[v] - fnr[v]));
+        double Rl[NV], Rr[NV], Fn[NV], Fv[NV], jsi = P.cmet[CART ? D : 0];
+        if (CART) {
+            rot2face_c<ND, EQ, 2 * D + 1>(Q[ii], Rl);
+            rot2face_c<ND, EQ, 2 * D + 1>(Q[ii + 1], Rr);
+            euler_numflux<ND>(P.fp, Rl, Rr, Fn);
+            rot2phys_c<ND, EQ, 2 * D + 1>(Fn, Fv);
+        } else {
+            double fr[3 * ND];
+#pragma unroll
+            for (int c = 0; c < 3 * ND; c++) fr[c] = (c < ND * ND || ND == 3) ? __ldg(P.sub_frames + (sub0 + ii + 1) * (3 * ND) + c) : 0.0;
+            jsi = __ldg(P.sub_jac + sub0 + ii + 1);
+            rotate2face<ND, EQ>(Q[ii], fr, Rl);
+            rotate2face<ND, EQ>(Q[ii + 1], fr, Rr);
+            euler_numflux<ND>(P.fp, Rl, Rr, Fn);
+            rotate2phys<ND, EQ>(Fn, fr, Fv);
+        }
+        double b = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            Fv[v] *= jsi;
+            b += (W[ii + 1][v] - W[ii][v]) * (Fb[ii + 1][v] - Fv[v]);
+        }
+        double delta = sqrt(b * b + P.blend);
+        delta = (delta - b) / delta;
+        delta = fmax(delta, 0.5);
+#pragma unroll
+        for (int v = 0; v < NV; v++) Fb[ii + 1][v] = (1.0 - delta) * Fv[v] + delta * Fb[ii + 1][v];
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++)
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[j][v] = (Fb[j][v] - Fb[j + 1][v]) / P.w1d[j];
+}
+
 // Surface term of the split form on nodes WITHOUT boundaries, one line
 // (_flux_splitdiv_nb_tensorproduct! + _surf_splitdiv_nb_tensorproduct!, OpDivergence.jl:389-437):
 //   W_i = vars_cons2entropy(Q_i);  Q(l) = vars_entropy2cons(l' W),  Q(r) = vars_entropy2cons(r' W)
@@ -600,9 +766,21 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
             // global node of the line's first node and the line's slot in the sub-grid tables
             const int64_t gnode0 = dof0 + base;
             const int64_t sub0 = (((dof0 / NPTS + el) * ND + d) * NFP + k) * (NP + 1);
+            if constexpr (C::NB) {
+                // nodes without boundaries: the face fluxes enter the sub-cell recursion itself
+                cp_async_wait<0>();
+                double fnl[NV], fnr[NV];
+                const double sl = sF[(2 * NV) * LT + task], sr = sF[(2 * NV + 1) * LT + task];
+#pragma unroll
+                for (int v = 0; v < NV; v++) { fnl[v] = sl * sF[v * LT + task]; fnr[v] = sr * sF[(NV + v) * LT + task]; }
+                if (d == 0) hybrid_nb_line<C, 0>(P, Qj, fnl, fnr, gnode0, stride, sub0, acc);
+                else if (ND >= 2 && d == 1) hybrid_nb_line<C, (ND >= 2 ? 1 : 0)>(P, Qj, fnl, fnr, gnode0, stride, sub0, acc);
+                else if (ND >= 3) hybrid_nb_line<C, (ND >= 3 ? 2 : 0)>(P, Qj, fnl, fnr, gnode0, stride, sub0, acc);
+            } else {
             if (d == 0) hybrid_line<C, 0>(P, Qj, gnode0, stride, sub0, acc);
             else if (ND >= 2 && d == 1) hybrid_line<C, (ND >= 2 ? 1 : 0)>(P, Qj, gnode0, stride, sub0, acc);
             else if (ND >= 3) hybrid_line<C, (ND >= 3 ? 2 : 0)>(P, Qj, gnode0, stride, sub0, acc);
+            }
         } else if (!SPLIT) {
             // strong form: dQ[line] -= Ds * F~[line, d]
 #pragma unroll
@@ -705,6 +883,8 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
                     acc[0][v] = fma(-w0, sF[v * LT + task], acc[0][v]);
                     acc[NP - 1][v] = fma(-w1, sF[(NV + v) * LT + task], acc[NP - 1][v]);
                 }
+            } else if (C::HYBRID) {
+                // hybrid operator on nodes without boundaries: hybrid_nb_line consumed the face fluxes
             } else if (SPLIT && EQ == EQ_EULER) {
                 // split form on nodes without boundaries (Gauss): the surface term couples every
                 // node of the line with the entropy-projected end states

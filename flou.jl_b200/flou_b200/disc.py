@@ -45,9 +45,6 @@ class MultielementDisc:
         if op.kind == L.OP_HYBRID:
             if equation.kind != L.EQ_EULER:
                 raise ValueError("HybridDivOperator needs entropy variables: Euler equations only")
-            if not std.basis.hasboundaries:
-                raise ValueError("HybridDivOperator on Gauss nodes (the reference's all-surface path, "
-                                 "OpDivergence.jl:647-779) is not on the B200 hot path")
         nd, npn, nv = mesh.nd, std.np, equation.nv
         self.nd, self.np, self.nv = nd, npn, nv
         self.npts, self.nfp = npn ** nd, npn ** (nd - 1)
@@ -80,7 +77,7 @@ class MultielementDisc:
             jac, metric = G.general_element_geometry(self._verts, std.xi)
             _, fjac, frames = self._face_geometry()
             keep.update(jac=jac, metric=metric, fjac=fjac, frames=frames)
-            if op.kind == L.OP_HYBRID or (op.kind == L.OP_SPLIT and not std.basis.hasboundaries):
+            if op.kind == L.OP_HYBRID or (op.kind == L.OP_SPLIT and not std.basis.hasboundaries):   # incl. hybrid on Gauss nodes
                 # requires_subgrid(op, std): geometry.subgrids (PhysicalRegions.jl:179-292)
                 sfr, sjac = G.general_subgrid_geometry(self._verts, std.xi1d, std.w1d)
                 keep.update(sub_frames=sfr, sub_jac=sjac)

@@ -54,8 +54,9 @@ extern "C" {
 #define FLOU_B200_OP_SPLIT  1
 /* HybridDivOperator(tpflux, numflux, blend) (OpDivergence.jl:452-477, volume term :557-612):
  * telescopic split form blended with sub-cell finite-volume fluxes (fvflux = numflux, as both
- * convenience constructors set it).  Euler, GLL nodes; Cartesian sub-grids or, with the
- * sub_frames / sub_jac tables, unstructured elements. */
+ * convenience constructors set it).  Euler; GLL nodes (volume form) or Gauss nodes (all-surface
+ * form, :629-779); Cartesian sub-grids or, with the sub_frames / sub_jac tables, unstructured
+ * elements. */
 #define FLOU_B200_OP_HYBRID 2
 
 /* numerical-flux structs: src/FlouSpatial/Interfaces.jl:16-23,

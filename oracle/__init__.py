@@ -197,8 +197,8 @@ class Problem:
         if split_nb and equation != EQ_EULER:
             raise ValueError("the split form on Gauss nodes (entropy-projected surface term) needs the "
                              "Euler equations")
-        if op == OP_HYBRID and not self.ops["hasboundaries"]:
-            raise ValueError("the oracle's HybridDivOperator covers nodes with boundaries (GLL)")
+        if op == OP_HYBRID and equation != EQ_EULER:
+            raise ValueError("HybridDivOperator needs entropy variables: Euler equations only")
         if op == OP_HYBRID or split_nb:
             # geometry.subgrids (PhysicalRegions.jl:28-292): Cartesian constants or, on general
             # meshes, frames / Jacobians from the mapping at the complementary-grid points

@@ -13,6 +13,8 @@
  *   SplitDivOperator         OpDivergence.jl:184-299
  *   SplitDivOperator, nodes  OpDivergence.jl:284-437 (_splitdiv_nb_surface_contribution!: Gauss
  *     without boundaries     nodes, entropy-projected end states; Cartesian sub-grid frames)
+ *   HybridDivOperator, nodes OpDivergence.jl:629-779 (_hybrid_nb_surface_contribution!: everything
+ *     without boundaries     as a surface contribution)
  *   HybridDivOperator        OpDivergence.jl:452-612, 781-801 (GLL nodes, Cartesian sub-grid
  *                            frames PhysicalRegions.jl:72-148); ORACLE ONLY -- it exists to
  *                            pin the 2-D machinery against the reference's Shockwave2D KAT
@@ -605,8 +607,9 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
                             }
                     }
                 } else if (P->op == OP_HYBRID) {
-                    /* _vol_hybrid_tensorproduct!   OpDivergence.jl:554-612 (fvflux = numflux) */
-                    for (int k = 0; k < nlines; k++) {
+                    /* _vol_hybrid_tensorproduct!   OpDivergence.jl:554-612 (fvflux = numflux); on
+                     * nodes without boundaries everything is a surface contribution (:478-492) */
+                    for (int k = 0; k < nlines && P->hasboundaries; k++) {
                         int base, stride;
                         line_of(nd, np, d, k, &base, &stride);
                         double Fb[MAXNP + 1][MAXV];
@@ -755,6 +758,7 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
     /* surface_contribution!   OpDivergence.jl:42-100; split form on nodes without boundaries:
      * _splitdiv_nb_surface_contribution!   OpDivergence.jl:300-437 */
     const int split_nb = (P->op == OP_SPLIT && !P->hasboundaries);
+    const int hybrid_nb = (P->op == OP_HYBRID && !P->hasboundaries);
     #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < ne; e++) {
         const int64_t *faces = P->faceinds + e * 2 * nd, *sides = P->facepos + e * 2 * nd;
@@ -798,7 +802,83 @@ void oracle_rhs(const oracle_problem *P, const double *Q, double *dQ, double tim
                         dQ[e * npts + base + ii * stride + ndof * v] += P->dgl[ii] * a - P->dgr[ii] * b;
                     }
             }
-            for (int k = 0; k < nlines && !split_nb; k++) {
+            for (int k = 0; k < nlines && hybrid_nb; k++) {
+                /* _hybrid_nb_surface_contribution!   OpDivergence.jl:629-779 for one row:
+                 * _flux_splitdiv_tensorproduct! (F#), _flux_splitdiv_nb_tensorproduct! (Fl, Fr),
+                 * _surf_hybrid_nb_tensorproduct! (sub-cell fluxes, FV blending, differencing) */
+                int base, stride;
+                line_of(nd, np, d, k, &base, &stride);
+                const double *Ja = P->metric + (int64_t)e * npts * nd * nd;
+                const int64_t sg0 = (((int64_t)e * nd + d) * nlines + k) * (np + 1);
+                double nl[3] = {0, 0, 0}, nr[3] = {0, 0, 0}, Wl[MAXV], Wr[MAXV], Qa[MAXV], Qb[MAXV];
+                double Qn[MAXNP][MAXV], Wn[MAXNP][MAXV], Fsh[MAXNP][MAXNP][MAXV];
+                double Fl[MAXNP][MAXV], Fr[MAXNP][MAXV], lFl[MAXV], rFr[MAXV], Fb[MAXNP + 1][MAXV];
+                for (int c = 0; c < nd; c++) {
+                    nl[c] = P->sub_frames[sg0 * 3 * nd + c] * P->sub_fjac[sg0];
+                    nr[c] = P->sub_frames[(sg0 + np) * 3 * nd + c] * P->sub_fjac[sg0 + np];
+                }
+                for (int v = 0; v < nv; v++) { Wl[v] = 0; Wr[v] = 0; lFl[v] = 0; rFr[v] = 0; }
+                for (int ii = 0; ii < np; ii++) {
+                    for (int v = 0; v < nv; v++) Qn[ii][v] = Q[e * npts + base + ii * stride + ndof * v];
+                    cons2entropy(Qn[ii], nd, P->gamma, Wn[ii]);
+                    for (int v = 0; v < nv; v++) { Wl[v] += P->lm[ii] * Wn[ii][v]; Wr[v] += P->lp[ii] * Wn[ii][v]; }
+                }
+                /* F#: diagonal = contravariant flux, off-diagonal = two-point flux (symmetric) */
+                for (int ii = 0; ii < np; ii++) {
+                    int i = base + ii * stride;
+                    double F[3][MAXV];
+                    volumeflux(P, Qn[ii], F);
+                    const double *M = Ja + i * nd * nd;
+                    for (int v = 0; v < nv; v++) {
+                        double t = F[0][v] * M[0 + nd * d];
+                        for (int c = 1; c < nd; c++) t += F[c][v] * M[c + nd * d];
+                        Fsh[ii][ii][v] = t;
+                    }
+                    for (int il = ii + 1; il < np; il++) {
+                        int l = base + il * stride;
+                        double F2[MAXV];
+                        twopointflux(P, Qn[ii], Qn[il], Ja + i * nd * nd + nd * d, Ja + l * nd * nd + nd * d, F2);
+                        for (int v = 0; v < nv; v++) { Fsh[ii][il][v] = F2[v]; Fsh[il][ii][v] = F2[v]; }
+                    }
+                }
+                entropy2cons(Wl, nd, P->gamma, Qa);
+                entropy2cons(Wr, nd, P->gamma, Qb);
+                for (int ii = 0; ii < np; ii++) {
+                    int i = base + ii * stride;
+                    twopointflux(P, Qn[ii], Qa, Ja + i * nd * nd + nd * d, nl, Fl[ii]);
+                    twopointflux(P, Qn[ii], Qb, Ja + i * nd * nd + nd * d, nr, Fr[ii]);
+                    for (int v = 0; v < nv; v++) { lFl[v] += P->lm[ii] * Fl[ii][v]; rFr[v] += P->lp[ii] * Fr[ii][v]; }
+                }
+                for (int ii = 0; ii < np; ii++)
+                    for (int v = 0; v < nv; v++) {
+                        Fl[ii][v] -= lFl[v] + FL[fl + k + nfd * v];
+                        Fr[ii][v] -= rFr[v] - FR[fr + k + nfd * v];
+                    }
+                for (int v = 0; v < nv; v++) { Fb[0][v] = -FL[fl + k + nfd * v]; Fb[np][v] = FR[fr + k + nfd * v]; }
+                for (int ii = 0; ii < np - 1; ii++) {
+                    for (int v = 0; v < nv; v++) {
+                        double t = 0;
+                        for (int jj = 0; jj < np; jj++) t += P->Dsharp[ii + np * jj] * Fsh[jj][ii][v];
+                        Fb[ii + 1][v] = Fb[ii][v] + t * P->w1d[ii] - P->lm[ii] * Fl[ii][v] + P->lp[ii] * Fr[ii][v];
+                    }
+                    const double *fr_ = P->sub_frames + (sg0 + ii + 1) * 3 * nd;
+                    double Qln[MAXV], Qrn[MAXV], Fn_[MAXV], Fv[MAXV], b = 0;
+                    rotate2face(P, Qn[ii], fr_, Qln);
+                    rotate2face(P, Qn[ii + 1], fr_, Qrn);
+                    numericalflux(P, Qln, Qrn, fr_, Fn_);
+                    rotate2phys(P, Fn_, fr_, Fv);
+                    for (int v = 0; v < nv; v++) Fv[v] *= P->sub_fjac[sg0 + ii + 1];
+                    for (int v = 0; v < nv; v++) b += (Wn[ii + 1][v] - Wn[ii][v]) * (Fb[ii + 1][v] - Fv[v]);
+                    double delta = sqrt(b * b + P->blend);
+                    delta = (delta - b) / delta;
+                    delta = fmax(delta, 0.5);
+                    for (int v = 0; v < nv; v++) Fb[ii + 1][v] = (1 - delta) * Fv[v] + delta * Fb[ii + 1][v];
+                }
+                for (int ii = 0; ii < np; ii++)
+                    for (int v = 0; v < nv; v++)
+                        dQ[e * npts + base + ii * stride + ndof * v] += (Fb[ii][v] - Fb[ii + 1][v]) / P->w1d[ii];
+            }
+            for (int k = 0; k < nlines && !split_nb && !hybrid_nb; k++) {
                 int base, stride;
                 line_of(nd, np, d, k, &base, &stride);
                 for (int ii = 0; ii < np; ii++)

@@ -126,7 +126,7 @@ def test_coords_follow_the_reference_node_order():
 
 def test_hybrid_operator_constructors_and_descriptor():
     """HybridDivOperator([tpflux], numflux, blend) (OpDivergence.jl:452-477): tpflux defaults to
-    numflux.avg, fvflux = numflux; refused on Gauss nodes and for linear advection."""
+    numflux.avg, fvflux = numflux; refused for linear advection."""
     nf = F.MatrixDissipation(F.ChandrasekharAverage(), 1.0)
     op = F.HybridDivOperator(nf, 0.25)
     assert isinstance(op.tpflux, F.ChandrasekharAverage) and op.fvflux is nf and op.numflux is nf
@@ -140,7 +140,6 @@ def test_hybrid_operator_constructors_and_descriptor():
     d = F.MultielementDisc(mesh, _std(2), eq, op, {}, create=False)._desc
     assert (d.divop, d.tpflux, d.numflux, d.blend) == (
         L.OP_HYBRID, L.FLUX_CHANDRASEKHAR, L.FLUX_MATRIXDISSIPATION, 0.25)
-    with pytest.raises(ValueError):
-        F.MultielementDisc(mesh, _std(2, nodes="GL"), eq, op, {}, create=False)
+    F.MultielementDisc(mesh, _std(2, nodes="GL"), eq, op, {}, create=False)      # Gauss nodes: all-surface form
     with pytest.raises(ValueError):
         F.MultielementDisc(mesh, _std(2, nv=1), F.LinearAdvection(1.0, 1.0), op, {}, create=False)

@@ -370,3 +370,23 @@ def test_curved_mesh_free_stream_and_conservation(nd, n, npn, which):
         assert abs(_integral(orc, dQ[:, v])) < 1e-12 * _integral(orc, np.abs(dQ[:, v])) + 1e-13
     Qc = np.asfortranarray(np.tile(Q[:1], (orc.ndof, 1)))
     assert np.max(np.abs(orc.rhs(Qc))) < 1e-10
+
+
+# ------------------------------------------------------------------ HybridDivOperator on Gauss nodes
+@pytest.mark.parametrize("nd,n,npn", [(1, (8,), 4), (2, (4, 3), 4), (3, (2, 2, 2), 3)])
+def test_hybrid_on_gauss_nodes_tends_to_the_gauss_split_form(nd, n, npn):
+    """_hybrid_nb_surface_contribution! (OpDivergence.jl:629-779): with delta = 1 (blend -> inf) the
+    sub-cell recursion Fbar[ii+1] = Fbar[ii] + w D# F# - l Fl + r Fr telescopes to the split form
+    with the entropy-projected surface term, which is pinned by its entropy balance; for a finite
+    blend it still conserves and preserves a free stream."""
+    sp = Case(nd, n, npn, nodes="GL", op="split", nf="mat", avg="cha").oracle()
+    Q = random_state(sp.ndof, nd, "euler", amp=0.15)
+    big = Case(nd, n, npn, nodes="GL", op="hybrid", nf="mat", avg="cha", blend=1e40).oracle()
+    assert np.max(np.abs(big.rhs(Q) - sp.rhs(Q))) <= 1e-12 * np.max(np.abs(sp.rhs(Q)))
+    hy = Case(nd, n, npn, nodes="GL", op="hybrid", nf="mat", avg="cha", blend=1.0).oracle()
+    dQ = hy.rhs(Q)
+    assert np.max(np.abs(dQ - sp.rhs(Q))) > 1e-6 * np.max(np.abs(dQ))         # the blending is active
+    for v in range(hy.nv):
+        assert abs(_integral(hy, dQ[:, v])) < 1e-12 * _integral(hy, np.abs(dQ[:, v])) + 1e-13
+    Qc = np.asfortranarray(np.tile(Q[:1], (hy.ndof, 1)))
+    assert np.max(np.abs(hy.rhs(Qc))) < 1e-11

@@ -257,6 +257,14 @@ HYBRID_CASES = [
     Case(2, (4, 3), 4, op="hybrid", nf="mat", avg="cha", blend=0.3, perturb_amp=0.08),
     Case(2, (3, 4), 5, op="hybrid", tp="std", nf="lxf", avg="std", blend=1.0, perturb_amp=0.1),
     Case(3, (2, 2, 2), 3, op="hybrid", nf="mat", avg="cha", blend=0.5, perturb_amp=0.06),
+    # Gauss nodes: everything as a surface contribution (_hybrid_nb_surface_contribution!,
+    # OpDivergence.jl:629-779)
+    Case(1, (9,), 4, nodes="GL", op="hybrid", nf="mat", avg="cha", blend=1.0),
+    Case(2, (4, 5), 4, nodes="GL", op="hybrid", nf="mat", avg="cha", blend=0.3),
+    Case(2, (3, 4), 5, nodes="GL", op="hybrid", tp="std", nf="lxf", avg="std", blend=1.0),
+    Case(3, (2, 2, 2), 3, nodes="GL", op="hybrid", nf="mat", avg="cha", blend=0.5),
+    Case(2, (4, 3), 4, nodes="GL", op="hybrid", nf="mat", avg="cha", blend=0.5, perturb_amp=0.08),
+    Case(3, (2, 2, 2), 3, nodes="GL", op="hybrid", tp="std", nf="sca", avg="cha", blend=1.0, perturb_amp=0.06),
 ]
 
 
@@ -317,11 +325,10 @@ def test_shockwave_2d_kat_on_gpu(gpu):
 
 @pytest.mark.gpu
 def test_hybrid_unsupported_combinations_raise(gpu):
-    """No silent fallback: Gauss nodes and the fused / node kernels are refused for the hybrid
-    operator."""
+    """No silent fallback: the fused / node kernels are refused for the hybrid operator."""
     import flou_b200 as F
     with pytest.raises(ValueError):
-        Case(2, (3, 3), 4, nodes="GL", op="hybrid").product()
+        Case(2, (3, 3), 4, op="hybrid").product(kernel="node")
     with pytest.raises(ValueError):
         Case(2, (3, 3), 4, op="hybrid").product(kernel="fused")
 
