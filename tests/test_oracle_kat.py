@@ -95,3 +95,62 @@ def test_shockwave_2d_kat():
     assert abs(u.max() / k["maximum"] - 1) <= k["rtol"]
     assert abs(u.max() / k["maximum"] - 1) <= 1e-11
     assert abs(u.min()) < 1e-9          # reference: -4.68e-13 with rtol 1 (round-off noise in rho*v)
+
+
+# ------------------------------------------------------------------ third-party RK tableaus
+def _butcher_from_2n(A, B):
+    """Butcher form of a Williamson 2N scheme: tmp_s = A_s tmp_{s-1} + dt k_s, u_s = u_{s-1} + B_s tmp_s
+    => u_s = u_0 + dt sum_j a[s][j] k_j; the last row is b."""
+    s = len(B)
+    coef = np.zeros((s, s))            # coef[i][j]: weight of k_j in tmp_i
+    U = np.zeros((s + 1, s))           # U[i][j]: weight of k_j in u_i
+    for i in range(s):
+        if i > 0:
+            coef[i] = A[i] * coef[i - 1]
+        coef[i, i] += 1.0
+        U[i + 1] = U[i] + B[i] * coef[i]
+    a = U[:s]                           # stage i evaluates f(u_{i}) with u_i = row i
+    return a, U[s]
+
+
+def test_low_storage_tableaus_satisfy_their_order_conditions():
+    """OrdinaryDiffEq's tableaus are third-party (not under the reference tree); the restated
+    coefficients are pinned here against the order conditions of the published schemes:
+    CarpenterKennedy2N54 (Carpenter & Kennedy 1994) is 4th order -- all 8 conditions to 1e-12,
+    which a single mistyped digit breaks at 1e-6 or more; ORK256 (Bernardini & Pirozzoli 2009)
+    is 2nd order.  The abscissae c must equal the row sums."""
+    for tab, order in ((O.CARPENTER_KENNEDY_2N54, 4), (O.ORK256, 2)):
+        A, B, c = (np.array(tab[k], dtype=float) for k in "ABc")
+        a, b = _butcher_from_2n(A, B)
+        cc = a.sum(axis=1)
+        tol = 1e-12 if order == 4 else 1e-4          # ORK256 is published with 5 digits
+        assert np.max(np.abs(cc - c)) <= (1e-12 if order == 4 else 2e-4)
+        conds = [(b.sum(), 1.0), (b @ cc, 1 / 2)]
+        if order >= 3:
+            conds += [(b @ cc ** 2, 1 / 3), (b @ (a @ cc), 1 / 6)]
+        if order >= 4:
+            conds += [(b @ cc ** 3, 1 / 4), ((b * cc) @ (a @ cc), 1 / 8), (b @ (a @ cc ** 2), 1 / 12),
+                      (b @ (a @ (a @ cc)), 1 / 24)]
+        for got, want in conds:
+            assert abs(got - want) <= tol, (order, got, want)
+
+
+def test_oracle_convergence_order_linear_advection():
+    """Order-of-accuracy cross-check (examples/src/Convergence.jl): 1-D periodic
+    advection of a smooth profile, GLL np = 4, CarpenterKennedy2N54 with a small step: the L2 error
+    falls with order ~np under mesh refinement."""
+    errs = []
+    for n in (4, 8, 16):
+        mesh = cn.cartesian_mesh((0.0,), (1.0,), (n,))
+        cn.apply_periodic_bcs(mesh, ("1", "2"))
+        pb = O.Problem(mesh, "GLL", 4, O.EQ_ADVECTION, O.OP_STRONG, O.FLUX_LXF,
+                       numflux_avg=O.FLUX_STDAVG, intensity=1.0, a=(1.0,))
+        x = pb.coords[:, 0]
+        Q = np.asfortranarray(np.sin(2 * np.pi * x)[:, None])
+        nsteps = 200
+        u = pb.lsrk2n(Q, O.CARPENTER_KENNEDY_2N54, 0.25 / nsteps, nsteps)
+        exact = np.sin(2 * np.pi * (x - 0.25))
+        w = pb.jac * np.tile(pb.weights, pb.ne)
+        errs.append(float(np.sqrt(w @ (u[:, 0] - exact) ** 2)))
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
+    assert errs[-1] < 1e-4 and min(rates) > 3.5, (errs, rates)
