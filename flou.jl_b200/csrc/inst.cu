@@ -220,27 +220,49 @@ struct NBCfg : KCfg<ND_, NP_, EQ_, VOL_, CART_> {
 #define NP FLOU_NP
 
 // [eq][vol][cart]; vol 4 / 5 = split form (StdAverage / Chandrasekhar), 6 = hybrid operator on nodes
-// without boundaries
+// without boundaries.  The instances of one (ND, NP) pair are spread over three translation units
+// (-DFLOU_PART=0|1|2) so that the build parallelises: 0 = strong / split form (all three kernel
+// families) and the trace kernels, 1 = hybrid operator, 2 = split form on Gauss nodes.
+#ifndef FLOU_PART
+#define FLOU_PART 0
+#endif
+#define FLOU_NONE {StageLauncher{}, StageLauncher{}}
 static const StageLauncher table[2][7][2] = {
     {   // linear advection: strong, split (StdAverage two-point flux); no Chandrasekhar
+#if FLOU_PART == 0
         {make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_ADV, VOL_SPLIT_STD, true>>()},
-        {StageLauncher{}, StageLauncher{}},
-        {StageLauncher{}, StageLauncher{}},
-        {StageLauncher{}, StageLauncher{}},
-        {StageLauncher{}, StageLauncher{}},
-        {StageLauncher{}, StageLauncher{}},
+#else
+        FLOU_NONE, FLOU_NONE,
+#endif
+        FLOU_NONE, FLOU_NONE, FLOU_NONE, FLOU_NONE, FLOU_NONE,
     },
     {   // Euler
+#if FLOU_PART == 0
         {make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_STRONG, true>>()},
         {make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, true>>()},
         {make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, false>>(), make<KCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
+#else
+        FLOU_NONE, FLOU_NONE, FLOU_NONE,
+#endif
+#if FLOU_PART == 1
         // HybridDivOperator (general geometry reads the sub-grid tables)
         {make_lines<KCfg<ND, NP, EQ_EULER, VOL_HYBRID, false>>(), make_lines<KCfg<ND, NP, EQ_EULER, VOL_HYBRID, true>>()},
+#else
+        FLOU_NONE,
+#endif
+#if FLOU_PART == 2
         // split form on Gauss nodes
         {make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, false>>(), make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_STD, true>>()},
         {make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, false>>(), make_lines<NBCfg<ND, NP, EQ_EULER, VOL_SPLIT_CHA, true>>()},
+#else
+        FLOU_NONE, FLOU_NONE,
+#endif
+#if FLOU_PART == 1
         {make_lines<NBCfg<ND, NP, EQ_EULER, VOL_HYBRID, false>>(), make_lines<NBCfg<ND, NP, EQ_EULER, VOL_HYBRID, true>>()},
+#else
+        FLOU_NONE,
+#endif
     },
 };
 
@@ -258,21 +280,25 @@ static cudaError_t emit_launch(const double *u, int64_t ndof, const int *list, i
     return cudaGetLastError();
 }
 
+#if FLOU_PART == 0
 static const EmitLauncher emit_adv = {&emit_launch<1>};
 static const EmitLauncher emit_euler = {&emit_launch<ND + 2>};
+#endif
 
-#define CAT_(a, b, c) a##b##_##c
-#define CAT(a, b, c) CAT_(a, b, c)
+#define CAT_(a, b, c, p) a##b##_##c##_p##p
+#define CAT(a, b, c, p) CAT_(a, b, c, p)
 
-const StageLauncher *CAT(stage_table_, FLOU_ND, FLOU_NP)(int eq, int vol, int cart)
+const StageLauncher *CAT(stage_table_, FLOU_ND, FLOU_NP, FLOU_PART)(int eq, int vol, int cart)
 {
     const StageLauncher *l = &table[eq][vol][cart ? 1 : 0];
     return (l->launch || l->launch_lines) ? l : nullptr;
 }
 
-const EmitLauncher *CAT(emit_table_, FLOU_ND, FLOU_NP)(int nv)
+#if FLOU_PART == 0
+const EmitLauncher *CAT(emit_table_, FLOU_ND, FLOU_NP, 0)(int nv)
 {
     return nv == 1 ? &emit_adv : &emit_euler;
 }
+#endif
 
 }  // namespace flou
