@@ -749,6 +749,20 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
             h->split_faces = false;
     }
     h->line_kernel = h->split_faces && !(d->flags & FLOU_B200_FLAG_NODE_KERNEL);
+    if (h->line_kernel) {
+        // the line kernel of this instance may need more shared memory than an SM has (one element
+        // per group at 3-D np = 8): fall back to the node-per-thread element kernel where one
+        // exists, refuse otherwise (hybrid operator, Gauss-node split form: line kernel only)
+        int optin = 0;
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+        if (optin > 0 && h->stage->line_smem > (size_t)optin) {
+            if (!h->stage->launch_elements || (d->flags & FLOU_B200_FLAG_LINE_KERNEL)) {
+                flou_b200_destroy(h);
+                return fail(FLOU_B200_EUNSUPPORTED, "the line kernel of this (nd, np, operator) needs more shared memory than the device offers");
+            }
+            h->line_kernel = false;
+        }
+    }
     h->n_faces = (int)pl.faces.size();
     h->n_faces_local_only = pl.n_faces_local_only;
     H_TRY(upload(&h->faces, pl.faces));

@@ -109,6 +109,15 @@ template <class C>
 static cudaError_t line_prepare()
 {
     using L = LineOf<C>;
+    {
+        // a group of one element can exceed the shared memory of an SM (3-D, np = 8: Euler strong
+        // form 278 KB, StdAverage split form 230 KB): the host then uses the node-per-thread element
+        // kernel (flou_b200_create compares line_smem with the same limit); nothing to prepare
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (optin > 0 && L::SMEM_BYTES > (size_t)optin) return cudaSuccess;
+    }
     cudaError_t e = cudaFuncSetAttribute(FLOU_LINE_KERNEL<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)L::SMEM_BYTES);
     if (e != cudaSuccess) return e;
