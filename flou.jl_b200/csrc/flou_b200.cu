@@ -749,6 +749,21 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
             h->split_faces = false;
     }
     h->line_kernel = h->split_faces && !(d->flags & FLOU_B200_FLAG_NODE_KERNEL);
+    {
+        // the fused / node-per-thread kernels of this instance may not fit an SM's shared memory
+        // either (3-D np = 8, general geometry, split form): use the line kernel, or refuse when the
+        // caller insisted on one of them
+        int optin = 0;
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+        if (optin > 0 && h->stage->launch && h->stage->smem > (size_t)optin && !h->line_kernel) {
+            if (d->flags & (FLOU_B200_FLAG_FUSED | FLOU_B200_FLAG_NODE_KERNEL)) {
+                flou_b200_destroy(h);
+                return fail(FLOU_B200_EUNSUPPORTED, "the fused / node kernels of this (nd, np, operator) need more shared memory than the device offers");
+            }
+            h->split_faces = true;
+            h->line_kernel = true;
+        }
+    }
     if (h->line_kernel) {
         // the line kernel of this instance may need more shared memory than an SM has (one element
         // per group at 3-D np = 8): fall back to the node-per-thread element kernel where one
@@ -756,9 +771,9 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         int optin = 0;
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
         if (optin > 0 && h->stage->line_smem > (size_t)optin) {
-            if (!h->stage->launch_elements || (d->flags & FLOU_B200_FLAG_LINE_KERNEL)) {
+            if (!h->stage->launch_elements || h->stage->smem > (size_t)optin || (d->flags & FLOU_B200_FLAG_LINE_KERNEL)) {
                 flou_b200_destroy(h);
-                return fail(FLOU_B200_EUNSUPPORTED, "the line kernel of this (nd, np, operator) needs more shared memory than the device offers");
+                return fail(FLOU_B200_EUNSUPPORTED, "the kernels of this (nd, np, operator) need more shared memory than the device offers");
             }
             h->line_kernel = false;
         }

@@ -28,6 +28,14 @@ static cudaError_t line_prepare();
 template <class C>
 static cudaError_t do_prepare()
 {
+    {
+        // 3-D np = 8 on general geometry: one element of the node-per-thread kernels needs more than
+        // an SM's shared memory (split form 228 / 232 KB); flou_b200_create then uses the line kernel
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (optin > 0 && C::SMEM_BYTES > (size_t)optin) return line_prepare<C>();
+    }
     cudaError_t e = cudaFuncSetAttribute(stage_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
