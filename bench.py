@@ -180,41 +180,190 @@ def ncu_traffic(workload):
 
 
 # ----------------------------------------------------------------------------- CPU baseline
-def cpu_sample_case(w):
+# Bounded sample of each workload for the CPU legs (config 4 does not
+# fit / finish on the host path, "time 32^3 ... at p=4 and state the per-DOF rate").
+CPU_SAMPLE = {"cfg1": (32, 32), "cfg2": (128, 128), "cfg3": (32, 32, 32), "cfg3b": (32, 32, 32),
+              "cfg4": (32, 32, 32), "cfg4s": (32, 32, 32), "cfg5": (96, 96), "cfg5b": (96, 96)}
+
+
+def cpu_sample_info(name):
+    w = WORKLOADS[name]
+    n = CPU_SAMPLE[name]
+    ndofs = int(np.prod(n)) * w["np"] ** w["nd"]
+    text = f"{'x'.join(map(str, n))} elements p={w['np'] - 1} ({ndofs} DOF), same operator / fluxes / IC"
+    if w.get("unstructured"):
+        text += " on a Cartesian quad mesh (the CPU legs do not read the unstructured mesh)"
+    return {"elements": list(n), "p": w["np"] - 1, "ndofs": ndofs, "what": text}
+
+
+def cpu_sample_case(name):
     """A bounded sample of the same workload for the CPU restatement (same operator, fluxes,
     node count; fewer elements)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from common import Case
-    nd = w["nd"]
-    n = {2: (48, 48), 3: (16, 16, 16)}[nd] if w["eq"] == "euler" else (32, 32)
-    # (config 5: the CPU sample is the same operator/order on a Cartesian quad mesh)
+    w = WORKLOADS[name]
+    nd, n = w["nd"], CPU_SAMPLE[name]
     if w["eq"] == "adv":
         return Case(nd, n, w["np"], nodes="GLL", eq="adv", op="strong", nf="lxf", avg="std",
                     a=(2.0, -1.0, 0.0)), n
     return Case(nd, n, w["np"], nodes="GLL", eq="euler", op="split", nf="mat", avg="cha"), n
 
 
-def run_cpu(w, steps, warmup):
-    """Times the oracle (CPU restatement of Flou's rhs! + ORK256 loop, OpenMP on all host
-    threads) on the bounded sample.  Returns (DOF-updates/s per stage, cores, sample text,
-    ms per step)."""
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def find_julia():
+    """Plan A of BASELINE.md section 4: a Julia that can load the reference (PATH, or an install
+    shipped under baseline/_ref/).  Returns (julia, project) or None."""
+    import shutil
+    exe = shutil.which("julia")
+    for cand in (os.path.join(ROOT, "baseline", "_ref", "julia", "bin", "julia"),):
+        if exe is None and os.path.exists(cand):
+            exe = cand
+    if exe is None:
+        return None
+    for proj in (os.path.join(ROOT, "baseline", "_ref", "Flou.jl"), "/root/reference"):
+        if os.path.exists(os.path.join(proj, "Project.toml")):
+            return exe, proj
+    return None
+
+
+def run_julia(name, steps, budget_s):
+    """Flou.jl's own multithreaded path (bench/flou_cpu.jl).  None when it cannot run."""
+    found = find_julia()
+    if not found:
+        return None
+    exe, proj = found
+    w, n = WORKLOADS[name], CPU_SAMPLE[name]
+    base = name if name in ("cfg1", "cfg2", "cfg3", "cfg4") else {"cfg3b": "cfg3", "cfg4s": "cfg4"}.get(name)
+    if base is None:
+        return None
+    try:
+        out = subprocess.run([exe, "-t", str(host_threads()), f"--project={proj}",
+                              os.path.join(ROOT, "bench", "flou_cpu.jl"), base, str(n[0]), str(w["np"]),
+                              str(steps)], capture_output=True, text=True, timeout=max(60, budget_s)).stdout
+        d = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+        return d
+    except Exception:
+        return None
+
+
+def run_cpu(name, steps, warmup, budget_s=150.0):
+    """Times the CPU path on the bounded sample with ALL host threads: Flou.jl itself when a Julia
+    is present (kind "reference"), else the oracle (CPU restatement of Flou's rhs! + ORK256 loop,
+    OpenMP; kind "port").  Stops early when the time budget is spent; returns a dict with the
+    rate (DOF-updates/s per stage), the threads actually used and the steps actually timed."""
+    w = WORKLOADS[name]
+    info = cpu_sample_info(name)
+    jl = run_julia(name, steps, budget_s)
+    if jl is not None:
+        return {"rate": jl["rate"], "cores": int(jl["threads"]), "kind": "reference", "steps": int(jl["steps"]),
+                "warmup": 1, "ms_per_step": jl["ms_per_step"],
+                "sample": info["what"] + f", {jl['steps']} ORK256 steps, Flou.jl (julia -t {jl['threads']}, bench/flou_cpu.jl)"}
     import oracle as O
-    case, n = cpu_sample_case(w)
+    case, n = cpu_sample_case(name)
     orc = case.oracle()
     start, finish = domain(w)
     # map the unit-box oracle coordinates onto the workload's domain for the IC
     lo, hi = np.zeros(w["nd"]), np.array([1.0 + 0.5 * d for d in range(w["nd"])])
     x = (orc.coords - lo) / (hi - lo) * (np.array(finish) - np.array(start)) + np.array(start)
     Q = np.asfortranarray(initial_condition(x, w))
-    cores = os.cpu_count() or 1
-    u = orc.lsrk2n(Q, O.ORK256, 1e-5, warmup) if warmup > 0 else Q
-    t = time.perf_counter()
-    orc.lsrk2n(u, O.ORK256, 1e-5, steps)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: set the thread count explicitly and
+    # report what OpenMP will really use
+    O.set_threads(host_threads())
+    cores = O.max_threads()
+    t0 = time.perf_counter()
+    u = Q
+    for _ in range(warmup):
+        u = orc.lsrk2n(u, O.ORK256, 1e-5, 1)
+    per = (time.perf_counter() - t0) / warmup if warmup > 0 else None
+    done, t = 0, time.perf_counter()
+    while done < steps:
+        u = orc.lsrk2n(u, O.ORK256, 1e-5, 1)
+        done += 1
+        el = time.perf_counter() - t
+        if done < steps and (time.perf_counter() - t0) + el / done > budget_s:
+            break
     dt = time.perf_counter() - t
-    rate = orc.ndof * 5 * steps / dt
-    sample = (f"{'x'.join(map(str, n))} elements p={w['np'] - 1} ({orc.ndof} DOF), "
-              f"{steps} ORK256 steps, oracle/pipeline.c OpenMP")
-    return rate, cores, sample, dt / steps * 1e3
+    return {"rate": orc.ndof * 5 * done / dt, "cores": cores, "kind": "port", "steps": done,
+            "warmup": warmup, "ms_per_step": dt / done * 1e3,
+            "sample": info["what"] + f", {done} ORK256 steps, oracle/pipeline.c (C restatement of the "
+                                     f"reference path, OpenMP x{cores}; no Julia on this box)"}
+
+
+# ----------------------------------------------------------------------------- self-checks
+def parity_check(device=0):
+    """--check (default on, rank 0 at N=1): BASELINE config 3 at size (32^3, p=3, EC split form +
+    matrix dissipation) through the public API against the oracle: RHS and the state after 2
+    ORK256 steps.  Returns the dict printed as `parity` (and `parity_err` = the larger error)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import flou_b200 as F
+    import oracle as O
+    from common import Case, random_state, relerr, smooth_state
+    O.set_threads(host_threads())
+    case = Case(3, (32, 32, 32), 4, nodes="GLL", eq="euler", op="split", nf="mat", avg="cha")
+    orc = case.oracle()
+    disc, eq = case.product(device=device)
+    Q = np.asfortranarray(0.9 * smooth_state(orc.coords, 3, "euler") + 0.1 * random_state(orc.ndof, 3, "euler", amp=0.3))
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    e_rhs = relerr(dQ, orc.rhs(Q))
+    nsteps, dt = 2, 2e-5
+    ref = orc.lsrk2n(Q, O.ORK256, dt, nsteps)
+    u = Q.copy(order="F")
+    sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), nsteps * dt, dt=dt)
+    e_state = relerr(sol.u[-1], ref) if sol is not None else float("inf")
+    disc.close()
+    return {"case": "config 3 at size: 3D Euler 32^3 p=3, SplitDiv(Chandrasekhar)+MatrixDissipation, "
+                    "0.9 smooth + 0.1 random state (seed 20230917)",
+            "against": "oracle/pipeline.c (CPU restatement of rhs! + ORK256)",
+            "rhs_err": e_rhs, "rhs_tol": 1e-12, "state_err": e_state, "state_steps": nsteps,
+            "state_tol": 1e-10, "ok": bool(e_rhs <= 1e-12 and e_state <= 1e-10)}
+
+
+def multi_gpu_check(dist, gloo, rank, world, local_rank, npn):
+    """N > 1: a small mesh of the workload's kernel instance, element-partitioned over the N ranks
+    with NCCL halo exchange, RHS + 4 RK steps; rank 0 repeats it unpartitioned on its own GPU and
+    compares the gathered result BITWISE.  Returns (flag, detail) on rank 0, (None, None) elsewhere."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import flou_b200 as F
+    from common import Case, random_state, smooth_state
+    case = Case(3, (6, 6, 4 * world), npn, nodes="GLL", eq="euler", op="split", nf="mat", avg="cha")
+    disc, eq = case.product(rank=rank, nranks=world, device=local_rank)
+    ids = [F.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0, group=gloo)
+    disc.comm_init(ids[0])
+    full, eq1 = case.product(rank=0, nranks=1, device=local_rank, create=(rank == 0))
+    Qg = np.asfortranarray(0.9 * smooth_state(full.coords(), 3, "euler")
+                           + 0.1 * random_state(full.coords().shape[0], 3, "euler", amp=0.3))
+    Q = np.asfortranarray(Qg[disc.local_rows()])
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    u = Q.copy(order="F")
+    nsteps, dt = 4, 1e-4
+    sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), nsteps * dt, dt=dt)
+    parts = [None] * world
+    dist.all_gather_object(parts, (dQ, None if sol is None else sol.u[-1]), group=gloo)
+    disc.close()
+    if rank != 0:
+        return None, None
+    dQ1 = full.new_state()
+    F.rhs(dQ1, Qg, F.EquationConfig(full, eq1), 0.0)
+    u1 = Qg.copy(order="F")
+    F.timeintegrate(u1, full, eq1, F.ORK256(), nsteps * dt, dt=dt)
+    full.close()
+    if any(p[1] is None for p in parts):
+        return False, "partitioned run crashed"
+    dQn = np.concatenate([p[0] for p in parts], axis=0)
+    un = np.concatenate([p[1] for p in parts], axis=0)
+    same = bool(np.array_equal(dQn, dQ1) and np.array_equal(un, u1))
+    detail = (f"3D Euler {case.n} p={npn - 1} over {world} ranks vs 1 rank: rhs max|d|="
+              f"{np.max(np.abs(dQn - dQ1)):.1e}, state after {nsteps} steps max|d|={np.max(np.abs(un - u1)):.1e}")
+    return same, detail
 
 
 # ----------------------------------------------------------------------------- main
@@ -240,6 +389,8 @@ def main():
     ap.add_argument("--dt", type=float, default=None, help="override the workload's time step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-check", action="store_true",
+                    help="skip the self-checks (parity vs the oracle at N=1, multi_gpu_bitwise at N>1)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -251,6 +402,9 @@ def main():
     config = {"workload": w["desc"], "elements": list(w["n"]), "p": w["np"] - 1,
               "ndofs": ndof_global, "nv": 1 if w["eq"] == "adv" else w["nd"] + 2,
               "rk": "ORK256 (5 stages)", "partition": f"contiguous element ranges x{world}",
+              # the CPU legs (cpu_baseline here, --impl reference) time this bounded sample of the
+              # workload, not the full mesh
+              "cpu_sample": cpu_sample_info(args.workload),
               "l2_policy": "inputs larger than L2 (state >> 126 MB)" if ndof_global * 40 > 2.5e8
               else "state fits L2; timed back-to-back as the RK loop runs it"}
 
@@ -258,18 +412,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
-        warm = max(0, min(args.warmup, 1))
-        rate, cores, sample, ms = run_cpu(w, steps, warm)
+        r = run_cpu(args.workload, max(1, args.steps), max(0, min(args.warmup, 1)))
+        rate = r["rate"]
         line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
-                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
+                "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"],
+                "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": sample},
+                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"]},
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "gpu_launches": 0,
+                "note": "per-DOF rate of the CPU path on config.cpu_sample (bounded sample of the workload); "
+                        "steps = steps actually timed inside the time budget"}
         emit(line)
         return
 
@@ -402,6 +558,13 @@ def main():
                "step": f"one timeintegrate() call = upload + {m} RK steps + download",
                "calls": args.e2e_calls, "pinned_host": pinned, "ms_per_call": te / args.e2e_calls * 1e3}
 
+    ndof_local = disc.ndofs
+    launch_info = disc.kernel_info()
+    # ---- self-checks (outside every timed region)
+    mg_flag = mg_detail = None
+    if world > 1 and not args.no_check and w["nd"] == 3 and w["eq"] == "euler" and not w.get("unstructured"):
+        disc.close()
+        mg_flag, mg_detail = multi_gpu_check(dist, gloo, rank, world, local_rank, w["np"])
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -413,7 +576,6 @@ def main():
     bytes_per_dof = 32 * eq.nv                      # read u,tmp + write u,tmp
     if w.get("unstructured"):
         bytes_per_dof += 8 * (nd * nd + 1)          # per-node metric + jac (config 5: 168 B)
-    ndof_local = disc.ndofs
     stages = nstages * args.steps
     stage_ms = ms_dev / stages                      # whole stage: every kernel of one RK stage
     stage_gbs = ndof_local * bytes_per_dof / (stage_ms * 1e-3) / 1e9
@@ -421,7 +583,7 @@ def main():
     # of the algorithmic bytes); the face-flux kernel only adds non-algorithmic traffic
     kernel_ms = ksplit["element_kernel_ms"] if ksplit else stage_ms
     achieved = ndof_local * bytes_per_dof / (kernel_ms * 1e-3) / 1e9
-    config["launch"] = disc.kernel_info()
+    config["launch"] = launch_info
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                 "kernel": "flou::line_kernel_ws (element kernel of the two-kernel stage)",
@@ -434,14 +596,25 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        rate, cores, sample, _ = run_cpu(w, 2, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        r = run_cpu(args.workload, 2, 1, budget_s=60.0)
+        cpu = {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+
+    parity = None
+    if world == 1 and not args.no_check:
+        disc.close()
+        parity = parity_check(local_rank)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "wall_ms_per_step": wall / args.steps * 1e3}
+    if parity is not None:
+        line["parity"] = parity
+        line["parity_err"] = max(parity["rhs_err"], parity["state_err"])
+    if mg_flag is not None:
+        line["multi_gpu_bitwise"] = mg_flag
+        line["multi_gpu_check"] = mg_detail
     emit(line)
     if dist is not None:
         dist.barrier()

@@ -1,7 +1,8 @@
 // Face-flux kernel of the two-kernel stage: interface_fluxes! + applyBCs! evaluated ONCE per
 // face point (src/FlouSpatial/Interfaces.jl:111-136 and :25-49), one thread per (face, master
-// face dof).  Output: Fn[(slot*nv + v)*NFP + i] = rotate2phys(F*(rotate2face(Ql), rotate2face(Qr)))
-// * jac, i.e. the reference's `Fn.sides[1]` (master-outward); the slave side is its negative with
+// face dof).  Output: Fn[slot][v][i] = rotate2phys(F*(rotate2face(Ql), rotate2face(Qr)))
+// * jac (slot stride fn_block(nv, nfp): 16-byte aligned blocks for the element kernel's TMA copies),
+// i.e. the reference's `Fn.sides[1]` (master-outward); the slave side is its negative with
 // the `master2slave` permutation and is applied by the element kernel when it copies the block.
 //
 // Traces (project2faces!, Interfaces.jl:51-109) are not materialised for every face: with
@@ -168,7 +169,7 @@ __device__ __forceinline__ void face_point(const KParams &P, int f, int i, const
     }
     if (CART) rot2phys_c<ND, EQ, LFM>(Fn, Fp);
     else rotate2phys<ND, EQ>(Fn, fr, Fp);
-    double *dst = P.Fn + (int64_t)f * (NV * NFP) + i;
+    double *dst = P.Fn + (int64_t)f * fn_block(NV, NFP) + i;
 #pragma unroll
     for (int v = 0; v < NV; v++) dst[v * NFP] = Fp[v] * fj;
 }

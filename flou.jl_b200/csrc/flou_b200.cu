@@ -314,6 +314,23 @@ int32_t validate_desc(const flou_b200_desc *d)
         return fail(FLOU_B200_EINVAL, "owned range does not match part_offsets[rank]");
     if (nranks == 1 && (d->elem_begin != 0 || d->elem_end != d->ne))
         return fail(FLOU_B200_EINVAL, "single-rank handle must own every element");
+    // value ranges of the byte / enum tables: an unknown bc_kind would fall into the TABLE branch of
+    // the face kernel and read past bc_table, a bad orientation into master2slave's default case
+    const int max_orient = d->nd == 1 ? 0 : (d->nd == 2 ? 1 : 7);
+    for (int64_t f = 0; f < d->nf; f++)
+        if (d->orientation[f] > max_orient)
+            return fail(FLOU_B200_EINVAL, "face orientation out of range (0 in 1-D, 0..1 in 2-D, 0..7 in 3-D)");
+    if (d->nbound > 0 && d->bc_offsets[0] != 0)
+        return fail(FLOU_B200_EINVAL, "bc_offsets must start at 0");
+    for (int ib = 0; ib < d->nbound; ib++) {
+        if (d->bc_kind[ib] < FLOU_B200_BC_INFLOW || d->bc_kind[ib] > FLOU_B200_BC_TABLE)
+            return fail(FLOU_B200_EINVAL, "unknown boundary-condition kind");
+        if (d->bc_offsets[ib + 1] < d->bc_offsets[ib])
+            return fail(FLOU_B200_EINVAL, "bc_offsets must not decrease");
+        for (int64_t m = d->bc_offsets[ib]; m < d->bc_offsets[ib + 1]; m++)
+            if (d->bc_faces[m] < 1 || d->bc_faces[m] > d->nf)
+                return fail(FLOU_B200_EINVAL, "bc_faces entry outside [1, nf]");
+    }
     return FLOU_B200_OK;
 }
 
@@ -529,6 +546,20 @@ int32_t run_steps_direct(flou_b200_handle *h, int nstages, const double *A, cons
                 if (rl) return rl;
             }
         }
+    return FLOU_B200_OK;
+}
+
+// State a query (get_max_dt, monitor, limiter call) works on: the device-resident state, or -- when
+// the caller passes an explicit host state -- a copy of it in the scratch ping-pong buffer u[cur^1],
+// which nothing uses between passes, so that the state of an ongoing advance() stays untouched.
+int32_t query_state(flou_b200_handle *h, const double *Q, double **state)
+{
+    *state = h->u[h->cur];
+    if (Q) {
+        *state = h->u[h->cur ^ 1];
+        CUDA_TRY(cudaMemcpyAsync(*state, Q, sizeof(double) * (size_t)h->ndof * h->nv,
+                                 cudaMemcpyHostToDevice, h->stream));
+    }
     return FLOU_B200_OK;
 }
 
@@ -783,7 +814,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     H_TRY(upload(&h->faces, pl.faces));
     H_TRY(upload(&h->econn, pl.econn));
     if (h->split_faces)
-        H_TRY(cudaMalloc((void **)&h->Fn, sizeof(double) * std::max<size_t>((size_t)h->n_faces * h->nfp * h->nv, 1)));
+        H_TRY(cudaMalloc((void **)&h->Fn, sizeof(double) * std::max<size_t>((size_t)h->n_faces * fn_block(h->nv, h->nfp), 2)));
     if (!cart) {
         // re-lay geometry as plane-major SoA restricted to owned elements / touched faces
         const int64_t ndof = h->ndof, npts = h->npts, nfp = h->nfp;
@@ -922,6 +953,16 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     P.ghost = h->ghost;
     P.ndof = h->ndof;
     P.status = h->status;
+    // the memsets and table uploads above ran on the legacy default stream, which the handle's
+    // non-blocking streams never synchronise with: finish them before the first upload / launch
+    {
+        const cudaError_t es = cudaDeviceSynchronize();
+        if (es != cudaSuccess) {
+            const std::string m = std::string("cudaDeviceSynchronize: ") + cudaGetErrorString(es);
+            flou_b200_destroy(h);
+            return fail(FLOU_B200_ECUDA, m);
+        }
+    }
     *out = h;
     return FLOU_B200_OK;
 }
@@ -976,11 +1017,8 @@ int32_t flou_b200_max_dt(flou_b200_handle *h, const double *Q, double cfl, doubl
 {
     if (!h || !dt) return fail(FLOU_B200_EINVAL, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (Q) {
-        CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, sizeof(double) * (size_t)h->ndof * h->nv,
-                                 cudaMemcpyHostToDevice, h->stream));
-        h->traces_valid = false;
-    }
+    double *state = nullptr;
+    if (int32_t rc = query_state(h, Q, &state)) return rc;
     const unsigned long long inf_bits = 0x7ff0000000000000ULL;
     CUDA_TRY(cudaMemcpyAsync(h->dt_bits, &inf_bits, sizeof(inf_bits), cudaMemcpyHostToDevice, h->stream));
     int sms = 148;
@@ -988,7 +1026,7 @@ int32_t flou_b200_max_dt(flou_b200_handle *h, const double *Q, double cfl, doubl
     const int threads = 256;
     const int64_t want = (h->ndof + threads - 1) / threads;
     const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 8);
-    max_dt_kernel<<<grid, threads, 0, h->stream>>>(h->u[h->cur], h->ndof, h->npts, h->nd,
+    max_dt_kernel<<<grid, threads, 0, h->stream>>>(state, h->ndof, h->npts, h->nd,
                                                    h->equation == FLOU_B200_EQ_EULER, h->gamma, h->anorm,
                                                    cfl, h->elem_dx, h->cart_dx, h->dt_bits);
     CUDA_TRY(cudaGetLastError());
@@ -1013,16 +1051,13 @@ int32_t flou_b200_monitor(flou_b200_handle *h, int32_t kind, const double *Q, do
     if (kind != FLOU_B200_MONITOR_KINETIC_ENERGY && kind != FLOU_B200_MONITOR_ENTROPY)
         return fail(FLOU_B200_EINVAL, "unknown monitor");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (Q) {
-        CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, sizeof(double) * (size_t)h->ndof * h->nv,
-                                 cudaMemcpyHostToDevice, h->stream));
-        h->traces_valid = false;
-    }
+    double *state = nullptr;
+    if (int32_t rc = query_state(h, Q, &state)) return rc;
     const int threads = 256;
     const int64_t want = (h->ndof + threads - 1) / threads;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, h->mon_blocks));
     double *out = h->mon_partial + h->mon_blocks;
-    monitor_kernel<<<grid, threads, 0, h->stream>>>(h->u[h->cur], h->ndof, h->npts, h->nd, kind, h->gamma,
+    monitor_kernel<<<grid, threads, 0, h->stream>>>(state, h->ndof, h->npts, h->nd, kind, h->gamma,
                                                     h->w_nodes, h->base.jac, h->base.cjac, h->mon_partial);
     CUDA_TRY(cudaGetLastError());
     monitor_reduce_kernel<<<1, 256, 0, h->stream>>>(h->mon_partial, grid, out);
@@ -1046,9 +1081,16 @@ int32_t flou_b200_zhang_shu(flou_b200_handle *h, double *Q, double minval)
         return fail(FLOU_B200_EINVAL, "the Zhang-Shu limiter is defined for the Euler equations (list_limiters)");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t bytes = sizeof(double) * (size_t)h->ndof * h->nv;
-    if (Q) CUDA_TRY(cudaMemcpyAsync(h->u[h->cur], Q, bytes, cudaMemcpyHostToDevice, h->stream));
-    if (int32_t rc = launch_zhang_shu(h, h->u[h->cur], minval)) return rc;
-    if (Q) CUDA_TRY(cudaMemcpyAsync(Q, h->u[h->cur], bytes, cudaMemcpyDeviceToHost, h->stream));
+    // explicit host state: limited in the scratch buffer and copied back; the device-resident state
+    // (and its traces) are untouched.  Q = NULL: the device-resident state is limited in place.
+    double *state = nullptr;
+    if (int32_t rc = query_state(h, Q, &state)) return rc;
+    const bool tv = h->traces_valid;
+    if (int32_t rc = launch_zhang_shu(h, state, minval)) return rc;
+    if (Q) {
+        h->traces_valid = tv;
+        CUDA_TRY(cudaMemcpyAsync(Q, state, bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return FLOU_B200_OK;
 }

@@ -6,9 +6,6 @@
 #include "face_kernel.cuh"
 #include "line_kernel.cuh"
 #include "line_kernel_ws.cuh"
-#ifdef FLOU_WS      // experimental warp-specialised persistent variant (slower, see profiles/)
-#include "stage_kernel_ws.cuh"
-#endif
 
 #ifndef FLOU_GRID_MULT_DEFAULT
 #define FLOU_GRID_MULT_DEFAULT 1
@@ -87,16 +84,11 @@ static cudaError_t do_launch_elements(const KParams &P, cudaStream_t s)
     return cudaGetLastError();
 }
 
-// ---- line-per-thread element kernel (default element kernel of the two-kernel stage)
-#ifndef FLOU_LINE_NOWS    // default: warp-specialised variant, TL line threads + one update warp
+// ---- line-per-thread element kernel (element kernel of the two-kernel stage): warp-specialised,
+// TL line threads + one update warp
 template <class C>
 using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, true, C::NB>;
 #define FLOU_LINE_KERNEL line_kernel_ws
-#else
-template <class C>
-using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, false, C::NB>;
-#define FLOU_LINE_KERNEL line_kernel
-#endif
 
 template <class C>
 static int line_resident_ctas()
@@ -159,60 +151,12 @@ static cudaError_t do_launch_faces(const KParams &P, cudaStream_t s)
     return cudaGetLastError();
 }
 
-#ifdef FLOU_WS
-// ---- warp-specialised persistent kernel -------------------------------------------------
-template <class C>
-static int ws_resident_ctas()
-{
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_kernel_ws<C>, WSCfg<C>::THREADS,
-                                                      WSCfg<C>::SMEM_BYTES);
-        n = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
-    }
-    return n;
-}
-
-template <class C>
-static cudaError_t ws_prepare()
-{
-    cudaError_t e = cudaFuncSetAttribute(stage_kernel_ws<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)WSCfg<C>::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(stage_kernel_ws<C>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    ws_resident_ctas<C>();
-    return cudaSuccess;
-}
-
-template <class C>
-static cudaError_t ws_launch(const KParams &P, cudaStream_t s)
-{
-    if (P.elem_count <= 0) return cudaSuccess;
-    const int ngroups = (P.elem_count + C::EPB - 1) / C::EPB;
-    const int resident = ws_resident_ctas<C>();
-    const int grid = ngroups < resident ? ngroups : resident;
-    stage_kernel_ws<C><<<grid, WSCfg<C>::THREADS, WSCfg<C>::SMEM_BYTES, s>>>(P);
-    return cudaGetLastError();
-}
-#endif
-
 template <class C>
 static constexpr StageLauncher make()
 {
-#ifdef FLOU_WS
-    return StageLauncher{&ws_launch<C>, &do_launch_elements<C>, &do_launch_lines<C>, &do_launch_faces<C>, &ws_prepare<C>,
-                         &ws_resident_ctas<C>, C::EPB, WSCfg<C>::THREADS, WSCfg<C>::SMEM_BYTES,
-                         LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES, &line_resident_ctas<C>};
-#else
     return StageLauncher{&do_launch<C>, &do_launch_elements<C>, &do_launch_lines<C>, &do_launch_faces<C>, &do_prepare<C>,
                          &resident_ctas<C>, C::EPB, C::THREADS, C::SMEM_BYTES,
                          LineOf<C>::E, LineOf<C>::T, LineOf<C>::SMEM_BYTES, &line_resident_ctas<C>};
-#endif
 }
 
 // operators that exist in the line-per-thread formulation only (HybridDivOperator): two-kernel

@@ -16,15 +16,13 @@
 // one third of the shared-memory traffic of the node-per-thread kernel (which ncu showed to be
 // bound by the shared-memory pipe at 83 % L1TEX, profiles/r1_kernel_notes.md).
 //
-// A CTA (T threads) walks over groups of E consecutive elements, g = blockIdx.x, +gridDim.x, ...:
+// A persistent CTA walks over groups of E consecutive elements, g = blockIdx.x, +gridDim.x, ...:
 //   phase 1  node tasks:  state of group g (already in shared memory) -> node primitives
-//   barrier
-//   issue    cp.async: face fluxes of group g, tmp of group g, STATE OF THE NEXT GROUP
 //   phase 2  line tasks:  (element, direction, line) -> partial sums, one plane set per direction
-//   barrier
 //   phase 3  node tasks:  sum the ND partial sums, 1/jac, RK update, x-face traces of u_out
-// so every global load of the kernel is in flight behind the flux arithmetic of phase 2 (the
-// first, non-pipelined line kernel spent 45 % of its stall samples on long-scoreboard waits).
+// with every global load in flight behind the flux arithmetic of phase 2.  This header holds the
+// configuration (LCfg) and the three phases; the kernel itself -- warp-specialised, TMA bulk copies,
+// mbarrier hand-offs -- is line_kernel_ws.cuh.
 #pragma once
 #include <type_traits>
 #include "stage_kernel.cuh"
@@ -63,6 +61,14 @@ __device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gmem_sr
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+// the same with the default L2 policy: face-flux blocks, which the second neighbour of the face
+// reads again a little later
+__device__ __forceinline__ void bulk_g2s_keep(double *smem_dst, const double *gmem_src, unsigned bytes, unsigned bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
 // Wait for the phase with the given parity.  A failed try_wait comes back within a few cycles on
 // sm_100a, so a plain retry loop spins at ~4 cycles per iteration and takes issue slots from the
@@ -129,8 +135,9 @@ constexpr ETPick pick_et(int nlines, int per_elem_doubles, int max_kb)
     return best;
 }
 
-// WS = warp-specialised variant (line_kernel_ws.cuh): TL line threads plus one update warp, three
-// state buffers and two node-data buffers.
+// Layout of the warp-specialised kernel (line_kernel_ws.cuh): TL line threads plus one update warp,
+// three state buffers and two node-data buffers (WS is kept in the template signature for the
+// instance names in profiles/; it is always true).
 // NB = nodes without boundaries (Gauss): the split form takes its surface term from entropy-
 // projected end states (splitdiv_nb_line); a separate instance, so that the GLL kernels carry none
 // of that code (inlined into the exact path it cost the GLL instance 35 %: local-memory frame).
@@ -155,9 +162,11 @@ struct LCfg {
     static constexpr int NPART = ND * NV;
     static constexpr int NUB = WS ? 3 : 2;                // state buffers
     static constexpr int NAB = WS ? 2 : 1;                // node-data buffers
-    // shared memory per element (doubles): state buffers, tmp, node data, partial sums, face
-    // fluxes + signs of every line
-    static constexpr int PER_ELEM = ((NUB + 1) * NV + NAB * NAUX + NPART) * NPTS + (2 * NV + 2) * NLINES;
+    // face-flux block of one face slot, [v][i] padded to a 16-byte multiple (one TMA bulk copy)
+    static constexpr int FNB = fn_block(NV, NFP);
+    // shared memory per element (doubles): state buffers, tmp, node data, partial sums, the
+    // flux blocks of its faces
+    static constexpr int PER_ELEM = ((NUB + 1) * NV + NAB * NAUX + NPART) * NPTS + NFACES * FNB;
 #if defined(FLOU_LINE_E) && defined(FLOU_LINE_T)
     static constexpr int E = FLOU_LINE_E, TL = FLOU_LINE_T;
 #else
@@ -173,10 +182,11 @@ struct LCfg {
     static constexpr int OFF_T = OFF_U + NUB * NV * N;    // [NV][N]         tmp
     static constexpr int OFF_A = OFF_T + NV * N;          // [NAB][NAUX][N]  node data
     static constexpr int OFF_P = OFF_A + NAB * NAUX * N;  // [ND*NV][N]      partial sums by direction
-    static constexpr int OFF_F = OFF_P + NPART * N;       // [2*NV + 2][LT]  face fluxes and signs by line
-    static constexpr int OFF_EC = OFF_F + (2 * NV + 2) * LT;    // [2][E*NFACES] int2: face connectivity of this / the next group
-    static constexpr int OFF_BAR = OFF_EC + 2 * E * NFACES;     // WS: 8 mbarriers
-    static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OFF_BAR + (WS ? 8 : 0));
+    static constexpr int OFF_F = (OFF_P + NPART * N + 1) & ~1;  // [E*NFACES][FNB]  flux blocks of the group's faces (16-byte aligned)
+    static constexpr int OFF_EC = OFF_F + E * NFACES * FNB;     // [2][E*NFACES] int2: face connectivity of this / the next group
+    static constexpr int OFF_BAR = OFF_EC + 2 * E * NFACES;     // 8 mbarriers
+    static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OFF_BAR + 8);
+    static_assert(WS, "the line kernel exists in its warp-specialised form only");
     // registers: a line task holds NP nodes and NP*NV accumulators
     static constexpr int MINB =
 #ifdef FLOU_LINE_MINB
@@ -603,20 +613,31 @@ __device__ __forceinline__ void hybrid_nb_line(const KParams &P, const double (&
         for (int v = 0; v < NV; v++) acc[j][v] = (Fb[j][v] - Fb[j + 1][v]) / P.w1d[j];
 }
 
+// Where a line task finds the Riemann fluxes at its two ends: the flux blocks of the group's faces
+// (one TMA bulk copy per face slot, issued by the update warp), the connectivity records that say
+// which side of each face the element is on, and the mbarrier the copies complete on.
+struct FaceSrc {
+    const double *sFn;      // [E*NFACES][FNB] master-outward fluxes in the master's face-dof order
+    const int2 *ec;         // [E*NFACES] {slot, master | orientation << 1}
+    unsigned bar, parity;
+};
+
 // Surface term of the split form on nodes WITHOUT boundaries, one line
 // (_flux_splitdiv_nb_tensorproduct! + _surf_splitdiv_nb_tensorproduct!, OpDivergence.jl:389-437):
 //   W_i = vars_cons2entropy(Q_i);  Q(l) = vars_entropy2cons(l' W),  Q(r) = vars_entropy2cons(r' W)
 //   Fl_i = F#(Q_i, Q(l)),  Fr_i = F#(Q_i, Q(r))
 //   Fl_i -= l' Fl + Fn_left,   Fr_i -= r' Fr - Fn_right,   dQ_i += dg_l[i] Fl_i - dg_r[i] Fr_i
 // in the folded Cartesian form of the caller: unit metric along the (permuted) axis 0, face fluxes
-// pre-divided by the metric factor (wl, wr carry sign and 1/metric), components in the order pc.
+// fnl / fnr (master-outward, in the caller's variable order) pre-divided by the metric factor
+// (wl, wr carry sign and 1/metric), components in the order pc.
 template <class C>
-__device__ __forceinline__ void splitdiv_nb_line(const KParams &P, const double *sA, const double *sF,
-                                              int base, int stride, const int (&pc)[C::ND], int task,
+__device__ __forceinline__ void splitdiv_nb_line(const KParams &P, const double *sA,
+                                              const double (&fnl)[C::NV], const double (&fnr)[C::NV],
+                                              int base, int stride, const int (&pc)[C::ND],
                                               double wl, double wr, int d, int64_t gnode0, int64_t sub0,
                                               double (&acc)[C::NP][C::NV])
 {
-    constexpr int ND = C::ND, NP = C::NP, NV = C::NV, N = C::N, LT = C::LT, VOL = C::VOL;
+    constexpr int ND = C::ND, NP = C::NP, NV = C::NV, N = C::N, VOL = C::VOL;
     constexpr bool CART = C::CART;
     const double g = P.fp.gamma;
     // general geometry: metric vector Ja[:, d] of the line's nodes and the sub-grid normals times
@@ -717,7 +738,7 @@ __device__ __forceinline__ void splitdiv_nb_line(const KParams &P, const double 
     }
 #pragma unroll
     for (int v = 0; v < NV; v++) {
-        const double a0 = lFl[v] + wl * sF[v * LT + task], b0 = rFr[v] - wr * sF[(NV + v) * LT + task];
+        const double a0 = lFl[v] + wl * fnl[v], b0 = rFr[v] - wr * fnr[v];
 #pragma unroll
         for (int j = 0; j < NP; j++)
             acc[j][v] += P.dgl[j] * (Fl[j][v] - a0) - P.dgr[j] * (Fr[j][v] - b0);
@@ -728,12 +749,12 @@ __device__ __forceinline__ void splitdiv_nb_line(const KParams &P, const double 
 // fluxes at its ends, written as the partial sums of direction d.  FAST (Chandrasekhar only):
 // branch-free pair fluxes; returns true when the line has to be redone with FAST = false.
 template <class C, bool FAST>
-__device__ __forceinline__ bool line_task(const KParams &P, const double *sA, double *sP, const double *sF,
+__device__ __forceinline__ bool line_task(const KParams &P, const double *sA, double *sP, const FaceSrc &fs,
                                           int task, int64_t dof0, unsigned free_bar = 0, unsigned free_parity = 0)
 {
     constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
-    constexpr int NPTS = C::NPTS, NFP = C::NFP, NLINES = C::NLINES;
-    constexpr int N = C::N, LT = C::LT;
+    constexpr int NPTS = C::NPTS, NFP = C::NFP, NLINES = C::NLINES, NFACES = C::NFACES;
+    constexpr int N = C::N, FNB = C::FNB;
     constexpr bool CART = C::CART, SPLIT = C::SPLIT, FOLD = C::FOLD;
     const int64_t ndof = P.ndof;
     bool redo = false;
@@ -750,6 +771,20 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
 #pragma unroll
         for (int c = 0; c < ND; c++) { const int s = d + c; pc[c] = FOLD ? (s >= ND ? s - ND : s) : c; }
         auto var_of = [&](int v) { return (FOLD && EQ == EQ_EULER && v >= 1 && v <= ND) ? 1 + pc[v - 1] : v; };
+        // Riemann fluxes at the line's two ends (surface_contribution!): Fn is the master-outward flux
+        // in the master's face-dof order; the slave side sees it negated (sgL / sgR) and permuted
+        const double *fL, *fR;
+        double sgL, sgR;
+        auto face_src = [&]() {
+            mbar_wait(fs.bar, fs.parity);      // the flux blocks of this group have landed
+            const int2 ecL = fs.ec[el * NFACES + 2 * d], ecR = fs.ec[el * NFACES + 2 * d + 1];
+            const int iL = (ecL.y & 1) ? k : slave2master<ND, NP>(k, (ecL.y >> 1) & 7);
+            const int iR = (ecR.y & 1) ? k : slave2master<ND, NP>(k, (ecR.y >> 1) & 7);
+            fL = fs.sFn + (el * NFACES + 2 * d) * FNB + iL;
+            fR = fs.sFn + (el * NFACES + 2 * d + 1) * FNB + iR;
+            sgL = (ecL.y & 1) ? 1.0 : -1.0;
+            sgR = (ecR.y & 1) ? 1.0 : -1.0;
+        };
 
         double acc[NP][NV];
 #pragma unroll
@@ -768,11 +803,10 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
             const int64_t sub0 = (((dof0 / NPTS + el) * ND + d) * NFP + k) * (NP + 1);
             if constexpr (C::NB) {
                 // nodes without boundaries: the face fluxes enter the sub-cell recursion itself
-                cp_async_wait<0>();
+                face_src();
                 double fnl[NV], fnr[NV];
-                const double sl = sF[(2 * NV) * LT + task], sr = sF[(2 * NV + 1) * LT + task];
 #pragma unroll
-                for (int v = 0; v < NV; v++) { fnl[v] = sl * sF[v * LT + task]; fnr[v] = sr * sF[(NV + v) * LT + task]; }
+                for (int v = 0; v < NV; v++) { fnl[v] = sgL * fL[v * NFP]; fnr[v] = sgR * fR[v * NFP]; }
                 if (d == 0) hybrid_nb_line<C, 0>(P, Qj, fnl, fnr, gnode0, stride, sub0, acc);
                 else if (ND >= 2 && d == 1) hybrid_nb_line<C, (ND >= 2 ? 1 : 0)>(P, Qj, fnl, fnr, gnode0, stride, sub0, acc);
                 else if (ND >= 3) hybrid_nb_line<C, (ND >= 3 ? 2 : 0)>(P, Qj, fnl, fnr, gnode0, stride, sub0, acc);
@@ -871,17 +905,17 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
 
         // lift of the two face fluxes (OpDivergence.jl:42-100); in FOLD mode the partial sum is
         // later multiplied by the metric factor of direction d, so the lift is pre-divided by it
-        cp_async_wait<0>();
+        if (!(C::HYBRID && C::NB)) face_src();
         {
             const double rm = FOLD ? pick<ND>(P.rcmet, d) : 1.0;
-            const double wl = sF[(2 * NV) * LT + task] * rm, wr = sF[(2 * NV + 1) * LT + task] * rm;
+            const double wl = sgL * rm, wr = sgR * rm;
             if (P.colloc) {
                 // GLL: only the two end nodes of the line see the face fluxes
                 const double w0 = P.dgl[0] * wl, w1 = P.dgr[NP - 1] * wr;
 #pragma unroll
                 for (int v = 0; v < NV; v++) {
-                    acc[0][v] = fma(-w0, sF[v * LT + task], acc[0][v]);
-                    acc[NP - 1][v] = fma(-w1, sF[(NV + v) * LT + task], acc[NP - 1][v]);
+                    acc[0][v] = fma(-w0, fL[var_of(v) * NFP], acc[0][v]);
+                    acc[NP - 1][v] = fma(-w1, fR[var_of(v) * NFP], acc[NP - 1][v]);
                 }
             } else if (C::HYBRID) {
                 // hybrid operator on nodes without boundaries: hybrid_nb_line consumed the face fluxes
@@ -892,7 +926,10 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
                 // never take the fast Chandrasekhar path, which has no surface code
                 if constexpr (C::NB && !FAST) {
                     const int64_t sub0 = (((dof0 / NPTS + el) * ND + d) * NFP + k) * (NP + 1);
-                    splitdiv_nb_line<C>(P, sA, sF, base, stride, pc, task, wl, wr, d, dof0 + base, sub0, acc);
+                    double fnl[NV], fnr[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; v++) { fnl[v] = fL[var_of(v) * NFP]; fnr[v] = fR[var_of(v) * NFP]; }
+                    splitdiv_nb_line<C>(P, sA, fnl, fnr, base, stride, pc, wl, wr, d, dof0 + base, sub0, acc);
                 }
             } else {
 #pragma unroll
@@ -900,8 +937,8 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
                     const double w0 = P.dgl[j] * wl, w1 = P.dgr[j] * wr;
 #pragma unroll
                     for (int v = 0; v < NV; v++) {
-                        acc[j][v] = fma(-w0, sF[v * LT + task], acc[j][v]);
-                        acc[j][v] = fma(-w1, sF[(NV + v) * LT + task], acc[j][v]);
+                        acc[j][v] = fma(-w0, fL[var_of(v) * NFP], acc[j][v]);
+                        acc[j][v] = fma(-w1, fR[var_of(v) * NFP], acc[j][v]);
                     }
                 }
             }
@@ -921,10 +958,10 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
 // exact redo of a line, kept out of line so that its register allocation (library log, calls) does
 // not weigh on the fast path
 template <class C>
-__device__ __noinline__ void line_task_exact(const KParams &P, const double *sA, double *sP, const double *sF,
+__device__ __noinline__ void line_task_exact(const KParams &P, const double *sA, double *sP, const FaceSrc &fs,
                                              int task, int64_t dof0, unsigned free_bar = 0, unsigned free_parity = 0)
 {
-    line_task<C, false>(P, sA, sP, sF, task, dof0, free_bar, free_parity);
+    line_task<C, false>(P, sA, sP, fs, task, dof0, free_bar, free_parity);
 }
 
 // Node data of the line phase from the conservative state of one node (phase 1):
@@ -1182,142 +1219,6 @@ __device__ __forceinline__ void trace_pass(const KParams &P, const double *Unew,
         double *dst = P.tr_out + (e * 2 + side) * (NV * NFP) + k;
 #pragma unroll
         for (int v = 0; v < NV; v++) __stcs(dst + v * NFP, Unew[v * N + n]);
-    }
-}
-
-// ------------------------------------------------------------------ the kernel
-template <class C>
-__global__ void
-#ifdef FLOU_LINE_MAXREG
-__maxnreg__(FLOU_LINE_MAXREG)
-#else
-__launch_bounds__(C::T, C::MINB)
-#endif
-line_kernel(const __grid_constant__ KParams P)
-{
-    constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
-    constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NLINES = C::NLINES;
-    constexpr int E = C::E, T = C::T, N = C::N, LT = C::LT;
-    constexpr bool CART = C::CART, SPLIT = C::SPLIT, FOLD = C::FOLD, ONE_ROUND = C::ONE_ROUND;
-    constexpr bool RU2 = (N > T);        // some threads own two nodes of a group
-
-    extern __shared__ __align__(16) double lsmem[];
-    double *const smem = lsmem;
-    double *sU = smem + C::OFF_U, *sT = smem + C::OFF_T, *sA = smem + C::OFF_A;
-    double *sP = smem + C::OFF_P, *sF = smem + C::OFF_F;
-
-    int tid = threadIdx.x;      // refreshed at the top of every group iteration (see below)
-    const int ngroups = (P.elem_count + E - 1) / E;
-    const int64_t ndof = P.ndof;
-    const bool need_tmp = (P.mode == MODE_STAGE);
-    int g = blockIdx.x;
-    if (g >= ngroups) return;
-
-    // NV planes of the nodes of group gg: global -> shared.  16-byte copies that bypass L1
-    // (cp.async.cg) when the planes are 16-byte aligned -- the streaming data then does not evict
-    // the few local-memory lines of the kernel from L1 -- else 8-byte copies.
-    const bool wide = ((ndof & 1) == 0) && (((int64_t)P.elem_first * NPTS & 1) == 0) && ((N & 1) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(P.u_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.tmp) & 15) == 0);
-    // the same alignment for the 128-bit stores of phase 3
-    const bool wide3 = wide && ((reinterpret_cast<uintptr_t>(P.u_out) & 15) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(P.k_out) & 15) == 0) &&
-                       (CART || (reinterpret_cast<uintptr_t>(P.jac) & 15) == 0);
-    auto issue_planes = [&](const double *src, double *dst, int gg) {
-        const int nn = min(E, P.elem_count - gg * E) * NPTS;
-        const double *s0 = src + (int64_t)(P.elem_first + gg * E) * NPTS;
-        if (wide && (nn & 1) == 0) {
-            for (int n = 2 * tid; n < nn; n += 2 * T) {
-#pragma unroll
-                for (int v = 0; v < NV; v++) cp_async16(dst + v * N + n, s0 + n + ndof * v);
-            }
-        } else {
-            for (int n = tid; n < nn; n += T) {
-#pragma unroll
-                for (int v = 0; v < NV; v++) cp_async8(dst + v * N + n, s0 + n + ndof * v);
-            }
-        }
-    };
-    // face connectivity (flux slot, master flag, orientation) of the elements of group gg ->
-    // shared memory, one 8-byte record per (element, local face); staged one group ahead so that
-    // neither the load latency nor registers holding the records cross the line phase
-    int2 *sEC = reinterpret_cast<int2 *>(smem + C::OFF_EC);
-    auto issue_ec = [&](int gg, int buf) {
-        const int nrec = min(E, P.elem_count - gg * E) * NFACES;
-        if (tid < nrec)
-            cp_async8(reinterpret_cast<double *>(sEC + buf * (E * NFACES) + tid),
-                      reinterpret_cast<const double *>(P.econn + (int64_t)(P.elem_first + gg * E) * NFACES + tid));
-    };
-    // face fluxes of a line (surface_contribution!): Fn is the master-outward flux in the
-    // master's face-dof order; the slave side sees it negated and permuted.  Column `task` of
-    // sF belongs to the thread that owns the line, so no barrier is needed, only wait_group.
-    auto issue_fn = [&](int task, const int2 *ec) {
-        const int el = task / NLINES, r_ = task - el * NLINES;
-        const int d = r_ / NFP, k = r_ - d * NFP;
-        const int2 ecL = ec[el * NFACES + 2 * d], ecR = ec[el * NFACES + 2 * d + 1];
-        const int iL = (ecL.y & 1) ? k : slave2master<ND, NP>(k, (ecL.y >> 1) & 7);
-        const int iR = (ecR.y & 1) ? k : slave2master<ND, NP>(k, (ecR.y >> 1) & 7);
-        const double *sL = P.Fn + (int64_t)ecL.x * (NV * NFP) + iL;
-        const double *sR = P.Fn + (int64_t)ecR.x * (NV * NFP) + iR;
-#pragma unroll
-        for (int v = 0; v < NV; v++) {
-            // FOLD mode handles the momentum components in cyclic order starting at d
-            int vv = v;
-            if (FOLD && EQ == EQ_EULER && v >= 1 && v <= ND) { const int s_ = d + v - 1; vv = 1 + (s_ >= ND ? s_ - ND : s_); }
-            cp_async8(sF + v * LT + task, sL + vv * NFP);
-            cp_async8(sF + (NV + v) * LT + task, sR + vv * NFP);
-        }
-        sF[(2 * NV) * LT + task] = (ecL.y & 1) ? 1.0 : -1.0;
-        sF[(2 * NV + 1) * LT + task] = (ecR.y & 1) ? 1.0 : -1.0;
-    };
-
-    // ---------------- prologue: state of the first group, connectivity of its lines
-    issue_planes(P.u_in, sU, g);
-    cp_async_commit();
-    issue_ec(g, 0);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-
-    for (int cur = 0; g < ngroups; g += gridDim.x, cur ^= 1) {
-        // thread index re-read every iteration: everything derived from it (line number, face-dof
-        // permutations, copy addresses) is then recomputed with a few integer instructions instead
-        // of living across the line phase, where the spills of such loop invariants cost two
-        // ~300-cycle local-memory round trips per iteration (ncu: 7 % of the kernel)
-        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-        const int nact = min(E, P.elem_count - g * E);
-        const int nn = nact * NPTS, nl = nact * NLINES;
-        const int gn = g + gridDim.x;
-        const int64_t dof0 = (int64_t)(P.elem_first + g * E) * NPTS;
-        const double *U = sU + cur * (NV * N);
-
-        // ---------------- phase 1: node primitives -> shared memory.  Warps whose threads own two
-        // nodes of the group handle both at once (loads first, stores last)
-        if (RU2 && (tid & ~31) + T < nn) phase1_nodes<C, 2, T>(P, U, sA, tid, nn, dof0);
-        else phase1_nodes<C, 1, T>(P, U, sA, tid, nn, dof0);
-        __syncthreads();      // node data visible; every warp has left phase 3 of the previous group
-
-        // ---------------- issue: face fluxes and tmp of this group, state of the next group
-        for (int task = tid; task < nl; task += T) issue_fn(task, sEC + cur * (E * NFACES));
-        if (need_tmp) issue_planes(P.tmp, sT, g);
-        if (gn < ngroups) { issue_planes(P.u_in, sU + (cur ^ 1) * (NV * N), gn); issue_ec(gn, cur ^ 1); }
-        cp_async_commit();
-
-        // ---------------- phase 2: one tensor-product line per thread
-        for (int task = tid; task < nl; task += T) {
-            if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA && !C::NB) {
-                if (line_task<C, true>(P, sA, sP, sF, task, dof0)) line_task_exact<C>(P, sA, sP, sF, task, dof0);
-            } else {
-                line_task<C, false>(P, sA, sP, sF, task, dof0);
-            }
-        }
-        cp_async_wait<0>();    // this thread's share of tmp and of the next state has landed
-        __syncthreads();
-
-
-        // ---------------- phase 3: sum the directions, mass matrix, RK stage update
-        if (wide3 && (nn & 1) == 0) phase3_pairs<C, 1, T>(P, U, sT, sP, tid, nn, dof0, g);
-        else if (RU2 && (tid & ~31) + T < nn) phase3_nodes<C, 2, T>(P, U, sT, sP, tid, nn, dof0, g);
-        else phase3_nodes<C, 1, T>(P, U, sT, sP, tid, nn, dof0, g);
     }
 }
 

@@ -9,15 +9,17 @@
 //     wait fullU[i%3]            state of group i in shared memory
 //     phase 1                    node data -> sA[i&1]
 //     bar.sync 1, TL             node data visible to the line threads
-//     cp.async                   own face fluxes -> sF (own column)
-//     line task                  ... wait freeP (partial sums of group i-1 consumed) ... -> sP
+//     line task                  pair fluxes ... wait fullF (flux blocks of the group's faces) ... lift
+//                                ... wait freeP (partial sums of group i-1 consumed) ... -> sP
 //     arrive fullP
 //   update warp (tid >= TL), group i:
-//     wait fullP                 partial sums of group i complete
+//     wait fullP                 partial sums of group i complete (and sFn no longer read)
+//     TMA                        flux blocks of the faces of group i+1 -> sFn, one bulk copy per face
+//                                slot (a lane each), complete_tx on fullF
 //     phase 3                    sP, sT, sU[i%3] -> tmp, u_out, traces
 //     arrive freeP
-//     cp.async                   tmp of group i+1 -> sT, state of group i+3 -> sU[i%3], arrive-on-
-//                                completion at fullU[i%3]
+//     TMA / cp.async             tmp of group i+1 -> sT, state of group i+3 -> sU[i%3], completion
+//                                on fullT / fullU[i%3]
 // Every mbarrier is one phase ahead of its waiters at most (see the ordering argument in
 // profiles/r1_kernel_notes.md), so single-bit parities are safe.
 #pragma once
@@ -31,16 +33,17 @@ line_kernel_ws(const __grid_constant__ KParams P)
 {
     constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
     constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NLINES = C::NLINES;
-    constexpr int E = C::E, TL = C::TL, N = C::N, LT = C::LT, NAUX = C::NAUX;
-    constexpr bool FOLD = C::FOLD;
+    constexpr int E = C::E, TL = C::TL, N = C::N, NAUX = C::NAUX;
     static_assert(C::WS, "line_kernel_ws needs the WS shared-memory layout");
 
     extern __shared__ __align__(16) double lsmem[];
     double *const smem = lsmem;
     double *sU = smem + C::OFF_U, *sT = smem + C::OFF_T, *sA = smem + C::OFF_A;
-    double *sP = smem + C::OFF_P, *sF = smem + C::OFF_F;
+    double *sP = smem + C::OFF_P, *sFn = smem + C::OFF_F;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem + C::OFF_BAR);
     const unsigned fullP = bar0 + 24, freeP = bar0 + 32;          // fullU[b] = bar0 + 8 b
+    const unsigned fullF = bar0 + 48;
+    constexpr int FNB = C::FNB;
 
     const int ngroups = (P.elem_count + E - 1) / E;
     const int64_t ndof = P.ndof;
@@ -61,6 +64,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
         mbar_init(fullP, TL);
         mbar_init(freeP, 32);
         mbar_init(fullT, 1);
+        mbar_init(fullF, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -86,9 +90,36 @@ line_kernel_ws(const __grid_constant__ KParams P)
                 if (bar != fullT) mbar_arrive_cp_async(bar);       // tmp: this warp's own wait_group
             }
         };
+        // Flux blocks of the faces of a group: the connectivity records {slot, side} of its
+        // (element, local face) pairs are read one group ahead into registers (a lane each), the
+        // block of every face slot then travels as one 16-byte aligned TMA bulk copy.
+        constexpr int RN = (E * NFACES + 31) / 32;
+        int slot_next[RN];
+        auto load_slots = [&](int gg) {
+            const int nrec = min(E, P.elem_count - gg * E) * NFACES;
+#pragma unroll
+            for (int q = 0; q < RN; q++) {
+                const int r = lane + 32 * q;
+                slot_next[q] = r < nrec ? __ldg(&P.econn[(int64_t)(P.elem_first + gg * E) * NFACES + r].x) : 0;
+            }
+        };
+        auto issue_fn = [&](int gg) {
+            const int nrec = min(E, P.elem_count - gg * E) * NFACES;
+            if (lane == 0) mbar_expect_tx(fullF, (unsigned)(nrec * FNB * sizeof(double)));
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < RN; q++) {
+                const int r = lane + 32 * q;
+                if (r < nrec)
+                    bulk_g2s_keep(sFn + r * FNB, P.Fn + (int64_t)slot_next[q] * FNB, (unsigned)(FNB * sizeof(double)), fullF);
+            }
+        };
         for (int i = 0; i < 3 && i < niter; i++) issue_planes(P.u_in, sU + i * (NV * N), g0 + i * gs, bar0 + 8 * i);
         if (need_tmp) issue_planes(P.tmp, sT, g0, fullT);
         cp_async_commit();
+        load_slots(g0);
+        issue_fn(g0);
+        if (niter > 1) load_slots(g0 + gs);
 
         for (int i = 0; i < niter; i++) {
             const int g = g0 + i * gs, ub = i % 3;
@@ -96,6 +127,12 @@ line_kernel_ws(const __grid_constant__ KParams P)
             const int64_t dof0 = (int64_t)(P.elem_first + g * E) * NPTS;
             double *U = sU + ub * (NV * N);
             mbar_wait(fullP, i & 1);
+            // every line thread is done with the flux blocks of group i: request those of group i+1
+            // (in flight behind phase 3 here and phase 1 + the pair fluxes of the line threads)
+            if (i + 1 < niter) {
+                issue_fn(g + gs);
+                if (i + 2 < niter) load_slots(g + 2 * gs);
+            }
             if (wide) {
                 mbar_wait(bar0 + 8 * ub, (i / 3) & 1);      // completed long ago: makes the TMA writes visible here
                 if (need_tmp) mbar_wait(fullT, i & 1);
@@ -128,26 +165,6 @@ line_kernel_ws(const __grid_constant__ KParams P)
             cp_async8(reinterpret_cast<double *>(sEC + buf * (E * NFACES) + t),
                       reinterpret_cast<const double *>(P.econn + (int64_t)(P.elem_first + gg * E) * NFACES + t));
     };
-    // face fluxes of a line: column `task` of sF belongs to the thread that owns the line
-    auto issue_fn = [&](int task, const int2 *ec) {
-        const int el = task / NLINES, r_ = task - el * NLINES;
-        const int d = r_ / NFP, k = r_ - d * NFP;
-        const int2 ecL = ec[el * NFACES + 2 * d], ecR = ec[el * NFACES + 2 * d + 1];
-        const int iL = (ecL.y & 1) ? k : slave2master<ND, NP>(k, (ecL.y >> 1) & 7);
-        const int iR = (ecR.y & 1) ? k : slave2master<ND, NP>(k, (ecR.y >> 1) & 7);
-        const double *sL = P.Fn + (int64_t)ecL.x * (NV * NFP) + iL;
-        const double *sR = P.Fn + (int64_t)ecR.x * (NV * NFP) + iR;
-#pragma unroll
-        for (int v = 0; v < NV; v++) {
-            int vv = v;     // FOLD mode handles the momentum components in cyclic order starting at d
-            if (FOLD && EQ == EQ_EULER && v >= 1 && v <= ND) { const int s_ = d + v - 1; vv = 1 + (s_ >= ND ? s_ - ND : s_); }
-            cp_async8(sF + v * LT + task, sL + vv * NFP);
-            cp_async8(sF + (NV + v) * LT + task, sR + vv * NFP);
-        }
-        sF[(2 * NV) * LT + task] = (ecL.y & 1) ? 1.0 : -1.0;
-        sF[(2 * NV + 1) * LT + task] = (ecR.y & 1) ? 1.0 : -1.0;
-    };
-
     int tid = threadIdx.x;
     issue_ec(g0, 0, tid);
     cp_async_commit();
@@ -170,17 +187,14 @@ line_kernel_ws(const __grid_constant__ KParams P)
         cp_async_wait<0>();          // connectivity records of this group (issued one iteration ago)
         asm volatile("bar.sync 1, %0;" ::"n"(TL) : "memory");
 
-        // ---------------- face fluxes of this group's lines
-        for (int task = tid; task < nl; task += TL) issue_fn(task, sEC + (i & 1) * (E * NFACES));
-        cp_async_commit();
-
         // ---------------- phase 2: one tensor-product line per thread
         const unsigned fb = i > 0 ? freeP : 0u, fpar = (unsigned)((i - 1) & 1);
+        const FaceSrc fs{sFn, sEC + (i & 1) * (E * NFACES), fullF, (unsigned)(i & 1)};
         for (int task = tid; task < nl; task += TL) {
             if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA && !C::NB) {
-                if (line_task<C, true>(P, A, sP, sF, task, dof0, fb, fpar)) line_task_exact<C>(P, A, sP, sF, task, dof0, fb, fpar);
+                if (line_task<C, true>(P, A, sP, fs, task, dof0, fb, fpar)) line_task_exact<C>(P, A, sP, fs, task, dof0, fb, fpar);
             } else {
-                line_task<C, false>(P, A, sP, sF, task, dof0, fb, fpar);
+                line_task<C, false>(P, A, sP, fs, task, dof0, fb, fpar);
             }
         }
         mbar_arrive(fullP);

@@ -48,6 +48,10 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __host__ __device__ constexpr int ipow_c(int b, int e) { return e <= 0 ? 1 : b * ipow_c(b, e - 1); }
+// Stride (in doubles) between the flux blocks Fn[slot][v][i] of consecutive face slots: nv*nfp
+// rounded up to an even count, so that every block starts on a 16-byte boundary and the element
+// kernel can fetch it with ONE TMA bulk copy (cp.async.bulk needs 16-byte addresses and sizes).
+__host__ __device__ constexpr int fn_block(int nv, int nfp) { return (nv * nfp + 1) & ~1; }
 
 enum : int { MODE_RHS = 0, MODE_STAGE = 1, MODE_STAGE_FIRST = 2 };
 enum : int { FK_INTERIOR = 0, FK_GHOST = 1, FK_BOUNDARY = 2 };
@@ -452,7 +456,7 @@ stage_kernel(const __grid_constant__ KParams P)
                 const bool master = ec.y & 1;
                 const int i = master ? k : slave2master<ND, NP>(k, (ec.y >> 1) & 7);
                 double *dst = sElem + (size_t)tel * C::PER_ELEM + C::FOFF + lf * NV * NFP + k;
-                const double *src = P.Fn + (int64_t)ec.x * (NV * NFP) + i;
+                const double *src = P.Fn + (int64_t)ec.x * fn_block(NV, NFP) + i;
 #pragma unroll
                 for (int v = 0; v < NV; v++) cp_async8(dst + v * NFP, src + v * NFP);
                 if (k == 0) sSign[tel * NFACES + lf] = master ? 1.0 : -1.0;

@@ -11,7 +11,7 @@ from .equations import (ChandrasekharAverage, EulerEquation, EulerInflowBC, Eule
                         HybridDivOperator, ScalarDissipation, SplitDivOperator, StdAverage, StrongDivOperator,
                         gaussian_bump, normal_shockwave, nvariables, soundvelocity, spatialdim,
                         vars_prim2cons)
-from .gmshmesh import RawMesh, UnstructuredMesh, read_msh, refine, write_msh
+from .gmshmesh import RawHexMesh, RawMesh, UnstructuredMesh, read_msh, refine, write_msh
 from .monitors import (MonitorOutput, get_cfl_callback, get_limiter, get_limiter_callback, get_monitor,
                        get_monitor_callback, list_limiters, list_monitors, make_callback_list)
 from .mesh import CartesianMesh, apply_periodicBCs, partition_offsets

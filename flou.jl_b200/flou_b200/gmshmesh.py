@@ -1,4 +1,6 @@
-"""UnstructuredMesh{2,Float64}(filename): MSH 4.1 (ASCII) quad meshes without libgmsh.
+"""UnstructuredMesh{2,Float64}(filename): MSH 4.1 (ASCII) quad meshes without libgmsh, and
+UnstructuredMesh{3,Float64} from hexahedral tables (`RawHexMesh`; `_facemap_3d`, GmshMesh.jl:311-393,
+face orientations 0..7).
 
 Mirrors `src/FlouCommon/GmshMesh.jl:37-172` and `_facemap_2d` (:254-309).  In the reference
 every id comes from libgmsh (Gmsh.jl v0.2.2 / gmsh_jll v4.10.2, third-party, not vendored):
@@ -172,14 +174,125 @@ def write_msh(raw, filename):
         fh.write("\n".join(out))
 
 
+class RawHexMesh:
+    """What libgmsh would hand to Flou for a hexahedral mesh: nodes by tag, hexes in order (gmsh
+    vertex order: 0-3 bottom counter-clockwise, 4-7 top), the boundary quads -- element tags
+    1..Nb in the order given -- with their surface entity, and the physical groups."""
+
+    def __init__(self, nodes, hexes, quads, quad_entity, groups):
+        self.nodes = np.ascontiguousarray(nodes, dtype=np.float64)        # (N, 3), row i = tag i+1
+        self.hexes = np.ascontiguousarray(hexes, dtype=np.int64)          # (ne, 8)
+        self.quads = np.ascontiguousarray(quads, dtype=np.int64).reshape(-1, 4)
+        self.quad_entity = np.ascontiguousarray(quad_entity, dtype=np.int64)
+        self.groups = groups
+
+
+# gmsh's local faces of a hexahedron (0-based vertices, MHexahedron order) re-ordered to Flou's
+# local faces [xi-, xi+, eta-, eta+, zeta-, zeta+] = gmsh faces [3, 4, 2, 5, 1, 6] (GmshMesh.jl:320-329),
+# each already permuted by `nodemap` (:333-340) so that the four corners run in the face-dof order of
+# that local face (first tangential index fastest)
+_HEX_FACE_CORNERS = np.array([[0, 3, 7, 4], [1, 2, 6, 5], [0, 1, 5, 4], [3, 2, 6, 7], [0, 1, 2, 3], [4, 5, 6, 7]])
+# gmsh visits the local faces in ITS order when it hands out new face tags
+_GMSH_VISIT = [4, 2, 0, 1, 3, 5]          # Flou local faces in gmsh order 1..6
+# orientation code from the positions (0-based) of the master's first two corners in the slave's list
+_ORIENT = {(0, 1): 0, (0, 3): 4, (1, 2): 1, (1, 0): 5, (2, 3): 2, (2, 1): 6, (3, 0): 3, (3, 2): 7}
+
+
+class _HexMesh:
+    """UnstructuredMesh(3, RawHexMesh): the tables of `UnstructuredMesh{3,Float64}` (GmshMesh.jl:49-172
+    with `_facemap_3d`, :311-393).  Face ids follow the same rule as in 2-D: boundary quads keep
+    their element tags 1..Nb, interior faces are numbered by first appearance walking the hexes in
+    order and their faces in gmsh's local order (create_faces(); parity unpinned)."""
+
+    cartesian = False
+    nd = 3
+
+    def __init__(self, raw):
+        self.raw, self.nodes, self.nodeinds = raw, raw.nodes, raw.hexes
+        ne, nb = len(raw.hexes), len(raw.quads)
+        corners = raw.hexes[:, _HEX_FACE_CORNERS]                       # (ne, 6, 4) node tags
+        keys = np.sort(corners, axis=2)
+        tags = {tuple(k): i + 1 for i, k in enumerate(np.sort(raw.quads, axis=1).tolist())}
+        if len(tags) != nb:
+            raise ValueError("duplicated boundary quad")
+        faceinds = np.zeros((ne, 6), dtype=np.int64)
+        owner = {}                                                       # tag -> [(element, local face)]
+        for e in range(ne):
+            for lf in _GMSH_VISIT:
+                k = tuple(keys[e, lf].tolist())
+                t = tags.get(k)
+                if t is None:
+                    t = tags[k] = len(tags) + 1
+                faceinds[e, lf] = t
+                owner.setdefault(t, []).append((e, lf))
+        nf = len(tags)
+        eleminds = np.zeros((nf, 2), dtype=np.int64)
+        elempos = np.zeros((nf, 2), dtype=np.int64)
+        orientation = np.zeros(nf, dtype=np.uint8)
+        self.face_nodeinds = np.zeros((nf, 4), dtype=np.int64)
+        for t in range(1, nf + 1):
+            own = owner.get(t)
+            if not own:
+                raise ValueError("a boundary quad does not coincide with an element face")
+            if len(own) > 2:
+                raise ValueError("a face is shared by more than two elements")
+            (em, lm) = own[0]
+            eleminds[t - 1, 0], elempos[t - 1, 0] = em + 1, lm + 1
+            first = corners[em, lm]
+            self.face_nodeinds[t - 1] = first
+            if len(own) == 2:
+                (es, ls) = own[1]
+                eleminds[t - 1, 1], elempos[t - 1, 1] = es + 1, ls + 1
+                second = corners[es, ls].tolist()
+                orientation[t - 1] = _ORIENT[(second.index(first[0]), second.index(first[1]))]
+        self.faceinds, self.eleminds, self.elempos, self.orientation = faceinds, eleminds, elempos, orientation
+        self.facepos = np.where(eleminds[faceinds - 1, 0] == np.arange(1, ne + 1)[:, None], 1, 2)
+        # an element that meets itself across a face is not representable (and not produced by gmsh)
+        interior = eleminds[:, 1] != 0
+        self.intfaces = np.nonzero(interior)[0].astype(np.int64) + 1
+        self.bdnames, self.bdfaces = [], []
+        for name, ents in raw.groups:
+            faces = []
+            for ent in ents:
+                faces.extend(sorted(int(t) + 1 for t in np.nonzero(raw.quad_entity == ent)[0]))
+            self.bdnames.append(name)
+            self.bdfaces.append(np.array(faces, dtype=np.int64))
+        self.bdmap = {i: i for i in range(1, len(self.bdfaces) + 1)}
+        self.periodic = {}
+        listed = np.concatenate(self.bdfaces) if self.bdfaces else np.zeros(0, dtype=np.int64)
+        if not np.array_equal(np.sort(listed), np.nonzero(~interior)[0] + 1):
+            raise ValueError("every boundary face must belong to exactly one physical group")
+
+    @property
+    def nelements(self):
+        return self.faceinds.shape[0]
+
+    @property
+    def nfaces(self):
+        return self.eleminds.shape[0]
+
+    def nboundaries(self):
+        return len(self.bdfaces)
+
+    def element_vertices(self):
+        return self.nodes[self.nodeinds - 1]
+
+
 class UnstructuredMesh:
-    """UnstructuredMesh(2, filename) == UnstructuredMesh{2,Float64}(filename)."""
+    """UnstructuredMesh(2, filename) == UnstructuredMesh{2,Float64}(filename);
+    UnstructuredMesh(3, RawHexMesh) builds the 3-D tables (no 3-D .msh reader on this path)."""
 
     cartesian = False
 
+    def __new__(cls, nd, source=None, refinement=1):
+        if nd == 3 and isinstance(source, RawHexMesh):
+            return _HexMesh(source)
+        return super().__new__(cls)
+
     def __init__(self, nd, source, refinement=1):
         if nd != 2:
-            raise ValueError("only 2-D quadrilateral meshes are imported on this path")
+            raise ValueError("only 2-D quadrilateral .msh files are imported on this path "
+                             "(3-D: pass a RawHexMesh)")
         raw = read_msh(source) if isinstance(source, str) else source
         raw = refine(raw, refinement)
         self.nd = 2

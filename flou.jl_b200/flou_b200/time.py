@@ -107,20 +107,42 @@ def timeintegrate(Q0, disc, equation, solver, tfinal, *, dt, adaptive=False, ali
     u0 = Q.copy(order="F") if (save_start or not alias_u0) else None
     if not alias_u0:
         Q = u0.copy(order="F")
+    # OrdinaryDiffEq with adaptive=false takes full steps of dt and shortens the last one so that it
+    # lands on tfinal (tstops); an explicit `nsteps` runs exactly that many full steps
+    last = 0.0
     if nsteps is None:
-        nsteps = int(round((tfinal - t0) / dt))
+        nsteps, last = _split_steps(t0, tfinal, dt)
     A, B, c = _tab(solver)
     _set_limiter(disc, solver)
     tic = _time.perf_counter()
     try:
-        L.check(L.lib().flou_b200_timeintegrate(disc.handle, _ptr(Q), solver.nstages, _ptr(A),
-                                                _ptr(B), _ptr(c), float(dt), float(t0),
-                                                int(nsteps)))
+        if last == 0.0:
+            L.check(L.lib().flou_b200_timeintegrate(disc.handle, _ptr(Q), solver.nstages, _ptr(A),
+                                                    _ptr(B), _ptr(c), float(dt), float(t0),
+                                                    int(nsteps)))
+        else:
+            disc.upload(Q)
+            for n, h, ts in ((nsteps, dt, t0), (1, last, t0 + nsteps * dt)):
+                L.check(L.lib().flou_b200_lsrk2n_advance(disc.handle, solver.nstages, _ptr(A), _ptr(B),
+                                                         _ptr(c), float(h), float(ts), int(n)))
+            disc.download(Q)
+            if disc.status() & 1:
+                raise L.DomainError("non-positive density/pressure or NaN (Simulation crashed!)")
     except L.DomainError:
         # FlouTime.jl:39-51: log and return `nothing` for the solution
         print("ERROR: Simulation crashed!")
         return None, _time.perf_counter() - tic
-    return Solution(u0, Q, t0, t0 + nsteps * dt), _time.perf_counter() - tic
+    return Solution(u0, Q, t0, t0 + nsteps * dt + last), _time.perf_counter() - tic
+
+
+def _split_steps(t0, tfinal, dt):
+    """(number of full steps of dt, length of the shortened last step or 0.0) from t0 to tfinal."""
+    r = (tfinal - t0) / dt
+    n = int(round(r))
+    if abs(r - n) <= 1e-9 * max(1.0, abs(r)):
+        return max(n, 0), 0.0
+    n = max(int(np.floor(r)), 0)
+    return n, (tfinal - t0) - n * dt
 
 
 class _Integrator:

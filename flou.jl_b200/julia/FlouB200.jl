@@ -223,16 +223,23 @@ function set_stage_limiter!(disc::B200Disc, lim::Union{B200StageLimiter,Nothing}
                 disc.handle, lim === nothing ? Int32(0) : Int32(1), lim === nothing ? 0.0 : lim.minval))
 end
 
-# 2N tableaus straight from the OrdinaryDiffEq solver objects' caches
-function tableau(solver::Union{ORK256,CarpenterKennedy2N54})
-    tab = OrdinaryDiffEq.alg_cache(solver, zeros(1), zeros(1), Float64, Float64, Float64,
-                                   zeros(1), zeros(1), nothing, 0.0, 0.0, 0.0, nothing, false,
-                                   Val(true)).tab
-    A = Float64[0.0; collect(tab.A2end)]
-    B = Float64[tab.B1; collect(tab.B2end)]
-    c = Float64[0.0; collect(tab.c2end)]
-    return A, B, c
-end
+# 2N tableaus of OrdinaryDiffEq's LowStorageRK2N solvers (A_1 = 0; tmp = A_s tmp + dt k, u += B_s tmp),
+# written out here so that the shim does not depend on the signature of the internal `alg_cache`:
+# ORK256 (Bernardini & Pirozzoli 2009, 5 stages, as tabulated by OrdinaryDiffEq v6.49.1) and
+# Carpenter & Kennedy (1994) 2N(5,4).  The same numbers as flou_b200/time.py, pinned by
+# tests/test_oracle_kat.py (Sod / Shockwave2D KATs, order conditions).
+tableau(::ORK256) = (
+    Float64[0.0, -1.0, -1.55798, -1.0, -0.45031],
+    Float64[0.2, 0.83204, 0.6, 0.35394, 0.2],
+    Float64[0.0, 0.2, 0.2, 0.8, 0.8])
+tableau(::CarpenterKennedy2N54) = (
+    Float64[0.0, -567301805773 / 1357537059087, -2404267990393 / 2016746695238,
+            -3550918686646 / 2091501179385, -1275806237668 / 842570457699],
+    Float64[1432997174477 / 9575080441755, 5161836677717 / 13612068292357,
+            1720146321549 / 2090206949498, 3134564353537 / 4481467310338,
+            2277821191437 / 14882151754819],
+    Float64[0.0, 1432997174477 / 9575080441755, 2526269341429 / 6820363962896,
+            2006345519317 / 3224310063776, 2802321613138 / 2924317926251])
 
 # timeintegrate(Q0, disc, equation, solver, tfinal; adaptive=false, dt, alias_u0=true)
 function timeintegrate(Q0::Matrix{Float64}, disc::B200Disc, equation,
@@ -243,19 +250,41 @@ function timeintegrate(Q0::Matrix{Float64}, disc::B200Disc, equation,
     set_stage_limiter!(disc, stage_limiter)
     A, B, c = tableau(solver)
     Q = alias_u0 ? Q0 : copy(Q0)
-    nsteps = round(Int64, tfinal / dt)
+    # adaptive=false: full steps of dt, the last one shortened so that it lands on tfinal (tstops)
+    r = tfinal / dt
+    nsteps = round(Int64, r)
+    last = 0.0
+    if abs(r - nsteps) > 1e-9 * max(1.0, abs(r))
+        nsteps = floor(Int64, r)
+        last = tfinal - nsteps * dt
+    end
+    advance(h, n) = ccall((:flou_b200_lsrk2n_advance, lib), Int32,
+                          (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                           Float64, Float64, Int64),
+                          disc.handle, Int32(length(B)), A, B, c, Float64(h), 0.0, Int64(n))
+    rc = Int32(0)
     exetime = @elapsed begin
-        rc = ccall((:flou_b200_timeintegrate, lib), Int32,
-                   (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-                    Float64, Float64, Int64),
-                   disc.handle, Q, Int32(length(B)), A, B, c, Float64(dt), 0.0, nsteps)
+        if last == 0.0
+            rc = ccall((:flou_b200_timeintegrate, lib), Int32,
+                       (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                        Float64, Float64, Int64),
+                       disc.handle, Q, Int32(length(B)), A, B, c, Float64(dt), 0.0, nsteps)
+        else
+            rc = ccall((:flou_b200_upload_state, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), disc.handle, Q)
+            rc == 0 && (rc = advance(dt, nsteps))
+            rc == 0 && (rc = advance(last, 1))
+            rc == 0 && (rc = ccall((:flou_b200_download_state, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), disc.handle, Q))
+            flags = Ref{Int32}(0)
+            rc == 0 && (rc = ccall((:flou_b200_status, lib), Int32, (Ptr{Cvoid}, Ref{Int32}), disc.handle, flags))
+            rc == 0 && (flags[] & 1) != 0 && (rc = Int32(4))
+        end
     end
     if rc == 4                       # FLOU_B200_EDOMAIN, cf. FlouTime.jl:39-51
         @error "Simulation crashed!"
         return (nothing, exetime)
     end
     check(rc)
-    return ((u=[Q], t=[nsteps * dt]), exetime)
+    return ((u=[Q], t=[tfinal]), exetime)
 end
 
 end # module

@@ -199,7 +199,9 @@ int32_t flou_b200_timeintegrate(flou_b200_handle *h, double *Q, int32_t nstages,
 /* get_max_dt(q, disc, equation, cfl) (MultielementDiscontinuous.jl:162-178 with the
  * per-node rule of FlouCommon/Euler.jl:116-135 / LinearAdvection.jl:46-48): the global minimum
  * of cfl*dx/(|v| + c), dx = (volume/npts)^(1/nd), over the device-resident state (Q == NULL) or
- * an uploaded one; an ncclAllReduce(min) joins the ranks of a partitioned run.  Row f1. */
+ * an explicit host state, which is staged in a scratch buffer: the device-resident state of an
+ * ongoing advance() is never replaced by a query (the same holds for _monitor and _zhang_shu);
+ * an ncclAllReduce(min) joins the ranks of a partitioned run.  Row f1. */
 int32_t flou_b200_max_dt(flou_b200_handle *h, const double *Q, double cfl, double *dt);
 
 /* ---- monitors and limiters ------------------------------------------ */
@@ -212,7 +214,8 @@ int32_t flou_b200_max_dt(flou_b200_handle *h, const double *Q, double cfl, doubl
 int32_t flou_b200_monitor(flou_b200_handle *h, int32_t kind, const double *Q, double *value);
 /* get_limiter(disc, eq, :zhang_shu, minval) (Equations/Euler.jl:597-660): positivity limiter of
  * Zhang & Shu, element by element.  Q == NULL: the device-resident state, in place; otherwise Q
- * (host, owned rows) is uploaded, limited and written back. */
+ * (host, owned rows) is staged in a scratch buffer, limited and written back (the device-resident
+ * state is not touched). */
 int32_t flou_b200_zhang_shu(flou_b200_handle *h, double *Q, double minval);
 /* ORK256(stage_limiter! = get_limiter_callback(dg, eq, :zhang_shu, minval)) as in
  * examples/src/3D_Euler.jl:76-80: flou_b200_lsrk2n_advance / _timeintegrate apply the limiter to

@@ -94,8 +94,20 @@ def lib():
         _LIB.oracle_lsrk2n.restype = None
         _LIB.oracle_max_dt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         _LIB.oracle_max_dt.restype = C.c_double
+        _LIB.oracle_set_threads.argtypes = [C.c_int]
+        _LIB.oracle_set_threads.restype = None
+        _LIB.oracle_max_threads.restype = C.c_int
         assert _LIB.oracle_sizeof_problem() == C.sizeof(_Problem)
     return _LIB
+
+
+def set_threads(n):
+    """OpenMP threads of the sweeps (bench.py: all host cores, whatever OMP_NUM_THREADS says)."""
+    lib().oracle_set_threads(int(n))
+
+
+def max_threads():
+    return int(lib().oracle_max_threads())
 
 
 def _ptr(a):

@@ -127,3 +127,82 @@ def unstructured_mesh_2d(filename=None, parsed=None):
                 {i: i for i in range(1, len(bdfaces) + 1)})
     mesh.enodes = elemnodes
     return mesh
+
+
+# gmsh's local faces of an 8-node hexahedron (MHexahedron, 0-based vertex numbers), the order in
+# which get_element_face_nodes(etype, 4) lists them
+_GMSH_HEX_FACES = ((0, 3, 2, 1), (0, 1, 5, 4), (0, 4, 7, 3), (1, 2, 6, 5), (2, 3, 7, 6), (4, 5, 6, 7))
+
+
+def unstructured_mesh_3d(nodes, hexes, quads, quad_entity, groups):
+    """Literal restatement of `UnstructuredMesh{3,Float64}()` (GmshMesh.jl:49-172) and
+    `_facemap_3d` (:311-393) for hexahedral meshes given as tables: `nodes` (N, 3) by tag, `hexes`
+    node tags in gmsh order, boundary `quads` (tags 1..Nb in the order given) with their surface
+    entity, `groups` [(name, [entities])].  libgmsh's `create_faces()` numbering is restated by the
+    same rule as in 2-D: boundary elements first, then element faces by first appearance (gmsh
+    local face order).  Parity unpinned (no reference test loads a mesh)."""
+    nodes = np.asarray(nodes, dtype=float)
+    elemnodes = [list(map(int, h)) for h in hexes]
+    numelements = len(elemnodes)
+    face_tag = {}
+    for q in quads:
+        key = frozenset(int(v) for v in q)
+        if key in face_tag:
+            raise ValueError("duplicated boundary quad")
+        face_tag[key] = len(face_tag) + 1
+    ntags, ftags = [], []               # get_element_face_nodes(etype, 4) / get_faces(4, ntags)
+    for en in elemnodes:
+        for loc in _GMSH_HEX_FACES:
+            fn = [en[v] for v in loc]
+            ntags += fn
+            key = frozenset(fn)
+            if key not in face_tag:
+                face_tag[key] = len(face_tag) + 1
+            ftags.append(face_tag[key])
+    # _facemap_3d, 1-based arithmetic kept
+    element2face = {}
+    cnt = 0
+    for i in range(1, numelements + 1):
+        element2face[i] = [ftags[cnt + 3 - 1], ftags[cnt + 4 - 1], ftags[cnt + 2 - 1],
+                           ftags[cnt + 5 - 1], ftags[cnt + 1 - 1], ftags[cnt + 6 - 1]]
+        cnt += 6
+    nodemap = ((1, 4, 3, 2), (1, 2, 3, 4), (1, 4, 3, 2), (1, 2, 3, 4), (2, 1, 4, 3), (1, 2, 3, 4))
+    face2element, face2node, f2n_second = {}, {}, {}
+    cnt = 0
+    for i, ftag in enumerate(ftags, start=1):
+        ielem = (i - 1) // 6 + 1
+        pos = (i - 1) % 6 + 1
+        four = [ntags[cnt + m - 1] for m in nodemap[pos - 1]]
+        if ftag in face2element:
+            face2element[ftag][1] = ielem
+            f2n_second[ftag] = four
+        else:
+            face2element[ftag] = [ielem, 0]
+            face2node[ftag] = four
+        cnt += 4
+    orientations = {t: 0 for t in face2node}
+    table = {(1, 2): 0, (1, 4): 4, (2, 3): 1, (2, 1): 5, (3, 4): 2, (3, 2): 6, (4, 1): 3, (4, 3): 7}
+    for iface, nodes2 in f2n_second.items():
+        n1, n2 = face2node[iface][0], face2node[iface][1]
+        orientations[iface] = table[(nodes2.index(n1) + 1, nodes2.index(n2) + 1)]
+    faceinds, eleminds = element2face, face2element
+    numfaces = len(eleminds)
+    intfaces = sorted(i for i, f in eleminds.items() if f[1] != 0)
+    bdnames, bdfaces = [], []
+    quad_entity = [int(e) for e in quad_entity]
+    for name, ents in groups:
+        bdnames.append(name)
+        faces = []
+        for entity in ents:
+            faces += sorted(t + 1 for t, e in enumerate(quad_entity) if e == entity)
+        bdfaces.append(faces)
+    facepos = [[eleminds[f].index(i) + 1 for f in faceinds[i]] for i in range(1, numelements + 1)]
+    elempos = []
+    for i in range(1, numfaces + 1):
+        elempos.append([0 if ie == 0 else faceinds[ie].index(i) + 1 for ie in eleminds[i]])
+    mesh = Mesh(3, (), (), nodes, [faceinds[i] for i in range(1, numelements + 1)], facepos,
+                [list(eleminds[i]) for i in range(1, numfaces + 1)], elempos,
+                [orientations[i] for i in range(1, numfaces + 1)], intfaces, bdfaces, bdnames,
+                {i: i for i in range(1, len(bdfaces) + 1)})
+    mesh.enodes = elemnodes
+    return mesh

@@ -42,6 +42,7 @@
  * has `@flouthreads` (Polyester @batch).
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -960,3 +961,9 @@ double oracle_max_dt(const oracle_problem *P, const double *Q, const double *vol
 }
 
 int oracle_sizeof_problem(void) { return (int)sizeof(oracle_problem); }
+
+/* Thread count of the `parallel for` sweeps: set explicitly by bench.py (torchrun exports
+ * OMP_NUM_THREADS=1 to its workers, which would silently make the CPU baseline single-threaded)
+ * and read back for the `cores` field of the bench line. */
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_max_threads(void) { return omp_get_max_threads(); }

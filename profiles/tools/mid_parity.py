@@ -1,5 +1,6 @@
 """Development check (GPU box): a 3-D p=4 mesh large enough for several groups per persistent CTA
-(12^3 elements = 864 groups on 296 CTAs), RHS + 6 RK steps against the oracle, with the library
+(12x12x13 elements by default: several groups per CTA and, for even element counts per group, a
+tail group; usage: mid_parity.py [n [np]]), RHS + 6 RK steps against the oracle, with the library
 selected by FLOU_B200_LIB."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,7 +11,8 @@ import flou_b200 as F
 import oracle as O
 from common import Case, relerr, smooth_state, random_state
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-case = Case(3, (n, n, n), 5)
+npn = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+case = Case(3, (n, n, n + 1), npn)
 orc = case.oracle(); disc, eq = case.product()
 Q = random_state(orc.ndof, 3, "euler", amp=0.2)
 dQ = disc.new_state(); F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)

@@ -1,0 +1,110 @@
+"""GPU parity at production shapes: meshes large enough that every persistent CTA of the element
+kernel walks over SEVERAL element groups (state ring reuse, mbarrier parity flips, freeP
+back-pressure), with a tail group behind full ones and the non-TMA copy path (odd plane sizes)
+over several iterations -- the steady-state pipeline the small cases of test_parity_gpu.py
+(niter = 1 everywhere) never enter.  BASELINE.json configs 2, 3 and 5 at (or near) size.
+
+Same bar as the small cases: RHS within 1e-12 of max|dQ| (oracle = CPU restatement of
+Hyperbolic.jl:31-69), state after 5 ORK256 steps within 1e-10; seeded random and smooth states.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from common import Case, random_state, relerr, smooth_state
+
+RHS_TOL = 1e-12
+STATE_TOL = 1e-10
+EC = dict(nodes="GLL", eq="euler", op="split", nf="mat", avg="cha")
+
+# (case, what it exercises)
+PRODUCTION = [
+    # 3-D p=4 (config 4 instance LCfg<3,5,...>): 864 groups of 2 elements on 296 persistent CTAs
+    (Case(3, (12, 12, 12), 5, **EC), "niter>=2 per CTA, TMA plane copies"),
+    # odd element count: tail group with one element, odd plane size -> 8-byte cp.async path
+    # (no TMA, phase3_nodes) over several iterations
+    (Case(3, (11, 11, 13), 5, **EC), "tail group, non-wide copy path"),
+    # 3-D p=3 (config 3 instance): even planes with an odd element count -> tail group on the TMA path
+    (Case(3, (23, 23, 25), 4, **EC), "tail group on the wide path, niter>=8"),
+    (Case(3, (24, 24, 24), 4, **EC), "niter>=9 per CTA"),
+    # config 3 at size
+    (Case(3, (32, 32, 32), 4, **EC), "BASELINE config 3 at size"),
+    # config 2 at size: 2-D p=4, 16384 elements in groups of 12 (tail of 4)
+    (Case(2, (128, 128), 5, **EC), "BASELINE config 2 at size"),
+    # strong form + LxF at a multi-iteration size (config 1 family, advection and Euler)
+    (Case(2, (200, 180), 4, nodes="GLL", eq="adv", op="strong", nf="lxf", avg="std"), "config 1 family, many groups"),
+    (Case(3, (14, 13, 12), 4, nodes="GLL", eq="euler", op="strong", nf="lxf", avg="std"), "strong form, many groups"),
+    # general (per-node metric) geometry at a multi-iteration size
+    (Case(3, (12, 11, 12), 4, perturb_amp=0.08, periodic=[], bcs={str(i): ("slip", None) for i in range(1, 7)},
+          **EC), "curved 3-D mesh, several groups per CTA"),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,why", PRODUCTION, ids=[repr(c) for c, _ in PRODUCTION])
+@pytest.mark.parametrize("state", ["random", "smooth"])
+def test_rhs_at_production_shape(gpu, case, why, state):
+    import flou_b200 as F
+    orc = case.oracle()
+    disc, eq = case.product()
+    info = disc.kernel_info()
+    ngroups = -(-orc.ne // info["elems_per_cta_iter"])
+    assert ngroups > info["grid_ctas"], f"{why}: {ngroups} groups on {info['grid_ctas']} CTAs is not a multi-iteration case"
+    Q = (random_state(orc.ndof, case.nd, case.eq, amp=case.amp) if state == "random"
+         else smooth_state(orc.coords, case.nd, case.eq))
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert np.all(np.isfinite(dQ))
+    assert relerr(dQ, orc.rhs(Q)) <= RHS_TOL
+    disc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,why", PRODUCTION[:6], ids=[repr(c) for c, _ in PRODUCTION[:6]])
+def test_state_after_5_steps_at_production_shape(gpu, case, why):
+    """Five ORK256 steps (25 fused stage passes: ping-pong buffers, traces written by the stage
+    kernel, CUDA-graph replay of two steps + one direct step) against the oracle's 2N loop."""
+    import flou_b200 as F
+    import oracle as O
+    orc = case.oracle()
+    disc, eq = case.product()
+    # smooth field + node-to-node noise (a convex combination of admissible states is admissible)
+    Q = np.asfortranarray(0.9 * smooth_state(orc.coords, case.nd, case.eq)
+                          + 0.1 * random_state(orc.ndof, case.nd, case.eq, amp=0.3))
+    dt = 2e-5
+    ref = orc.lsrk2n(Q, O.ORK256, dt, 5)
+    u = Q.copy(order="F")
+    sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), 5 * dt, dt=dt)
+    assert sol is not None
+    assert relerr(sol.u[-1], ref) <= STATE_TOL
+    disc.close()
+
+
+@pytest.mark.gpu
+def test_config5_refined_8x8(gpu, tmp_path):
+    """BASELINE config 5: the reference's 2D_cylinder mesh (committed tables) refined 8x8 (4672
+    quads, p=5, slip walls + inflow/outflow): RHS and 5 RK steps against the oracle."""
+    import flou_b200 as F
+    import oracle as O
+    from unstructured import build_pair, euler_bcs
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cylinder_p5.npz"), allow_pickle=False)
+    groups = [(str(n), [int(v) for v in str(e).split(",")])
+              for n, e in zip(g["group_names"], g["group_entities"])]
+    raw = F.RawMesh(g["nodes"], g["quads"], g["lines"], g["line_tags"], g["line_entity"], groups)
+    path = str(tmp_path / "cylinder_r8.msh")
+    F.write_msh(F.refine(raw, 8), path)
+    orc, disc, eq = build_pair(path, 6, euler_bcs([n for n, _ in groups]))
+    info = disc.kernel_info()
+    assert -(-orc.ne // info["elems_per_cta_iter"]) > info["grid_ctas"]
+    Q = np.asfortranarray(np.tile(np.array([1.0, 0.45, 0.05, 2.8]), (orc.ndof, 1)))
+    Q += 0.02 * random_state(orc.ndof, 2, "euler", amp=0.3)
+    dQ = disc.new_state()
+    F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+    assert relerr(dQ, orc.rhs(Q)) <= RHS_TOL
+    dt = 2e-6
+    ref = orc.lsrk2n(Q, O.ORK256, dt, 5)
+    u = Q.copy(order="F")
+    sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), 5 * dt, dt=dt)
+    assert sol is not None and relerr(sol.u[-1], ref) <= STATE_TOL
+    disc.close()
