@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <map>
@@ -398,6 +399,12 @@ struct flou_b200_handle {
     int2 *econn = nullptr;
     double *Fn = nullptr;
     int n_faces = 0, n_faces_local_only = 0;
+    // source term (row a13) and boundary data that change between stages
+    double *source = nullptr;            // [dof + ndof*v], allocated by the first flou_b200_set_source
+    int64_t bc_rows = 0;                 // rows (boundary-face nodes) of bc_table
+    int *bd_list = nullptr;              // owned boundary faces: local element*2nd + local face
+    std::vector<int64_t> bd_ordinal;     // ... and their ordinal m in the concatenated bc_faces
+    double *bd_traces = nullptr;         // [owned boundary face][v][k]
 };
 
 namespace {
@@ -859,6 +866,9 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         for (int k : kinds) { need_table |= k == FLOU_B200_BC_TABLE; need_state |= k == FLOU_B200_BC_INFLOW; }
         if ((need_table && table.empty()) || (need_state && state.empty()))
             { flou_b200_destroy(h); return fail(FLOU_B200_EINVAL, "boundary-condition data missing"); }
+        // full-size table even when no boundary is tabulated yet (flou_b200_set_bc_table)
+        if (d->nbound > 0 && table.empty())
+            table.assign((size_t)d->bc_offsets[d->nbound] * h->nfp * d->nv, 0.0);
         H_TRY(upload(&h->bc_kind, kinds));
         H_TRY(upload(&h->bc_state, state));
         H_TRY(upload(&h->bc_table, table));
@@ -909,6 +919,26 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, h->device);
         h->mon_blocks = sms_ * 4;
         H_TRY(cudaMalloc((void **)&h->mon_partial, sizeof(double) * (size_t)(h->mon_blocks + 1)));
+    }
+    {
+        // owned boundary faces in bc_faces order (flou_b200_boundary_traces)
+        std::vector<int> bl;
+        for (int64_t le = 0; le < pl.ne_local; le++)
+            for (int lf = 0; lf < 2 * nd; lf++) {
+                const Conn &c = conn[(size_t)le * 2 * nd + lf];
+                if (((c.info >> 7) & 3) == FK_BOUNDARY) { bl.push_back((int)(le * 2 * nd + lf)); h->bd_ordinal.push_back(c.nbr); }
+            }
+        // sort by ordinal
+        std::vector<size_t> ord(bl.size());
+        for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return h->bd_ordinal[a] < h->bd_ordinal[b]; });
+        std::vector<int> bl2(bl.size());
+        std::vector<int64_t> bo2(bl.size());
+        for (size_t i = 0; i < ord.size(); i++) { bl2[i] = bl[ord[i]]; bo2[i] = h->bd_ordinal[ord[i]]; }
+        h->bd_ordinal.swap(bo2);
+        H_TRY(upload(&h->bd_list, bl2));
+        H_TRY(cudaMalloc((void **)&h->bd_traces, sizeof(double) * std::max<size_t>(bl2.size() * h->nfp * h->nv, 1)));
+        h->bc_rows = d->nbound > 0 ? d->bc_offsets[d->nbound] * (int64_t)h->nfp : 0;
     }
     H_TRY(upload(&h->send_list, send_list));
     H_TRY(upload(&h->interior_list, interior));
@@ -978,7 +1008,7 @@ int32_t flou_b200_destroy(flou_b200_handle *h)
     void *ptrs[] = {h->u[0], h->u[1], h->tr[0], h->tr[1], h->tr_all, h->tmp, h->k, h->conn, h->faceid, h->jac, h->metric, h->fjac,
                     h->frames, h->faces, h->econn, h->Fn, h->elem_dx, h->dt_bits, h->bc_kind, h->bc_state, h->bc_table, h->status, h->d_lm, h->d_lp,
                     h->ghost, h->sendbuf, h->send_list, h->interior_list, h->boundary_list, h->w_nodes, h->mon_partial,
-                    h->sub_frames, h->sub_jac};
+                    h->sub_frames, h->sub_jac, h->source, h->bd_list, h->bd_traces};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev_emit) cudaEventDestroy(h->ev_emit);
@@ -1150,10 +1180,14 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
     if (!h || !A || !B || nstages < 1 || nstages > 16 || nsteps < 0)
         return fail(FLOU_B200_EINVAL, "bad RK arguments");
     CUDA_TRY(cudaSetDevice(h->device));
-    // CUDA graph of two steps (2*nstages passes bring u back to the same ping-pong buffer);
-    // only for single-rank handles: NCCL calls are issued directly.
-    const bool use_graph = !(h->flags & FLOU_B200_FLAG_NO_GRAPH) && h->nranks == 1 && nsteps >= 4 &&
-                           !h->profile;
+    // CUDA graph of two steps (2*nstages passes bring u back to the same ping-pong buffer).
+    // Partitioned handles capture the halo exchange with it: the comm stream forks from the compute
+    // stream at the pack event and joins it at the receive event inside every pass, and NCCL's
+    // send/recv are capturable (every rank captures and replays the same sequence).
+    // FLOU_B200_MG_GRAPH=0 keeps partitioned handles on direct launches.
+    static const bool mg_graph = [] { const char *e = std::getenv("FLOU_B200_MG_GRAPH"); return !(e && e[0] == '0'); }();
+    const bool use_graph = !(h->flags & FLOU_B200_FLAG_NO_GRAPH) && nsteps >= 4 && !h->profile &&
+                           (h->nranks == 1 || h->nghost == 0 || (h->comm && mg_graph));
     int64_t done = 0;
     if (use_graph && !h->traces_valid) {
         // bring the traces of the current state up to date outside the captured region
@@ -1217,6 +1251,63 @@ int32_t flou_b200_timeintegrate(flou_b200_handle *h, double *Q, int32_t nstages,
     CUDA_TRY(cudaMemcpyAsync(&f, h->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (f & 1) return fail(FLOU_B200_EDOMAIN, "non-positive density/pressure or NaN (Simulation crashed!)");
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_set_source(flou_b200_handle *h, const double *S)
+{
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(double) * (size_t)h->ndof * h->nv;
+    const double *before = h->base.source;
+    if (S) {
+        if (!h->source) CUDA_TRY(cudaMalloc((void **)&h->source, bytes));
+        CUDA_TRY(cudaMemcpyAsync(h->source, S, bytes, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));      // the host buffer is borrowed for this call only
+        h->base.source = h->source;
+    } else {
+        h->base.source = nullptr;
+    }
+    if (h->base.source != before) destroy_graph(h);      // captured kernel parameters hold the pointer
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_set_bc_table(flou_b200_handle *h, const double *table)
+{
+    if (!h || !table) return fail(FLOU_B200_EINVAL, "null argument");
+    if (h->bc_rows <= 0) return fail(FLOU_B200_EINVAL, "the discretisation has no boundary faces");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->bc_table, table, sizeof(double) * (size_t)h->bc_rows * h->nv,
+                             cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_boundary_traces(flou_b200_handle *h, double *Qin, int64_t *ordinals, int64_t *count)
+{
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    const int64_t n = (int64_t)h->bd_ordinal.size();
+    if (count) *count = n;
+    if (ordinals) std::copy(h->bd_ordinal.begin(), h->bd_ordinal.end(), ordinals);
+    if (!Qin || n == 0) return FLOU_B200_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(h->emit->launch(h->u[h->cur], h->ndof, h->bd_list, (int)n, h->nfaces, h->base.colloc,
+                             h->d_lm, h->d_lp, h->bd_traces, h->stream));
+    h->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(Qin, h->bd_traces, sizeof(double) * (size_t)n * h->nfp * h->nv,
+                             cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_lsrk2n_stage(flou_b200_handle *h, double A, double B, double dt, int32_t first)
+{
+    if (!h) return fail(FLOU_B200_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int32_t rc = run_pass(h, first ? MODE_STAGE_FIRST : MODE_STAGE, A, B, dt, h->u[h->cur], h->u[h->cur ^ 1]);
+    if (rc) return rc;
+    h->cur ^= 1;
+    if (h->stage_limiter) return launch_zhang_shu(h, h->u[h->cur], h->limiter_minval);
     return FLOU_B200_OK;
 }
 

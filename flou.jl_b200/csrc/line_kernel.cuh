@@ -165,12 +165,13 @@ struct LCfg {
     // face-flux block of one face slot, [v][i] padded to a 16-byte multiple (one TMA bulk copy)
     static constexpr int FNB = fn_block(NV, NFP);
     // shared memory per element (doubles): state buffers, tmp, node data, partial sums, the
-    // flux blocks of its faces
-    static constexpr int PER_ELEM = ((NUB + 1) * NV + NAB * NAUX + NPART) * NPTS + NFACES * FNB;
+    // flux blocks of its faces (two sets: the blocks of a group are requested two groups ahead)
+    static constexpr int PER_ELEM = ((NUB + 1) * NV + NAB * NAUX + NPART) * NPTS + 2 * NFACES * FNB;
 #if defined(FLOU_LINE_E) && defined(FLOU_LINE_T)
     static constexpr int E = FLOU_LINE_E, TL = FLOU_LINE_T;
 #else
-    static constexpr int E = pick_et(NLINES, PER_ELEM, WS ? 108 : 96).e, TL = pick_et(NLINES, PER_ELEM, WS ? 108 : 96).t;
+    // 112 KB per CTA: two CTAs (+ 1 KB each the driver reserves) fill the 228 KB of an SM
+    static constexpr int E = pick_et(NLINES, PER_ELEM, 112).e, TL = pick_et(NLINES, PER_ELEM, 112).t;
 #endif
     static constexpr int T = WS ? TL + 32 : TL;           // threads per CTA
     static constexpr int N = E * NPTS;                    // nodes of a group = plane stride
@@ -182,8 +183,8 @@ struct LCfg {
     static constexpr int OFF_T = OFF_U + NUB * NV * N;    // [NV][N]         tmp
     static constexpr int OFF_A = OFF_T + NV * N;          // [NAB][NAUX][N]  node data
     static constexpr int OFF_P = OFF_A + NAB * NAUX * N;  // [ND*NV][N]      partial sums by direction
-    static constexpr int OFF_F = (OFF_P + NPART * N + 1) & ~1;  // [E*NFACES][FNB]  flux blocks of the group's faces (16-byte aligned)
-    static constexpr int OFF_EC = OFF_F + E * NFACES * FNB;     // [2][E*NFACES] int2: face connectivity of this / the next group
+    static constexpr int OFF_F = (OFF_P + NPART * N + 1) & ~1;  // [2][E*NFACES][FNB]  flux blocks of the faces of this / the next group (16-byte aligned)
+    static constexpr int OFF_EC = OFF_F + 2 * E * NFACES * FNB; // [2][E*NFACES] int2: face connectivity of this / the next group
     static constexpr int OFF_BAR = OFF_EC + 2 * E * NFACES;     // 8 mbarriers
     static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OFF_BAR + 8);
     static_assert(WS, "the line kernel exists in its warp-specialised form only");
@@ -192,7 +193,9 @@ struct LCfg {
 #ifdef FLOU_LINE_MINB
         FLOU_LINE_MINB;
 #else
-        (HYBRID || NP * (NAUX + NV) > 64) ? 1 : 2;
+        // light line tasks (3-D p=3: 163 registers) fit three CTAs per SM: cfg3 +12 % (profiles/r2_kernel_notes.md)
+        (HYBRID || NP * (NAUX + NV) > 64) ? 1
+        : (ND == 3 && NP * (NAUX + NV) <= 40 && 3 * (SMEM_BYTES + 1024) <= 233472 ? 3 : 2);
 #endif
 };
 
@@ -1091,14 +1094,18 @@ __device__ __forceinline__ void phase3_nodes(const KParams &P, const double *U, 
             const int n = n0 + u * T;
             if (n >= nn) break;
             const int64_t dof = dof0 + n;
+            // apply_sourceterm! (MultielementDiscontinuous.jl:139-146): tabulated source, after the mass matrix
+            double src[NV];
+#pragma unroll
+            for (int v = 0; v < NV; v++) src[v] = P.source ? __ldg(P.source + dof + ndof * v) : 0.0;
             if (P.mode == MODE_RHS) {
 #pragma unroll
-                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[u][v] * rjac[u];
+                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = fma(acc[u][v], rjac[u], src[v]);
             } else {
                 double un[NV];
 #pragma unroll
                 for (int v = 0; v < NV; v++) {
-                    const double kv = acc[u][v] * rjac[u];
+                    const double kv = fma(acc[u][v], rjac[u], src[v]);
                     const double t = need_tmp ? fma(P.dt, kv, P.rkA * tv[u][v]) : P.dt * kv;
                     P.tmp[dof + ndof * v] = t;
                     un[v] = fma(P.rkB, t, uv[u][v]);
@@ -1166,16 +1173,22 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
             const int n = 2 * (p0 + r * T);
             if (n >= nn) break;
             const int64_t dof = dof0 + n;
+            // apply_sourceterm! (MultielementDiscontinuous.jl:139-146): tabulated source, after the
+            // mass matrix; a warp-uniform branch that the default (no source) never takes
+            double2 src[NV];
+#pragma unroll
+            for (int v = 0; v < NV; v++)
+                src[v] = P.source ? __ldg(reinterpret_cast<const double2 *>(P.source + dof + ndof * v)) : make_double2(0.0, 0.0);
             if (P.mode == MODE_RHS) {
 #pragma unroll
                 for (int v = 0; v < NV; v++)
                     __stcs(reinterpret_cast<double2 *>(P.k_out + dof + ndof * v),
-                           make_double2(acc[r][v].x * rjac[r].x, acc[r][v].y * rjac[r].y));
+                           make_double2(fma(acc[r][v].x, rjac[r].x, src[v].x), fma(acc[r][v].y, rjac[r].y, src[v].y)));
             } else {
                 double2 un[NV];
 #pragma unroll
                 for (int v = 0; v < NV; v++) {
-                    const double kx = acc[r][v].x * rjac[r].x, ky = acc[r][v].y * rjac[r].y;
+                    const double kx = fma(acc[r][v].x, rjac[r].x, src[v].x), ky = fma(acc[r][v].y, rjac[r].y, src[v].y);
                     double2 t;
                     t.x = need_tmp ? fma(P.dt, kx, P.rkA * tv[r][v].x) : P.dt * kx;
                     t.y = need_tmp ? fma(P.dt, ky, P.rkA * tv[r][v].y) : P.dt * ky;

@@ -13,9 +13,11 @@
 //                                ... wait freeP (partial sums of group i-1 consumed) ... -> sP
 //     arrive fullP
 //   update warp (tid >= TL), group i:
-//     wait fullP                 partial sums of group i complete (and sFn no longer read)
-//     TMA                        flux blocks of the faces of group i+1 -> sFn, one bulk copy per face
-//                                slot (a lane each), complete_tx on fullF
+//     wait fullP                 partial sums of group i complete (and sFn[i&1] no longer read)
+//     TMA                        flux blocks of the faces of group i+2 -> sFn[i&1], one bulk copy per
+//                                face slot (a lane each), complete_tx on fullF[i&1]; a full iteration
+//                                of lead (requested one group ahead they arrived late: 13 % of the
+//                                stall samples of the line threads were this wait)
 //     phase 3                    sP, sT, sU[i%3] -> tmp, u_out, traces
 //     arrive freeP
 //     TMA / cp.async             tmp of group i+1 -> sT, state of group i+3 -> sU[i%3], completion
@@ -42,8 +44,8 @@ line_kernel_ws(const __grid_constant__ KParams P)
     double *sP = smem + C::OFF_P, *sFn = smem + C::OFF_F;
     const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem + C::OFF_BAR);
     const unsigned fullP = bar0 + 24, freeP = bar0 + 32;          // fullU[b] = bar0 + 8 b
-    const unsigned fullF = bar0 + 48;
-    constexpr int FNB = C::FNB;
+    const unsigned fullF = bar0 + 48;                             // fullF[b] = bar0 + 48 + 8 b
+    constexpr int FNB = C::FNB, FSET = E * NFACES * FNB;
 
     const int ngroups = (P.elem_count + E - 1) / E;
     const int64_t ndof = P.ndof;
@@ -65,6 +67,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
         mbar_init(freeP, 32);
         mbar_init(fullT, 1);
         mbar_init(fullF, 1);
+        mbar_init(fullF + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -103,23 +106,25 @@ line_kernel_ws(const __grid_constant__ KParams P)
                 slot_next[q] = r < nrec ? __ldg(&P.econn[(int64_t)(P.elem_first + gg * E) * NFACES + r].x) : 0;
             }
         };
-        auto issue_fn = [&](int gg) {
+        auto issue_fn = [&](int gg, int buf) {
             const int nrec = min(E, P.elem_count - gg * E) * NFACES;
-            if (lane == 0) mbar_expect_tx(fullF, (unsigned)(nrec * FNB * sizeof(double)));
+            const unsigned bar = fullF + 8 * buf;
+            if (lane == 0) mbar_expect_tx(bar, (unsigned)(nrec * FNB * sizeof(double)));
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < RN; q++) {
                 const int r = lane + 32 * q;
                 if (r < nrec)
-                    bulk_g2s_keep(sFn + r * FNB, P.Fn + (int64_t)slot_next[q] * FNB, (unsigned)(FNB * sizeof(double)), fullF);
+                    bulk_g2s_keep(sFn + buf * FSET + r * FNB, P.Fn + (int64_t)slot_next[q] * FNB, (unsigned)(FNB * sizeof(double)), bar);
             }
         };
         for (int i = 0; i < 3 && i < niter; i++) issue_planes(P.u_in, sU + i * (NV * N), g0 + i * gs, bar0 + 8 * i);
         if (need_tmp) issue_planes(P.tmp, sT, g0, fullT);
         cp_async_commit();
         load_slots(g0);
-        issue_fn(g0);
-        if (niter > 1) load_slots(g0 + gs);
+        issue_fn(g0, 0);
+        if (niter > 1) { load_slots(g0 + gs); issue_fn(g0 + gs, 1); }
+        if (niter > 2) load_slots(g0 + 2 * gs);
 
         for (int i = 0; i < niter; i++) {
             const int g = g0 + i * gs, ub = i % 3;
@@ -127,11 +132,11 @@ line_kernel_ws(const __grid_constant__ KParams P)
             const int64_t dof0 = (int64_t)(P.elem_first + g * E) * NPTS;
             double *U = sU + ub * (NV * N);
             mbar_wait(fullP, i & 1);
-            // every line thread is done with the flux blocks of group i: request those of group i+1
-            // (in flight behind phase 3 here and phase 1 + the pair fluxes of the line threads)
-            if (i + 1 < niter) {
-                issue_fn(g + gs);
-                if (i + 2 < niter) load_slots(g + 2 * gs);
+            // every line thread is done with the flux blocks of group i: their buffer takes those of
+            // group i+2 (in flight during a whole iteration of the line threads)
+            if (i + 2 < niter) {
+                issue_fn(g + 2 * gs, i & 1);
+                if (i + 3 < niter) load_slots(g + 3 * gs);
             }
             if (wide) {
                 mbar_wait(bar0 + 8 * ub, (i / 3) & 1);      // completed long ago: makes the TMA writes visible here
@@ -189,7 +194,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
 
         // ---------------- phase 2: one tensor-product line per thread
         const unsigned fb = i > 0 ? freeP : 0u, fpar = (unsigned)((i - 1) & 1);
-        const FaceSrc fs{sFn, sEC + (i & 1) * (E * NFACES), fullF, (unsigned)(i & 1)};
+        const FaceSrc fs{sFn + (i & 1) * FSET, sEC + (i & 1) * (E * NFACES), fullF + 8 * (i & 1), (unsigned)((i >> 1) & 1)};
         for (int task = tid; task < nl; task += TL) {
             if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA && !C::NB) {
                 if (line_task<C, true>(P, A, sP, fs, task, dof0, fb, fpar)) line_task_exact<C>(P, A, sP, fs, task, dof0, fb, fpar);

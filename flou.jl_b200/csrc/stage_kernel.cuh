@@ -137,6 +137,9 @@ struct KParams {
     double *u_out;
     double *tmp;
     double *k_out;
+    // apply_sourceterm! (MultielementDiscontinuous.jl:139-146): S(x, t[, Q]) tabulated per node,
+    // added to dQ after the mass matrix; nullptr = the reference's default no-op source
+    const double *source;       // [dof + ndof*v]
     int64_t ndof;               // local dofs = plane stride of the state
     int elem_first, elem_count;
     const int *elem_list;       // optional indirection
@@ -859,13 +862,16 @@ stage_kernel(const __grid_constant__ KParams P)
             }
             // mass matrix: dQ / jac (Diagonal ldiv!, MultielementDiscontinuous.jl:132-137)
             const double rjac = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof));
+            double src[NV];
+#pragma unroll
+            for (int v = 0; v < NV; v++) src[v] = P.source ? __ldg(P.source + dof + ndof * v) : 0.0;
             if (P.mode == MODE_RHS) {
 #pragma unroll
-                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[v] * rjac;
+                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = fma(acc[v], rjac, src[v]);
             } else {
 #pragma unroll
                 for (int v = 0; v < NV; v++) {
-                    const double kv = acc[v] * rjac;
+                    const double kv = fma(acc[v], rjac, src[v]);
                     double t;
                     if (P.mode == MODE_STAGE_FIRST) t = P.dt * kv;
                     else t = fma(P.dt, kv, P.rkA * sT[v * NPTS + node]);

@@ -7,7 +7,7 @@ in include/flou_b200.h.  No CPU fallback exists.
 from ._lib import DomainError, FlouB200Error, LIB_PATH, device_count, lib
 from .disc import EquationConfig, MultielementDisc, nccl_unique_id, rhs
 from .equations import (ChandrasekharAverage, EulerEquation, EulerInflowBC, EulerOutflowBC,
-                        EulerSlipBC, GenericBC, LinearAdvection, LxF, MatrixDissipation,
+                        EulerSlipBC, Frame, GenericBC, LinearAdvection, Source, LxF, MatrixDissipation,
                         HybridDivOperator, ScalarDissipation, SplitDivOperator, StdAverage, StrongDivOperator,
                         gaussian_bump, normal_shockwave, nvariables, soundvelocity, spatialdim,
                         vars_prim2cons)

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib as L
 from . import geometry as G
-from .equations import GenericBC
+from .equations import Frame, GenericBC, Source, _DependsOn
 from .mesh import partition_offsets
 
 
@@ -31,8 +31,14 @@ class MultielementDisc:
     def __init__(self, mesh, std, equation, operators, bcs, source=None, *,
                  rank=0, nranks=1, device=None, geometry=None, use_graph=True, create=True,
                  fused=None, kernel=None):
-        if source is not None:
-            raise ValueError("source terms are not part of the B200 hot path (default no-op only)")
+        # source term (MultielementDiscontinuous.jl:75-79, 139-146): None = the default no-op;
+        # a plain callable f(Q_i, x_i, t) -> increment of dQ_i is treated as depending on
+        # everything (re-tabulated every stage); Source(f, state=False, time=False) is static
+        if source is not None and not isinstance(source, Source):
+            if not callable(source):
+                raise ValueError("source must be a callable f(Q, x, t) or a flou_b200.Source")
+            source = Source(source)
+        self.source = source
         if std.nd != mesh.nd or equation.nd != mesh.nd:
             raise ValueError("mesh, standard region and equation dimensions differ")
         self.mesh, self.std, self.equation = mesh, std, equation
@@ -116,15 +122,27 @@ class MultielementDisc:
                  .astype(np.int64))
         state = np.zeros((max(nb, 1), nv))
         table = np.zeros((max(int(offs[-1]), 1) * self.nfp, nv))
+        self._dynamic_bcs = []              # [(boundary index, GenericBC)] re-tabulated every stage
         if any(isinstance(bc, GenericBC) for bc in self.bcs):
-            fcoords = self.face_coords()
+            fcoords = self._fcoords = self.face_coords()
         for ib, bc in enumerate(self.bcs):
             if bc.kind == L.BC_INFLOW:
                 if len(bc.Qext) != nv:
                     raise ValueError("EulerInflowBC state length does not match the equation")
                 state[ib] = bc.Qext
             elif bc.kind == L.BC_TABLE:
-                for m in range(int(offs[ib]), int(offs[ib + 1])):
+                rows = range(int(offs[ib]), int(offs[ib + 1]))
+                dynamic = bc.dynamic
+                if dynamic is None and len(rows):      # probe: does the closure read Qin / frame / time?
+                    try:
+                        bc.tabulate(fcoords[(int(faces[rows[0]]) - 1) * self.nfp], equation)
+                        dynamic = False
+                    except _DependsOn:
+                        dynamic = True
+                if dynamic:
+                    self._dynamic_bcs.append((ib, bc))
+                    continue
+                for m in rows:
                     f = int(faces[m]) - 1
                     for i in range(self.nfp):
                         table[m * self.nfp + i] = bc.tabulate(fcoords[f * self.nfp + i], equation)
@@ -168,6 +186,61 @@ class MultielementDisc:
             # the library copied everything it needs; drop the big host tables
             for name in ("jac", "metric", "fjac", "frames", "sub_frames", "sub_jac"):
                 keep.pop(name, None)
+            self._init_dynamic()
+
+    # ------------------------------------------------------------------ source / dynamic BCs
+    @property
+    def has_dynamic(self):
+        """True when source or boundary data have to be re-tabulated by the host before every
+        stage (the RK loop then runs stage by stage instead of from the captured graph)."""
+        return bool(self._dynamic_bcs) or (self.source is not None and self.source.dynamic)
+
+    def _init_dynamic(self):
+        self._bc_table = self._keep["bc_table"]
+        if self.source is not None:
+            self._xloc = self.coords()[self.local_rows()]
+            if not self.source.dynamic:
+                S = self.source.tabulate(None, self._xloc, 0.0, self.nv)
+                L.check(L.lib().flou_b200_set_source(self.handle, _ptr(S)))
+        if self._dynamic_bcs:
+            n = C.c_int64(0)
+            L.check(L.lib().flou_b200_boundary_traces(self.handle, None, None, C.byref(n)))
+            self._bd_ord = np.zeros(max(n.value, 1), dtype=np.int64)
+            L.check(L.lib().flou_b200_boundary_traces(self.handle, None, _ptr(self._bd_ord), C.byref(n)))
+            self._bd_ord = self._bd_ord[:n.value]
+            self._bd_traces = np.zeros((max(n.value, 1), self.nv, self.nfp))
+            offs = self._keep["bc_offsets"]
+            self._bd_ib = np.searchsorted(offs, self._bd_ord, side="right") - 1      # boundary of each owned face
+            _, _, frames = self._face_geometry()
+            self._fframes = frames.reshape(-1, 3, self.nd)
+
+    def refresh(self, t, Q=None):
+        """Re-tabulate what depends on (Q, t) -- the dynamic source and GenericBC closures -- for a
+        pass at time t on the device-resident state (`Q`: that state on the host, if the caller
+        has it; downloaded otherwise when the source needs it)."""
+        src = self.source
+        if src is not None and src.dynamic:
+            if src.state and Q is None:
+                Q = self.download()
+            S = src.tabulate(Q if src.state else None, self._xloc, float(t), self.nv)
+            L.check(L.lib().flou_b200_set_source(self.handle, _ptr(S)))
+        if self._dynamic_bcs:
+            n = C.c_int64(0)
+            L.check(L.lib().flou_b200_boundary_traces(self.handle, _ptr(self._bd_traces), None, C.byref(n)))
+            dyn = dict(self._dynamic_bcs)
+            faces = self._keep["bc_faces"]
+            for j in range(n.value):
+                bc = dyn.get(int(self._bd_ib[j]))
+                if bc is None:
+                    continue
+                m = int(self._bd_ord[j])
+                f = int(faces[m]) - 1
+                for i in range(self.nfp):
+                    fr = self._fframes[f * self.nfp + i]
+                    self._bc_table[m * self.nfp + i] = bc.evaluate(
+                        self._bd_traces[j, :, i].copy(), self._fcoords[f * self.nfp + i],
+                        Frame(fr[0], fr[1], fr[2]), float(t), self.equation)
+            L.check(L.lib().flou_b200_set_bc_table(self.handle, _ptr(self._bc_table)))
 
     def partition_plan(self):
         """Host-only halo plan (no GPU needed): dict with peers, per-peer slot counts, the
@@ -297,6 +370,12 @@ def rhs(dQ, Q, p, time=0.0):
     disc = p.disc
     Q = _state(Q, disc.ndofs, disc.nv)
     dQ = _state(dQ, disc.ndofs, disc.nv, writable=True)
+    if disc.has_dynamic:
+        # source / boundary closures evaluated by the host for this (Q, time), then the device pass
+        disc.upload(Q)
+        disc.refresh(time, Q)
+        L.check(L.lib().flou_b200_rhs(disc.handle, None, _ptr(dQ), float(time)))
+        return None
     L.check(L.lib().flou_b200_rhs(disc.handle, _ptr(Q), _ptr(dQ), float(time)))
     return None
 

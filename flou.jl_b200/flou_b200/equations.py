@@ -189,22 +189,41 @@ class EulerSlipBC:
 
 
 class GenericBC:
-    """GenericBC(Qext) with `Qext(Qin, x, frame, time, eq)`.
+    """GenericBC(Qext) with `Qext(Qin, x, frame, time, eq)` (FlouSpatial.jl:85-91, called from
+    applyBC!, Interfaces.jl:44-48).
 
-    On the device only closures that depend on the position `x` alone are supported: they are
-    tabulated once per boundary-face node when the discretisation is built (this covers
-    every use in the reference's tests, test/tests.jl:103-113,152-159).  A closure reading
-    `Qin`, `frame` or `time` raises at construction time instead of silently falling back to
-    the host.
+    The closure is host code, so the exterior state is TABULATED per boundary-face node and the
+    device reads the table.  A closure that depends on the position `x` alone (every use in the
+    reference's tests, test/tests.jl:103-113,152-159) is tabulated once when the discretisation is
+    built.  One that reads `Qin`, `frame` or `time` is detected at construction (`dynamic=None`)
+    or declared (`dynamic=True`) and re-tabulated by the host before every RK stage from the
+    interior traces of the device-resident state; `frame` has fields n, t, b.  `dynamic=False`
+    insists on the static table and raises if the closure reads anything else.
     """
     kind = L.BC_TABLE
 
-    def __init__(self, Qext: Callable):
+    def __init__(self, Qext: Callable, dynamic=None):
         self.Qext = Qext
+        self.dynamic = dynamic
 
     def tabulate(self, x, eq):
         return np.asarray(self.Qext(_Forbidden("Qin"), x, _Forbidden("frame"), _Forbidden("time"), eq),
                           dtype=np.float64)
+
+    def evaluate(self, Qin, x, frame, time, eq):
+        return np.asarray(self.Qext(Qin, x, frame, time, eq), dtype=np.float64)
+
+
+class Frame:
+    """geometry.faces.frames[i]: unit normal, tangent and bi-tangent of a face node."""
+    __slots__ = ("n", "t", "b")
+
+    def __init__(self, n, t, b):
+        self.n, self.t, self.b = n, t, b
+
+
+class _DependsOn(ValueError):
+    pass
 
 
 class _Forbidden:
@@ -212,10 +231,38 @@ class _Forbidden:
         self._what = what
 
     def _raise(self, *a, **k):
-        raise ValueError(
-            f"GenericBC closures may only depend on the coordinates on the B200 path; "
-            f"this one reads `{self._what}`")
+        raise _DependsOn(
+            f"GenericBC closure reads `{self._what}`: not a position-only boundary condition "
+            f"(pass dynamic=True, or drop dynamic=False, to have it re-tabulated every stage)")
 
     __getitem__ = __iter__ = __float__ = __add__ = __radd__ = __mul__ = __rmul__ = _raise
     __sub__ = __rsub__ = __neg__ = __lt__ = __gt__ = __le__ = __ge__ = __len__ = _raise
-    __truediv__ = __rtruediv__ = __array__ = _raise
+    __truediv__ = __rtruediv__ = __array__ = __getattr__ = _raise
+
+
+class Source:
+    """Source term of `MultielementDisc(mesh, std, eq, operators, bcs, source)`
+    (MultielementDiscontinuous.jl:29-36, applied by apply_sourceterm!, :139-146, after the mass
+    matrix).  `f(Q_i, x_i, t)` returns the increment of dQ at one node (length nv) -- the
+    reference's closure receives `dQ.dofs[i]` to add it to; with `vectorized=True` it is called
+    once with (Q (n, nv), x (n, nd), t) and returns (n, nv).  The source is tabulated per node by
+    the host and added on the device; `state` / `time` say what it depends on: a position-only
+    source (both False) is tabulated once and costs nothing afterwards, the others are
+    re-tabulated before every RK stage (`state=True` downloads the state for it)."""
+
+    def __init__(self, f, state=True, time=True, vectorized=False):
+        self.f, self.state, self.time, self.vectorized = f, bool(state), bool(time), bool(vectorized)
+
+    @property
+    def dynamic(self):
+        return self.state or self.time
+
+    def tabulate(self, Q, x, t, nv):
+        if self.vectorized:
+            return np.asfortranarray(np.asarray(self.f(Q, x, t), dtype=np.float64).reshape(x.shape[0], nv))
+        out = np.zeros((x.shape[0], nv), order="F")
+        for i in range(x.shape[0]):
+            r = self.f(None if Q is None else Q[i], x[i], t)
+            if r is not None:
+                out[i] = r
+        return out

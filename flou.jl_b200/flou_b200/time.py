@@ -64,10 +64,24 @@ def _set_limiter(disc, solver):
                                                 lim.minval if lim is not None else 0.0))
 
 
+def _advance_stagewise(disc, solver, dt, nsteps, t0):
+    """Source or boundary closures that depend on (Q, t): the host re-tabulates them before every
+    stage at t + c_s dt (OrdinaryDiffEq evaluates f(u, p, t + c_s dt)) and launches one stage."""
+    A, B, c = _tab(solver)
+    lib = L.lib()
+    for n in range(int(nsteps)):
+        t = t0 + n * dt
+        for s in range(solver.nstages):
+            disc.refresh(t + c[s] * dt)
+            L.check(lib.flou_b200_lsrk2n_stage(disc.handle, float(A[s]), float(B[s]), float(dt), 1 if s == 0 else 0))
+
+
 def advance(disc, solver, dt, nsteps, t0=0.0):
     """Device-resident fast path: nsteps RK steps on the uploaded state (asynchronous)."""
     A, B, c = _tab(solver)
     _set_limiter(disc, solver)
+    if disc.has_dynamic:
+        return _advance_stagewise(disc, solver, dt, nsteps, t0)
     L.check(L.lib().flou_b200_lsrk2n_advance(disc.handle, solver.nstages, _ptr(A), _ptr(B), _ptr(c),
                                              float(dt), float(t0), int(nsteps)))
 
@@ -116,15 +130,20 @@ def timeintegrate(Q0, disc, equation, solver, tfinal, *, dt, adaptive=False, ali
     _set_limiter(disc, solver)
     tic = _time.perf_counter()
     try:
-        if last == 0.0:
+        if last == 0.0 and not disc.has_dynamic:
             L.check(L.lib().flou_b200_timeintegrate(disc.handle, _ptr(Q), solver.nstages, _ptr(A),
                                                     _ptr(B), _ptr(c), float(dt), float(t0),
                                                     int(nsteps)))
         else:
             disc.upload(Q)
             for n, h, ts in ((nsteps, dt, t0), (1, last, t0 + nsteps * dt)):
-                L.check(L.lib().flou_b200_lsrk2n_advance(disc.handle, solver.nstages, _ptr(A), _ptr(B),
-                                                         _ptr(c), float(h), float(ts), int(n)))
+                if h == 0.0:
+                    continue
+                if disc.has_dynamic:
+                    _advance_stagewise(disc, solver, float(h), n, float(ts))
+                else:
+                    L.check(L.lib().flou_b200_lsrk2n_advance(disc.handle, solver.nstages, _ptr(A), _ptr(B),
+                                                             _ptr(c), float(h), float(ts), int(n)))
             disc.download(Q)
             if disc.status() & 1:
                 raise L.DomainError("non-positive density/pressure or NaN (Simulation crashed!)")
@@ -178,8 +197,11 @@ def _timeintegrate_callbacks(Q0, disc, equation, solver, tfinal, *, dt, alias_u0
     try:
         while integ.t < tfinal - 1e-14 * max(1.0, abs(tfinal)):
             h = min(integ.dt, tfinal - integ.t)       # the last step lands on tfinal (tstops)
-            L.check(L.lib().flou_b200_lsrk2n_advance(disc.handle, solver.nstages, _ptr(A), _ptr(B),
-                                                     _ptr(c), h, integ.t, 1))
+            if disc.has_dynamic:
+                _advance_stagewise(disc, solver, h, 1, integ.t)
+            else:
+                L.check(L.lib().flou_b200_lsrk2n_advance(disc.handle, solver.nstages, _ptr(A), _ptr(B),
+                                                         _ptr(c), h, integ.t, 1))
             integ.t += h
             integ.iter += 1
             for cb in cbs:

@@ -48,6 +48,17 @@ struct Desc
     sub_frames::Ptr{Float64}; sub_jac::Ptr{Float64}
 end
 
+# the hand-written mirror above against the header's offsetof table (generated, desc_offsets.jl):
+# a field added to, or reordered in, include/flou_b200.h without the same change here fails at
+# module load instead of corrupting a descriptor
+include("desc_offsets.jl")
+@assert sizeof(Desc) == DESC_SIZEOF "FlouB200.Desc does not match flou_b200_desc (sizeof)"
+@assert fieldcount(Desc) == length(DESC_OFFSETS) "FlouB200.Desc does not match flou_b200_desc (field count)"
+for (i, (name, off)) in enumerate(DESC_OFFSETS)
+    @assert fieldname(Desc, i) == name "FlouB200.Desc field $i is $(fieldname(Desc, i)), header has $name"
+    @assert fieldoffset(Desc, i) == off "FlouB200.Desc.$name at offset $(fieldoffset(Desc, i)), header has $off"
+end
+
 fluxkind(::StdAverage) = Int32(0)
 fluxkind(::LxF) = Int32(1)
 fluxkind(::ChandrasekharAverage) = Int32(2)

@@ -222,6 +222,28 @@ int32_t flou_b200_zhang_shu(flou_b200_handle *h, double *Q, double minval);
  * the state after every RK stage, on the device. */
 int32_t flou_b200_set_stage_limiter(flou_b200_handle *h, int32_t enable, double minval);
 
+/* ---- source term and boundary data that change between stages ---
+ * apply_sourceterm! (MultielementDiscontinuous.jl:139-146; default no-op :75-79): the source
+ * S(Q_i, x_i, t) is TABULATED per node by the host -- it is a user closure in the reference, which
+ * cannot run on the device -- and added to dQ after the mass matrix by the stage kernels.
+ * S: host (ndofs_local, nv) column-major, copied before the call returns; NULL removes the source.
+ * A position-only source is set once; one that depends on t or Q is re-tabulated by the host
+ * between stages (flou_b200_lsrk2n_stage below; Q through flou_b200_download_state). */
+int32_t flou_b200_set_source(flou_b200_handle *h, const double *S);
+/* GenericBC closures bc(Qin, x, frame, t, eq) (Interfaces.jl:44-48, FlouSpatial.jl:85-91) that
+ * read Qin, the frame or the time: the host re-tabulates the exterior state of every boundary-face
+ * node between stages.  table: same layout as flou_b200_desc.bc_table (all rows). */
+int32_t flou_b200_set_bc_table(flou_b200_handle *h, const double *table);
+/* Interior traces Qin of the device-resident state at the nodes of the boundary faces this handle
+ * owns: Qin[(j*nv + v)*nfp + k] for the j-th owned boundary face (k in the element's face-dof
+ * order), ordinals[j] = its position m in the concatenated bc_faces (the row block m*nfp.. of
+ * bc_table); *count = number of owned boundary faces.  Any of Qin / ordinals / count may be NULL. */
+int32_t flou_b200_boundary_traces(flou_b200_handle *h, double *Qin, int64_t *ordinals, int64_t *count);
+/* ONE low-storage stage  tmp = A*tmp + dt*k(u);  u += B*tmp  (first != 0: tmp = dt*k) on the
+ * device-resident state, followed by the stage limiter when one is set: the unit the host loops
+ * over when source or boundary data change from stage to stage. */
+int32_t flou_b200_lsrk2n_stage(flou_b200_handle *h, double A, double B, double dt, int32_t first);
+
 int32_t flou_b200_synchronize(flou_b200_handle *h);
 /* sticky device flags: bit 0 = non-positive density/pressure or NaN seen since the last
  * flou_b200_upload_state / flou_b200_timeintegrate (both clear them) */

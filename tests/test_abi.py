@@ -49,6 +49,29 @@ def test_descriptor_layout_matches_the_library():
     d.struct_size -= 8
 
 
+def test_descriptor_mirrors_match_the_header_offsets():
+    """offsetof of every flou_b200_desc field (tests/abi_offsets.c, compiled here with gcc) against
+    the ctypes mirror and the generated Julia table the un-run shim asserts at load time."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "gen_desc_offsets", os.path.join(ROOT, "flou.jl_b200", "julia", "gen_desc_offsets.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    rows, size = gen.offsets()
+    assert size == C.sizeof(L.Desc)
+    assert [r[0] for r in rows] == [f[0] for f in L.Desc._fields_]
+    for name, off, sz in rows:
+        assert getattr(L.Desc, name).offset == off, name
+        assert getattr(L.Desc, name).size == sz, name
+    committed = open(os.path.join(ROOT, "flou.jl_b200", "julia", "desc_offsets.jl")).read()
+    assert committed == gen.render(rows, size), "stale desc_offsets.jl: run flou.jl_b200/julia/gen_desc_offsets.py"
+    # the Julia struct lists the same fields in the same order
+    jl = open(os.path.join(ROOT, "flou.jl_b200", "julia", "FlouB200.jl")).read()
+    body = jl[jl.index("struct Desc"):jl.index("\nend", jl.index("struct Desc"))]
+    fields = re.findall(r"(\w+)::", body)
+    assert fields == [r[0] for r in rows]
+
+
 @pytest.mark.parametrize("field,value", [("nd", 4), ("np", 9), ("np", 1), ("nv", 3), ("equation", 7),
                                          ("divop", 5), ("numflux", 9), ("tpflux", 3),
                                          ("numflux_avg", 4), ("geometry", 2), ("ne", 0)])
@@ -116,3 +139,26 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert "oracle/" not in text and "liboracle" not in text, f
+
+
+def test_descriptor_value_ranges_are_checked():
+    """Byte / enum tables: an unknown bc_kind, an orientation code outside the dimension's range, a
+    boundary-face id outside [1, nf] or decreasing offsets are refused (EINVAL), not read blindly."""
+    case = Case(2, (3, 3), 4, periodic=[("3", "4")], bcs={"1": ("slip", None), "2": ("outflow", None)})
+
+    def rc_after(mutate):
+        disc, _ = case.product(create=False)
+        mutate(disc._keep)
+        return L.lib().flou_b200_partition_plan(C.byref(disc._desc), None, None, None, None, None, None,
+                                                None, None)
+    assert rc_after(lambda k: None) == L.OK
+    assert rc_after(lambda k: k["bc_kind"].__setitem__(0, 7)) == L.EINVAL
+    assert rc_after(lambda k: k["bc_kind"].__setitem__(1, -1)) == L.EINVAL
+    assert rc_after(lambda k: k["orientation"].__setitem__(2, 2)) == L.EINVAL      # 2-D: 0..1
+    assert rc_after(lambda k: k["bc_faces"].__setitem__(0, 0)) == L.EINVAL
+    assert rc_after(lambda k: k["bc_faces"].__setitem__(0, 10 ** 6)) == L.EINVAL
+    assert rc_after(lambda k: k["bc_offsets"].__setitem__(1, k["bc_offsets"][2] + 1)) == L.EINVAL
+    disc3, _ = Case(3, (2, 2, 2), 3).product(create=False)
+    disc3._keep["orientation"][0] = 8
+    assert L.lib().flou_b200_partition_plan(C.byref(disc3._desc), None, None, None, None, None, None,
+                                            None, None) == L.EINVAL

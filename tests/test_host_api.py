@@ -73,9 +73,15 @@ def test_generic_bc_is_tabulated_at_face_nodes():
 
     def state_dependent(Qin, x, frame, t, e):
         return 2 * Qin[0]
+    # a closure that reads Qin / frame / time is detected and re-tabulated every stage ...
+    dyn = F.MultielementDisc(mesh, _std(1), eq, F.StrongDivOperator(F.StdAverage()),
+                             {"1": F.GenericBC(state_dependent), "2": F.GenericBC(qext)}, create=False)
+    assert [ib for ib, _ in dyn._dynamic_bcs] == [0] and dyn.has_dynamic
+    assert not disc.has_dynamic
+    # ... unless the caller insists on the static table
     with pytest.raises(ValueError):
         F.MultielementDisc(mesh, _std(1), eq, F.StrongDivOperator(F.StdAverage()),
-                           {"1": F.GenericBC(state_dependent), "2": F.GenericBC(qext)}, create=False)
+                           {"1": F.GenericBC(state_dependent, dynamic=False), "2": F.GenericBC(qext)}, create=False)
 
 
 def test_out_of_scope_features_raise_instead_of_falling_back():
@@ -87,9 +93,16 @@ def test_out_of_scope_features_raise_instead_of_falling_back():
     with pytest.raises(ValueError):
         F.MultielementDisc(mesh, _std(2, nodes="GL", nv=1), F.LinearAdvection(1.0, 0.5),
                            F.SplitDivOperator(F.StdAverage(), F.LxF(F.StdAverage(), 1.0)), {}, create=False)
-    with pytest.raises(ValueError):        # source terms
-        F.MultielementDisc(mesh, _std(2), eq, F.StrongDivOperator(F.StdAverage()), {},
-                           source=lambda *a: None, create=False)
+    # source terms (row a13): a plain callable is re-tabulated every stage, Source(...) says more
+    d1 = F.MultielementDisc(mesh, _std(2), eq, F.StrongDivOperator(F.StdAverage()), {},
+                            source=lambda Q, x, t: None, create=False)
+    assert d1.has_dynamic and d1.source.state and d1.source.time
+    d2 = F.MultielementDisc(mesh, _std(2), eq, F.StrongDivOperator(F.StdAverage()), {},
+                            source=F.Source(lambda Q, x, t: [0.0, 1.0, 0.0, 0.0], state=False, time=False),
+                            create=False)
+    assert not d2.has_dynamic
+    with pytest.raises(ValueError):
+        F.MultielementDisc(mesh, _std(2), eq, F.StrongDivOperator(F.StdAverage()), {}, source=3.0, create=False)
     with pytest.raises(ValueError):
         F.ORK256(williamson_condition=True)
     with pytest.raises(ValueError):

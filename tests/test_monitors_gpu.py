@@ -26,12 +26,22 @@ def test_monitors_match_oracle(gpu, case):
     disc, eq = case.product()
     assert F.list_monitors(disc, eq) == ("kinetic_energy", "entropy")
     Q = random_state(orc.ndof, case.nd, "euler")
+    # an explicit host state is staged in a scratch buffer: the device-resident state of an ongoing
+    # run (here: another state, uploaded first) is not replaced by the query
+    resident = random_state(orc.ndof, case.nd, "euler", seed=99, amp=0.2)
+    disc.upload(resident)
     for name in ("kinetic_energy", "entropy", "energy"):
         mon = F.get_monitor(disc, eq, name)
         want = orc.monitor(Q, name)
         got = mon(Q, disc, eq)
         assert abs(got / want - 1) <= 1e-12
-        assert mon(None, disc, eq) == got          # same kernels on the resident copy: bitwise
+        assert abs(mon(None, disc, eq) / orc.monitor(resident, name) - 1) <= 1e-12
+        assert F.get_max_dt(Q, disc, eq, 0.5) > 0.0
+    assert np.array_equal(disc.download(), resident)
+    disc.upload(Q)
+    for name in ("kinetic_energy", "entropy"):
+        mon = F.get_monitor(disc, eq, name)
+        assert mon(None, disc, eq) == mon(Q, disc, eq)      # same kernels on the resident copy: bitwise
     with pytest.raises(ValueError):
         F.get_monitor(disc, eq, "enstrophy")
     disc.close()
