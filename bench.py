@@ -170,6 +170,18 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def fp64_peak():
+    """Measured DFMA rate of the device (profiles/tools/dfma_peak.cu, thread-instructions/s at the
+    burst clock) and the fp64 thread-instructions per DOF and stage of the two kernels, counted by
+    ncu (smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on).  None if not recorded."""
+    try:
+        peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+        cnt = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        return peak, cnt
+    except Exception:
+        return None, None
+
+
 def ncu_traffic(workload):
     """DRAM bytes per launch of the stage kernel from the committed ncu capture, if any."""
     try:
@@ -585,7 +597,10 @@ def main():
     achieved = ndof_local * bytes_per_dof / (kernel_ms * 1e-3) / 1e9
     config["launch"] = launch_info
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+                "frac": achieved / peak,
+                # per-launch DRAM bytes from the committed ncu capture of the single-GPU run; a rank of
+                # a partitioned run moves 1/N of it plus the halo, not re-captured: null
+                "traffic": ncu_traffic(args.workload) if world == 1 else None,
                 "kernel": "flou::line_kernel_ws (element kernel of the two-kernel stage)",
                 "algorithmic_bytes_per_dof": bytes_per_dof,
                 "dofs_per_launch": ndof_local, "avg_launch_ms": kernel_ms,
@@ -593,6 +608,18 @@ def main():
                 "kernels_per_stage": ksplit, "peak_source": peak_src,
                 "note": "frac = dominant kernel alone; stage_frac = all kernels of an RK stage "
                         "(what `value` is made of)"}
+
+    # second roof: the EC split-form kernel sits near the fp64/HBM ridge
+    fpk, cnt = fp64_peak()
+    per_dof = (cnt or {}).get(args.workload, {}).get("fp64_thread_instr_per_dof")
+    if fpk and per_dof:
+        rate = ndof_local / (stage_ms * 1e-3)
+        roofline["fp64_frac"] = per_dof["stage"] * rate / fpk["dfma_per_s"]
+        roofline["fp64"] = {"thread_instr_per_dof": per_dof, "peak_dfma_per_s": fpk["dfma_per_s"],
+                            "peak_source": "measured: profiles/fp64_peak.json (profiles/tools/dfma_peak.cu, "
+                                           f"{fpk['dfma_per_clk_per_sm']:.1f} DFMA/clk/SM at {fpk['sm_mhz_during']} MHz)",
+                            "note": "fraction of the measured DFMA issue rate the whole stage sustains; the "
+                                    "power cap lowers the SM clock under this kernel (see clocks)"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

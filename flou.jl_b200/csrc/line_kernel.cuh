@@ -186,7 +186,9 @@ struct LCfg {
     static constexpr int OFF_F = (OFF_P + NPART * N + 1) & ~1;  // [2][E*NFACES][FNB]  flux blocks of the faces of this / the next group (16-byte aligned)
     static constexpr int OFF_EC = OFF_F + 2 * E * NFACES * FNB; // [2][E*NFACES] int2: face connectivity of this / the next group
     static constexpr int OFF_BAR = OFF_EC + 2 * E * NFACES;     // 8 mbarriers
-    static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OFF_BAR + 8);
+    // + 16 iteration counters (int, one per warp) + the flux slots of the faces of an upcoming group (int each)
+    static constexpr int OFF_SLOT = OFF_BAR + 8 + 8;
+    static constexpr size_t SMEM_BYTES = sizeof(double) * (size_t)(OFF_SLOT + (E * NFACES + 1) / 2);
     static_assert(WS, "the line kernel exists in its warp-specialised form only");
     // registers: a line task holds NP nodes and NP*NV accumulators
     static constexpr int MINB =
@@ -616,13 +618,19 @@ __device__ __forceinline__ void hybrid_nb_line(const KParams &P, const double (&
         for (int v = 0; v < NV; v++) acc[j][v] = (Fb[j][v] - Fb[j + 1][v]) / P.w1d[j];
 }
 
-// Where a line task finds the Riemann fluxes at its two ends: the flux blocks of the group's faces
-// (one TMA bulk copy per face slot, issued by the update warp), the connectivity records that say
-// which side of each face the element is on, and the mbarrier the copies complete on.
-struct FaceSrc {
-    const double *sFn;      // [E*NFACES][FNB] master-outward fluxes in the master's face-dof order
-    const int2 *ec;         // [E*NFACES] {slot, master | orientation << 1}
-    unsigned bar, parity;
+// Shared-memory addresses of the kernel's mbarriers (line_kernel_ws.cuh), from the layout alone
+template <class C>
+struct WsBars {
+    __device__ __forceinline__ static unsigned base()
+    {
+        extern __shared__ __align__(16) double lsmem[];
+        return (unsigned)__cvta_generic_to_shared(lsmem + C::OFF_BAR);
+    }
+    __device__ __forceinline__ static unsigned fullU(int b) { return base() + 8 * b; }
+    __device__ __forceinline__ static unsigned fullP() { return base() + 24; }
+    __device__ __forceinline__ static unsigned freeP() { return base() + 32; }
+    __device__ __forceinline__ static unsigned fullT() { return base() + 40; }
+    __device__ __forceinline__ static unsigned fullF(int b) { return base() + 48 + 8 * b; }
 };
 
 // Surface term of the split form on nodes WITHOUT boundaries, one line
@@ -751,40 +759,55 @@ __device__ __forceinline__ void splitdiv_nb_line(const KParams &P, const double 
 // One line task: volume term of the line's NP nodes in direction d plus the lift of the two face
 // fluxes at its ends, written as the partial sums of direction d.  FAST (Chandrasekhar only):
 // branch-free pair fluxes; returns true when the line has to be redone with FAST = false.
+// `it`: the warp's iteration counter in shared memory.  Everything that depends on the iteration --
+// node-data buffer, flux-block buffer, mbarrier parities -- is derived from a fresh read of it where
+// it is needed, so that nothing but the line's own data is live across the pair fluxes (the counter
+// and the buffer pointers used to be spilled to local memory there; with the shared-memory carve-out
+// this kernel asks for, L1 is too small to keep those lines: ncu showed 15 % of the stall samples on
+// the reloads, profiles/r2_kernel_notes.md).
 template <class C, bool FAST>
-__device__ __forceinline__ bool line_task(const KParams &P, const double *sA, double *sP, const FaceSrc &fs,
-                                          int task, int64_t dof0, unsigned free_bar = 0, unsigned free_parity = 0)
+__device__ __forceinline__ bool line_task(const KParams &P, int task, int64_t dof0, const volatile int *it)
 {
+    extern __shared__ __align__(16) double lsmem[];
+    const double *const sA = lsmem + C::OFF_A + (*it & 1) * (C::NAUX * C::N);
+    double *const sP = lsmem + C::OFF_P;
     constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
     constexpr int NPTS = C::NPTS, NFP = C::NFP, NLINES = C::NLINES, NFACES = C::NFACES;
     constexpr int N = C::N, FNB = C::FNB;
     constexpr bool CART = C::CART, SPLIT = C::SPLIT, FOLD = C::FOLD;
     const int64_t ndof = P.ndof;
     bool redo = false;
-        const int el = task / NLINES, r_ = task - el * NLINES;
-        const int d = r_ / NFP, k = r_ - d * NFP;
-        int base, stride;
-        line_of<ND, NP>(d, k, base, stride);
-        base += el * NPTS;
-        double *pt = sP + (d * NV) * N;
-
-        // Cartesian split form: momentum components are handled in the cyclic order that puts
-        // the line's direction first, so the flux code is the same instruction stream for every d
-        int pc[ND];
+        // indices of the line: element of the group, direction, line of that direction, first node
+        // and node stride; pc: Cartesian split form, momentum components in the cyclic order that
+        // puts the line's direction first (the flux code is then the same instruction stream for every d)
+        int el, d, k, base, stride, pc[ND];
+        double *pt;
+        auto line_indices = [&](int t) {
+            el = t / NLINES;
+            const int r_ = t - el * NLINES;
+            d = r_ / NFP; k = r_ - d * NFP;
+            line_of<ND, NP>(d, k, base, stride);
+            base += el * NPTS;
+            pt = sP + (d * NV) * N;
 #pragma unroll
-        for (int c = 0; c < ND; c++) { const int s = d + c; pc[c] = FOLD ? (s >= ND ? s - ND : s) : c; }
+            for (int c = 0; c < ND; c++) { const int s_ = d + c; pc[c] = FOLD ? (s_ >= ND ? s_ - ND : s_) : c; }
+        };
+        line_indices(task);
         auto var_of = [&](int v) { return (FOLD && EQ == EQ_EULER && v >= 1 && v <= ND) ? 1 + pc[v - 1] : v; };
         // Riemann fluxes at the line's two ends (surface_contribution!): Fn is the master-outward flux
         // in the master's face-dof order; the slave side sees it negated (sgL / sgR) and permuted
         const double *fL, *fR;
         double sgL, sgR;
         auto face_src = [&]() {
-            mbar_wait(fs.bar, fs.parity);      // the flux blocks of this group have landed
-            const int2 ecL = fs.ec[el * NFACES + 2 * d], ecR = fs.ec[el * NFACES + 2 * d + 1];
+            const int i_ = *it, fbuf = i_ & 1;
+            mbar_wait(WsBars<C>::fullF(fbuf), (unsigned)((i_ >> 1) & 1));      // the flux blocks of this group have landed
+            const int2 *ec = reinterpret_cast<const int2 *>(lsmem + C::OFF_EC) + fbuf * (C::E * NFACES);
+            const double *sFn = lsmem + C::OFF_F + fbuf * (C::E * NFACES * FNB);
+            const int2 ecL = ec[el * NFACES + 2 * d], ecR = ec[el * NFACES + 2 * d + 1];
             const int iL = (ecL.y & 1) ? k : slave2master<ND, NP>(k, (ecL.y >> 1) & 7);
             const int iR = (ecR.y & 1) ? k : slave2master<ND, NP>(k, (ecR.y >> 1) & 7);
-            fL = fs.sFn + (el * NFACES + 2 * d) * FNB + iL;
-            fR = fs.sFn + (el * NFACES + 2 * d + 1) * FNB + iR;
+            fL = sFn + (el * NFACES + 2 * d) * FNB + iL;
+            fR = sFn + (el * NFACES + 2 * d + 1) * FNB + iR;
             sgL = (ecL.y & 1) ? 1.0 : -1.0;
             sgR = (ecR.y & 1) ? 1.0 : -1.0;
         };
@@ -906,6 +929,13 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
             }
         }
 
+        // one line per thread and iteration (task == thread index): the indices are derived again
+        // from a fresh read of the thread index instead of being kept (spilled) across the pair fluxes
+        if constexpr (C::ONE_ROUND && !C::HYBRID && !C::NB) {
+            int t_;
+            asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t_));
+            line_indices(t_);
+        }
         // lift of the two face fluxes (OpDivergence.jl:42-100); in FOLD mode the partial sum is
         // later multiplied by the metric factor of direction d, so the lift is pre-divided by it
         if (!(C::HYBRID && C::NB)) face_src();
@@ -948,7 +978,10 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
         }
         // partial sums of direction d, momentum components back in physical order (warp-specialised
         // kernel: once the update warp has consumed the partial sums of the previous group)
-        if (free_bar) mbar_wait(free_bar, free_parity);
+        {
+            const int i_ = *it;
+            if (i_ > 0) mbar_wait(WsBars<C>::freeP(), (unsigned)((i_ - 1) & 1));
+        }
 #pragma unroll
         for (int j = 0; j < NP; j++) {
             const int node = base + j * stride;
@@ -961,10 +994,9 @@ __device__ __forceinline__ bool line_task(const KParams &P, const double *sA, do
 // exact redo of a line, kept out of line so that its register allocation (library log, calls) does
 // not weigh on the fast path
 template <class C>
-__device__ __noinline__ void line_task_exact(const KParams &P, const double *sA, double *sP, const FaceSrc &fs,
-                                             int task, int64_t dof0, unsigned free_bar = 0, unsigned free_parity = 0)
+__device__ __noinline__ void line_task_exact(const KParams &P, int task, int64_t dof0, const volatile int *it)
 {
-    line_task<C, false>(P, sA, sP, fs, task, dof0, free_bar, free_parity);
+    line_task<C, false>(P, task, dof0, it);
 }
 
 // Node data of the line phase from the conservative state of one node (phase 1):

@@ -29,54 +29,64 @@
 
 namespace flou {
 
+// grid-wide loop bounds re-read from the special registers where they are needed: values computed
+// once in a common prologue were spilled to local memory by ptxas (the line phase needs every
+// register) and reloaded by BOTH roles on their critical paths
+__device__ __forceinline__ int ws_cta() { int v; asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(v)); return v; }
+__device__ __forceinline__ int ws_nctas() { int v; asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(v)); return v; }
+
+// 16-byte aligned planes and an even node count per group: the update warp moves the state with TMA
+// bulk copies issued by one lane (and works on node pairs); otherwise 8-byte cp.async
+template <class C>
+__device__ __forceinline__ bool ws_wide(const KParams &P)
+{
+    return ((P.ndof & 1) == 0) && (((int64_t)P.elem_first * C::NPTS & 1) == 0) && ((C::N & 1) == 0) &&
+           ((reinterpret_cast<uintptr_t>(P.u_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.tmp) & 15) == 0) &&
+           ((reinterpret_cast<uintptr_t>(P.u_out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.k_out) & 15) == 0) &&
+           (C::CART || (reinterpret_cast<uintptr_t>(P.jac) & 15) == 0);
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::T, C::MINB)
 line_kernel_ws(const __grid_constant__ KParams P)
 {
-    constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
-    constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NLINES = C::NLINES;
+    constexpr int EQ = C::EQ, VOL = C::VOL, NV = C::NV;
+    constexpr int NPTS = C::NPTS, NFACES = C::NFACES, NLINES = C::NLINES;
     constexpr int E = C::E, TL = C::TL, N = C::N, NAUX = C::NAUX;
     static_assert(C::WS, "line_kernel_ws needs the WS shared-memory layout");
+    using B = WsBars<C>;
 
     extern __shared__ __align__(16) double lsmem[];
     double *const smem = lsmem;
-    double *sU = smem + C::OFF_U, *sT = smem + C::OFF_T, *sA = smem + C::OFF_A;
-    double *sP = smem + C::OFF_P, *sFn = smem + C::OFF_F;
-    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(smem + C::OFF_BAR);
-    const unsigned fullP = bar0 + 24, freeP = bar0 + 32;          // fullU[b] = bar0 + 8 b
-    const unsigned fullF = bar0 + 48;                             // fullF[b] = bar0 + 48 + 8 b
     constexpr int FNB = C::FNB, FSET = E * NFACES * FNB;
 
-    const int ngroups = (P.elem_count + E - 1) / E;
-    const int64_t ndof = P.ndof;
-    const bool need_tmp = (P.mode == MODE_STAGE);
-    const int g0 = blockIdx.x, gs = gridDim.x;
-    if (g0 >= ngroups) return;
-    const int niter = (ngroups - g0 + gs - 1) / gs;
-
-    // 16-byte aligned planes and an even node count per group: the update warp moves the state with
-    // TMA bulk copies issued by one lane (and works on node pairs); otherwise 8-byte cp.async
-    const bool wide = ((ndof & 1) == 0) && (((int64_t)P.elem_first * NPTS & 1) == 0) && ((N & 1) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(P.u_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.tmp) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(P.u_out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.k_out) & 15) == 0) &&
-                      (C::CART || (reinterpret_cast<uintptr_t>(P.jac) & 15) == 0);
-    const unsigned fullT = bar0 + 40;
+    if (ws_cta() * E >= P.elem_count) return;
     if (threadIdx.x == 0) {
-        for (int b = 0; b < 3; b++) mbar_init(bar0 + 8 * b, wide ? 1 : 32);
-        mbar_init(fullP, TL);
-        mbar_init(freeP, 32);
-        mbar_init(fullT, 1);
-        mbar_init(fullF, 1);
-        mbar_init(fullF + 8, 1);
+        const bool wide = ws_wide<C>(P);
+        for (int b = 0; b < 3; b++) mbar_init(B::fullU(b), wide ? 1 : 32);
+        mbar_init(B::fullP(), TL);
+        mbar_init(B::freeP(), 32);
+        mbar_init(B::fullT(), 1);
+        mbar_init(B::fullF(0), 1);
+        mbar_init(B::fullF(1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // iteration counters of the line warps (see line_task)
+    volatile int *const sIt = reinterpret_cast<volatile int *>(smem + C::OFF_BAR + 8);
+    if (threadIdx.x < 16) sIt[threadIdx.x] = 0;
     __syncthreads();
 
     if (threadIdx.x >= TL) {
         // =========================================================== update warp
         const int lane = threadIdx.x - TL;
+        const int64_t ndof = P.ndof;
+        // group gg exists
+        auto live = [&](int gg) { return gg * E < P.elem_count; };
+        const bool need_tmp = (P.mode == MODE_STAGE);
+        const bool wide = ws_wide<C>(P);
+        double *sU = smem + C::OFF_U, *sT = smem + C::OFF_T, *sP = smem + C::OFF_P, *sFn = smem + C::OFF_F;
         // NV planes of the nodes of group gg -> shared memory, completion on `bar`
-        auto issue_planes = [&](const double *src, double *dst, int gg, unsigned bar) {
+        auto issue_planes = [&](const double *src, double *dst, int gg, unsigned bar, bool is_tmp) {
             const int nn = min(E, P.elem_count - gg * E) * NPTS;
             const double *s0 = src + (int64_t)(P.elem_first + gg * E) * NPTS;
             if (wide) {
@@ -90,57 +100,68 @@ line_kernel_ws(const __grid_constant__ KParams P)
 #pragma unroll
                     for (int v = 0; v < NV; v++) cp_async8(dst + v * N + n, s0 + n + ndof * v);
                 }
-                if (bar != fullT) mbar_arrive_cp_async(bar);       // tmp: this warp's own wait_group
+                if (!is_tmp) mbar_arrive_cp_async(bar);       // tmp: this warp's own wait_group
             }
         };
-        // Flux blocks of the faces of a group: the connectivity records {slot, side} of its
-        // (element, local face) pairs are read one group ahead into registers (a lane each), the
+        // Flux blocks of the faces of a group: the flux slots of its (element, local face) pairs
+        // are staged in shared memory one group ahead (cp.async, a lane each: in registers they were
+        // spilled across phase 3 and reloaded from local memory on this warp's critical path), the
         // block of every face slot then travels as one 16-byte aligned TMA bulk copy.
         constexpr int RN = (E * NFACES + 31) / 32;
-        int slot_next[RN];
+        int *const sSlot = reinterpret_cast<int *>(smem + C::OFF_SLOT);
         auto load_slots = [&](int gg) {
             const int nrec = min(E, P.elem_count - gg * E) * NFACES;
 #pragma unroll
             for (int q = 0; q < RN; q++) {
                 const int r = lane + 32 * q;
-                slot_next[q] = r < nrec ? __ldg(&P.econn[(int64_t)(P.elem_first + gg * E) * NFACES + r].x) : 0;
+                if (r < nrec) cp_async4(sSlot + r, &P.econn[(int64_t)(P.elem_first + gg * E) * NFACES + r].x);
             }
+            cp_async_commit();
         };
         auto issue_fn = [&](int gg, int buf) {
             const int nrec = min(E, P.elem_count - gg * E) * NFACES;
-            const unsigned bar = fullF + 8 * buf;
+            const unsigned bar = B::fullF(buf);
             if (lane == 0) mbar_expect_tx(bar, (unsigned)(nrec * FNB * sizeof(double)));
+            cp_async_wait<0>();          // this lane's slots (requested an iteration ago)
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < RN; q++) {
                 const int r = lane + 32 * q;
                 if (r < nrec)
-                    bulk_g2s_keep(sFn + buf * FSET + r * FNB, P.Fn + (int64_t)slot_next[q] * FNB, (unsigned)(FNB * sizeof(double)), bar);
+                    bulk_g2s_keep(sFn + buf * FSET + r * FNB, P.Fn + (int64_t)sSlot[r] * FNB, (unsigned)(FNB * sizeof(double)), bar);
             }
+            __syncwarp();
         };
-        for (int i = 0; i < 3 && i < niter; i++) issue_planes(P.u_in, sU + i * (NV * N), g0 + i * gs, bar0 + 8 * i);
-        if (need_tmp) issue_planes(P.tmp, sT, g0, fullT);
-        cp_async_commit();
-        load_slots(g0);
-        issue_fn(g0, 0);
-        if (niter > 1) { load_slots(g0 + gs); issue_fn(g0 + gs, 1); }
-        if (niter > 2) load_slots(g0 + 2 * gs);
-
-        for (int i = 0; i < niter; i++) {
-            const int g = g0 + i * gs, ub = i % 3;
+        {
+            const int g0 = ws_cta(), gs = ws_nctas();
+            for (int i = 0; i < 3 && live(g0 + i * gs); i++) issue_planes(P.u_in, sU + i * (NV * N), g0 + i * gs, B::fullU(i), false);
+            if (need_tmp) issue_planes(P.tmp, sT, g0, B::fullT(), true);
+            cp_async_commit();
+            load_slots(g0);
+            issue_fn(g0, 0);
+            if (live(g0 + gs)) { load_slots(g0 + gs); issue_fn(g0 + gs, 1); }
+            if (live(g0 + 2 * gs)) load_slots(g0 + 2 * gs);
+        }
+        // iteration counter in shared memory, grid bounds re-read: nothing of the loop is carried
+        // in registers (spilled) across phase 3
+        volatile int *const itU = sIt + (threadIdx.x >> 5);
+        for (;;) {
+            const int i = *itU, gs = ws_nctas();
+            const int g = ws_cta() + i * gs, ub = i % 3;
+            if (!live(g)) break;
             const int nact = min(E, P.elem_count - g * E), nn = nact * NPTS;
             const int64_t dof0 = (int64_t)(P.elem_first + g * E) * NPTS;
             double *U = sU + ub * (NV * N);
-            mbar_wait(fullP, i & 1);
+            mbar_wait(B::fullP(), i & 1);
             // every line thread is done with the flux blocks of group i: their buffer takes those of
             // group i+2 (in flight during a whole iteration of the line threads)
-            if (i + 2 < niter) {
+            if (live(g + 2 * gs)) {
                 issue_fn(g + 2 * gs, i & 1);
-                if (i + 3 < niter) load_slots(g + 3 * gs);
+                if (live(g + 3 * gs)) load_slots(g + 3 * gs);
             }
             if (wide) {
-                mbar_wait(bar0 + 8 * ub, (i / 3) & 1);      // completed long ago: makes the TMA writes visible here
-                if (need_tmp) mbar_wait(fullT, i & 1);
+                mbar_wait(B::fullU(ub), (i / 3) & 1);      // completed long ago: makes the TMA writes visible here
+                if (need_tmp) mbar_wait(B::fullT(), i & 1);
             } else {
                 cp_async_wait<0>();      // tmp of this group and this lane's share of the state copies
                 __syncwarp();
@@ -153,39 +174,49 @@ line_kernel_ws(const __grid_constant__ KParams P)
             } else if (N >= 64) phase3_nodes<C, 2, 32>(P, U, sT, sP, lane, nn, dof0, g);
             else phase3_nodes<C, 1, 32>(P, U, sT, sP, lane, nn, dof0, g);
             __syncwarp();                // every lane is done with sP, sT and sU[ub]
-            mbar_arrive(freeP);
-            if (need_tmp && i + 1 < niter) issue_planes(P.tmp, sT, g + gs, fullT);
-            if (i + 3 < niter) issue_planes(P.u_in, sU + ub * (NV * N), g + 3 * gs, bar0 + 8 * ub);
-            cp_async_commit();
+            mbar_arrive(B::freeP());
+            {
+                const int i2 = *itU, gs2 = ws_nctas(), g2 = ws_cta() + i2 * gs2, ub2 = i2 % 3;
+                if (need_tmp && live(g2 + gs2)) issue_planes(P.tmp, sT, g2 + gs2, B::fullT(), true);
+                if (live(g2 + 3 * gs2)) issue_planes(P.u_in, sU + ub2 * (NV * N), g2 + 3 * gs2, B::fullU(ub2), false);
+                cp_async_commit();
+                __syncwarp();
+                if (lane == 0) *itU = i2 + 1;
+                __syncwarp();
+            }
         }
         return;
     }
 
     // =============================================================== line threads
-    // face connectivity of the elements of a group, staged one group ahead (see line_kernel.cuh)
-    int2 *sEC = reinterpret_cast<int2 *>(smem + C::OFF_EC);
+    // face connectivity of the elements of a group, staged one group ahead
+    int2 *const sEC = reinterpret_cast<int2 *>(smem + C::OFF_EC);
     auto issue_ec = [&](int gg, int buf, int t) {
         const int nrec = min(E, P.elem_count - gg * E) * NFACES;
         if (t < nrec)
             cp_async8(reinterpret_cast<double *>(sEC + buf * (E * NFACES) + t),
                       reinterpret_cast<const double *>(P.econn + (int64_t)(P.elem_first + gg * E) * NFACES + t));
     };
-    int tid = threadIdx.x;
-    issue_ec(g0, 0, tid);
+    issue_ec(ws_cta(), 0, threadIdx.x);
     cp_async_commit();
+    const volatile int *const it = sIt + (threadIdx.x >> 5);
 
-    for (int i = 0; i < niter; i++) {
-        // thread index re-read every iteration (see line_kernel.cuh: keeps loop invariants out of
-        // the registers of the line phase)
+    for (;;) {
+        // thread index, grid bounds and the iteration counter are re-read every iteration instead of
+        // being carried across the line phase (see line_task)
+        int tid;
         asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-        const int g = g0 + i * gs, ub = i % 3;
+        const int i = *it;
+        const int g = ws_cta() + i * ws_nctas();
+        if (g * E >= P.elem_count) break;
+        const int ub = i % 3;
         const int nact = min(E, P.elem_count - g * E);
         const int nn = nact * NPTS, nl = nact * NLINES;
         const int64_t dof0 = (int64_t)(P.elem_first + g * E) * NPTS;
-        const double *U = sU + ub * (NV * N);
-        double *A = sA + (i & 1) * (NAUX * N);
+        const double *U = smem + C::OFF_U + ub * (NV * N);
+        double *A = smem + C::OFF_A + (i & 1) * (NAUX * N);
 
-        mbar_wait(bar0 + 8 * ub, (i / 3) & 1);
+        mbar_wait(B::fullU(ub), (i / 3) & 1);
         // ---------------- phase 1
         if (N > TL && (tid & ~31) + TL < nn) phase1_nodes<C, 2, TL>(P, U, A, tid, nn, dof0);
         else phase1_nodes<C, 1, TL>(P, U, A, tid, nn, dof0);
@@ -193,20 +224,36 @@ line_kernel_ws(const __grid_constant__ KParams P)
         asm volatile("bar.sync 1, %0;" ::"n"(TL) : "memory");
 
         // ---------------- phase 2: one tensor-product line per thread
-        const unsigned fb = i > 0 ? freeP : 0u, fpar = (unsigned)((i - 1) & 1);
-        const FaceSrc fs{sFn + (i & 1) * FSET, sEC + (i & 1) * (E * NFACES), fullF + 8 * (i & 1), (unsigned)((i >> 1) & 1)};
-        for (int task = tid; task < nl; task += TL) {
+        auto one_task = [&](int task) {
             if (EQ == EQ_EULER && VOL == VOL_SPLIT_CHA && !C::NB) {
-                if (line_task<C, true>(P, A, sP, fs, task, dof0, fb, fpar)) line_task_exact<C>(P, A, sP, fs, task, dof0, fb, fpar);
+                if (line_task<C, true>(P, task, dof0, it)) {
+                    // exact redo (rare): task and dof0 from scratch, nothing kept for it across the fast path
+                    int t_;
+                    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t_));
+                    const int g_ = ws_cta() + *it * ws_nctas();
+                    line_task_exact<C>(P, C::ONE_ROUND ? t_ : task, (int64_t)(P.elem_first + g_ * E) * NPTS, it);
+                }
             } else {
-                line_task<C, false>(P, A, sP, fs, task, dof0, fb, fpar);
+                line_task<C, false>(P, task, dof0, it);
             }
+        };
+        if constexpr (C::ONE_ROUND) {
+            if (tid < nl) one_task(tid);
+        } else {
+            for (int task = tid; task < nl; task += TL) one_task(task);
         }
-        mbar_arrive(fullP);
+        mbar_arrive(B::fullP());
         // connectivity of the next group: in flight during the wait for its state and phase 1
-        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-        if (i + 1 < niter) issue_ec(g0 + (i + 1) * gs, (i + 1) & 1, tid);
-        cp_async_commit();
+        {
+            int t2;
+            asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t2));
+            const int i2 = *it + 1, g2 = ws_cta() + i2 * ws_nctas();
+            if (g2 * E < P.elem_count) issue_ec(g2, i2 & 1, t2);
+            cp_async_commit();
+            __syncwarp();            // every lane has read the counter of this iteration
+            if ((t2 & 31) == 0) sIt[t2 >> 5] = i2;
+            __syncwarp();
+        }
     }
 }
 

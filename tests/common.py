@@ -32,15 +32,18 @@ def random_state(ndof, nd, eq, gamma=1.4, seed=SEED, amp=0.5):
     return Q
 
 
-def smooth_state(coords, nd, eq, gamma=1.4):
+def smooth_state(coords, nd, eq, gamma=1.4, waves=1):
+    """Smooth periodic field on the unit box of `box`; `waves` (int or one per direction):
+    wavelengths per box length."""
     x = coords
     s = np.ones(len(x))
+    w = [waves] * nd if np.isscalar(waves) else list(waves)
     for d in range(nd):
-        s = s * np.sin(2 * np.pi * x[:, d] / (1.0 + 0.5 * d) + 0.3 * d)
+        s = s * np.sin(2 * np.pi * w[d] * x[:, d] / (1.0 + 0.5 * d) + 0.3 * d)
     if eq == "adv":
         return np.asfortranarray((1.0 + 0.5 * s)[:, None])
     rho = 1.0 + 0.2 * s
-    vel = np.stack([0.3 * np.cos(2 * np.pi * x[:, d] / (1.0 + 0.5 * d)) * (1 + 0.1 * s)
+    vel = np.stack([0.3 * np.cos(2 * np.pi * w[d] * x[:, d] / (1.0 + 0.5 * d)) * (1 + 0.1 * s)
                     for d in range(nd)], axis=1)
     p = 1.0 + 0.1 * s
     Q = np.zeros((len(x), nd + 2), order="F")
