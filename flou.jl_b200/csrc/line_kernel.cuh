@@ -173,7 +173,12 @@ struct LCfg {
     // 112 KB per CTA: two CTAs (+ 1 KB each the driver reserves) fill the 228 KB of an SM
     static constexpr int E = pick_et(NLINES, PER_ELEM, 112).e, TL = pick_et(NLINES, PER_ELEM, 112).t;
 #endif
-    static constexpr int T = WS ? TL + 32 : TL;           // threads per CTA
+#ifdef FLOU_LINE_NUPD
+    static constexpr int NUPD = FLOU_LINE_NUPD;
+#else
+    static constexpr int NUPD = 1;                        // update warps per CTA
+#endif
+    static constexpr int T = WS ? TL + 32 * NUPD : TL;    // threads per CTA
     static constexpr int N = E * NPTS;                    // nodes of a group = plane stride
     static constexpr int L = E * NLINES;                  // line tasks of a group
     static constexpr int ROUNDS = (L + TL - 1) / TL;

@@ -47,7 +47,12 @@ __device__ __forceinline__ bool ws_wide(const KParams &P)
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::T, C::MINB)
+__global__ void
+#ifdef FLOU_LINE_MAXREG
+__maxnreg__(FLOU_LINE_MAXREG)
+#else
+__launch_bounds__(C::T, C::MINB)
+#endif
 line_kernel_ws(const __grid_constant__ KParams P)
 {
     constexpr int EQ = C::EQ, VOL = C::VOL, NV = C::NV;
@@ -65,7 +70,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
         const bool wide = ws_wide<C>(P);
         for (int b = 0; b < 3; b++) mbar_init(B::fullU(b), wide ? 1 : 32);
         mbar_init(B::fullP(), TL);
-        mbar_init(B::freeP(), 32);
+        mbar_init(B::freeP(), 32 * C::NUPD);
         mbar_init(B::fullT(), 1);
         mbar_init(B::fullF(0), 1);
         mbar_init(B::fullF(1), 1);
@@ -77,8 +82,15 @@ line_kernel_ws(const __grid_constant__ KParams P)
     __syncthreads();
 
     if (threadIdx.x >= TL) {
-        // =========================================================== update warp
-        const int lane = threadIdx.x - TL;
+        // =========================================================== update warp(s)
+        // NUPD warps share phase 3 and the trace pass of a group; the first one issues every copy
+        constexpr int TU = 32 * C::NUPD;
+        const int tu = threadIdx.x - TL;                 // index among the update threads
+        const int lane = tu < 32 ? tu : 1000;            // copy issue: first update warp only
+        auto upd_sync = [&]() {
+            if constexpr (C::NUPD == 1) __syncwarp();
+            else asm volatile("bar.sync 2, %0;" ::"n"(TU) : "memory");
+        };
         const int64_t ndof = P.ndof;
         // group gg exists
         auto live = [&](int gg) { return gg * E < P.elem_count; };
@@ -87,6 +99,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
         double *sU = smem + C::OFF_U, *sT = smem + C::OFF_T, *sP = smem + C::OFF_P, *sFn = smem + C::OFF_F;
         // NV planes of the nodes of group gg -> shared memory, completion on `bar`
         auto issue_planes = [&](const double *src, double *dst, int gg, unsigned bar, bool is_tmp) {
+            if (tu >= 32) return;
             const int nn = min(E, P.elem_count - gg * E) * NPTS;
             const double *s0 = src + (int64_t)(P.elem_first + gg * E) * NPTS;
             if (wide) {
@@ -110,6 +123,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
         constexpr int RN = (E * NFACES + 31) / 32;
         int *const sSlot = reinterpret_cast<int *>(smem + C::OFF_SLOT);
         auto load_slots = [&](int gg) {
+            if (tu >= 32) return;
             const int nrec = min(E, P.elem_count - gg * E) * NFACES;
 #pragma unroll
             for (int q = 0; q < RN; q++) {
@@ -121,6 +135,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
         auto issue_fn = [&](int gg, int buf) {
             const int nrec = min(E, P.elem_count - gg * E) * NFACES;
             const unsigned bar = B::fullF(buf);
+            if (tu >= 32) return;
             if (lane == 0) mbar_expect_tx(bar, (unsigned)(nrec * FNB * sizeof(double)));
             cp_async_wait<0>();          // this lane's slots (requested an iteration ago)
             __syncwarp();
@@ -164,16 +179,16 @@ line_kernel_ws(const __grid_constant__ KParams P)
                 if (need_tmp) mbar_wait(B::fullT(), i & 1);
             } else {
                 cp_async_wait<0>();      // tmp of this group and this lane's share of the state copies
-                __syncwarp();
+                upd_sync();
             }
             if (wide) {
-                if (N >= 128) phase3_pairs<C, 2, 32, true>(P, U, sT, sP, lane, nn, dof0, g);
-                else phase3_pairs<C, 1, 32, true>(P, U, sT, sP, lane, nn, dof0, g);
-                __syncwarp();
-                if (P.mode != MODE_RHS && P.colloc) trace_pass<C, 32>(P, U, lane, nact, g);
-            } else if (N >= 64) phase3_nodes<C, 2, 32>(P, U, sT, sP, lane, nn, dof0, g);
-            else phase3_nodes<C, 1, 32>(P, U, sT, sP, lane, nn, dof0, g);
-            __syncwarp();                // every lane is done with sP, sT and sU[ub]
+                if (N >= 128 && C::NUPD == 1) phase3_pairs<C, 2, TU, true>(P, U, sT, sP, tu, nn, dof0, g);
+                else phase3_pairs<C, 1, TU, true>(P, U, sT, sP, tu, nn, dof0, g);
+                upd_sync();
+                if (P.mode != MODE_RHS && P.colloc) trace_pass<C, TU>(P, U, tu, nact, g);
+            } else if (N >= 32 * C::NUPD) phase3_nodes<C, 2, TU>(P, U, sT, sP, tu, nn, dof0, g);
+            else phase3_nodes<C, 1, TU>(P, U, sT, sP, tu, nn, dof0, g);
+            upd_sync();                  // every update thread is done with sP, sT and sU[ub]
             mbar_arrive(B::freeP());
             {
                 const int i2 = *itU, gs2 = ws_nctas(), g2 = ws_cta() + i2 * gs2, ub2 = i2 % 3;
@@ -181,7 +196,7 @@ line_kernel_ws(const __grid_constant__ KParams P)
                 if (live(g2 + 3 * gs2)) issue_planes(P.u_in, sU + ub2 * (NV * N), g2 + 3 * gs2, B::fullU(ub2), false);
                 cp_async_commit();
                 __syncwarp();
-                if (lane == 0) *itU = i2 + 1;
+                if ((tu & 31) == 0) *itU = i2 + 1;
                 __syncwarp();
             }
         }

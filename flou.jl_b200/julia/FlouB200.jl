@@ -298,4 +298,53 @@ function timeintegrate(Q0::Matrix{Float64}, disc::B200Disc, equation,
     return ((u=[Q], t=[tfinal]), exetime)
 end
 
+# ---- source term and boundary data that change between stages ---------------------------------
+# apply_sourceterm! (MultielementDiscontinuous.jl:139-146) and GenericBC closures that read Qin,
+# frame or time (Interfaces.jl:44-48) are host closures: the shim tabulates them and the device reads
+# the tables.  `S`: (ndofs, nv) increments of dQ after the mass matrix; `nothing` removes the source.
+function set_source!(disc::B200Disc, S::Union{Matrix{Float64},Nothing})
+    check(ccall((:flou_b200_set_source, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}),
+                disc.handle, S === nothing ? Ptr{Float64}(C_NULL) : pointer(S)))
+end
+# interior traces at the nodes of the owned boundary faces: (nfp, nv, count) and the ordinal of
+# every face in the concatenated `bdfaces` (row block ordinal*nfp .. of the BC table)
+function boundary_traces(disc::B200Disc, nfp::Integer, nv::Integer)
+    n = Ref{Int64}(0)
+    check(ccall((:flou_b200_boundary_traces, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Ref{Int64}),
+                disc.handle, C_NULL, C_NULL, n))
+    Qin = Array{Float64}(undef, nfp, nv, n[]); ord = Vector{Int64}(undef, n[])
+    check(ccall((:flou_b200_boundary_traces, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Ref{Int64}),
+                disc.handle, Qin, ord, n))
+    return Qin, ord
+end
+set_bc_table!(disc::B200Disc, table::Matrix{Float64}) =       # (nv, rows): row-major rows of nv values
+    check(ccall((:flou_b200_set_bc_table, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), disc.handle, table))
+lsrk2n_stage!(disc::B200Disc, A, B, dt, first::Bool) =
+    check(ccall((:flou_b200_lsrk2n_stage, lib), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Int32),
+                disc.handle, Float64(A), Float64(B), Float64(dt), Int32(first)))
+
+"""
+    timeintegrate_stagewise(Q0, disc, solver, tf, refresh!; dt)
+
+The RK loop for discretisations whose source term or `GenericBC` closures depend on the state or
+the time: `refresh!(disc, t)` re-tabulates them (with `set_source!`, `boundary_traces`,
+`set_bc_table!`) before every stage at `t + c_s dt`, as OrdinaryDiffEq evaluates `f(u, p, t + c_s dt)`.
+"""
+function timeintegrate_stagewise(Q0::Matrix{Float64}, disc::B200Disc,
+                                 solver::Union{ORK256,CarpenterKennedy2N54}, tf, refresh!; dt)
+    A, B, c = tableau(solver)
+    check(ccall((:flou_b200_upload_state, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), disc.handle, Q0))
+    t = 0.0
+    while t < tf - 1e-14 * max(1.0, abs(tf))
+        h = min(dt, tf - t)
+        for s in eachindex(B)
+            refresh!(disc, t + c[s] * h)
+            lsrk2n_stage!(disc, A[s], B[s], h, s == 1)
+        end
+        t += h
+    end
+    check(ccall((:flou_b200_download_state, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}), disc.handle, Q0))
+    return Q0
+end
+
 end # module
