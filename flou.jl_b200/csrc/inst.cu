@@ -88,7 +88,14 @@ static cudaError_t do_launch_elements(const KParams &P, cudaStream_t s)
 // TL line threads + one update warp
 template <class C>
 using LineOf = LCfg<C::ND, C::NP, C::EQ, C::VOL, C::CART, true, C::NB>;
-#define FLOU_LINE_KERNEL line_kernel_ws
+// the kernel symbol of an instance: launch-bounds build or explicit register cap (only the one used
+// is instantiated)
+template <class L>
+static constexpr auto line_kernel_of()
+{
+    if constexpr (L::MAXREG > 0) return &line_kernel_ws_mr<L>;
+    else return &line_kernel_ws<L>;
+}
 
 template <class C>
 static int line_resident_ctas()
@@ -99,7 +106,7 @@ static int line_resident_ctas()
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, FLOU_LINE_KERNEL<L>, L::T, L::SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, line_kernel_of<L>(), L::T, L::SMEM_BYTES);
         n = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
     }
     return n;
@@ -118,10 +125,10 @@ static cudaError_t line_prepare()
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (optin > 0 && L::SMEM_BYTES > (size_t)optin) return cudaSuccess;
     }
-    cudaError_t e = cudaFuncSetAttribute(FLOU_LINE_KERNEL<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(line_kernel_of<L>(), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)L::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(FLOU_LINE_KERNEL<L>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(line_kernel_of<L>(), cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     line_resident_ctas<C>();
@@ -137,7 +144,7 @@ static cudaError_t do_launch_lines(const KParams &P0, cudaStream_t s)
     const int ngroups = (P.elem_count + L::E - 1) / L::E;
     const int resident = line_resident_ctas<C>();
     const int grid = ngroups < resident ? ngroups : resident;      // persistent CTAs
-    FLOU_LINE_KERNEL<L><<<grid, L::T, L::SMEM_BYTES, s>>>(P);
+    line_kernel_of<L>()<<<grid, L::T, L::SMEM_BYTES, s>>>(P);
     return cudaGetLastError();
 }
 

@@ -70,6 +70,21 @@ __device__ __forceinline__ void bulk_g2s_keep(double *smem_dst, const double *gm
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
+// TMA 1-D bulk copy shared -> global (bulk async-group completion): tmp and the new state are
+// streamed out once per stage, L2 evict-first like the loads
+__device__ __forceinline__ void bulk_s2g(double *gmem_dst, const double *smem_src, unsigned bytes)
+{
+    const unsigned s_ = (unsigned)__cvta_generic_to_shared(smem_src);
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(gmem_dst), "r"(s_), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory sources of every committed bulk store have been read (they may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory made visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // Wait for the phase with the given parity.  A failed try_wait comes back within a few cycles on
 // sm_100a, so a plain retry loop spins at ~4 cycles per iteration and takes issue slots from the
 // compute warps of the same scheduler (ncu: 157 retries per wait of the line threads on freeP).
@@ -173,10 +188,16 @@ struct LCfg {
     // 112 KB per CTA: two CTAs (+ 1 KB each the driver reserves) fill the 228 KB of an SM
     static constexpr int E = pick_et(NLINES, PER_ELEM, 112).e, TL = pick_et(NLINES, PER_ELEM, 112).t;
 #endif
+    // update warps per CTA and (MAXREG > 0) an explicit register cap instead of the launch bounds
 #ifdef FLOU_LINE_NUPD
     static constexpr int NUPD = FLOU_LINE_NUPD;
 #else
-    static constexpr int NUPD = 1;                        // update warps per CTA
+    static constexpr int NUPD = 1;
+#endif
+#ifdef FLOU_LINE_MAXREG
+    static constexpr int MAXREG = FLOU_LINE_MAXREG;
+#else
+    static constexpr int MAXREG = 0;
 #endif
     static constexpr int T = WS ? TL + 32 * NUPD : TL;    // threads per CTA
     static constexpr int N = E * NPTS;                    // nodes of a group = plane stride
@@ -1171,38 +1192,65 @@ __device__ __forceinline__ void phase3_nodes(const KParams &P, const double *U, 
 // condition of the copies).  RP pairs per thread at a time, loads first.
 // STAGE_TR: the new state is also written back over the old one in shared memory and the x-face
 // traces are emitted afterwards by trace_pass (warp-specialised kernel).
-template <class C, int RP, int T, bool STAGE_TR = false>
+// BULK (with STAGE_TR): tmp and the new state are ONLY written to shared memory (tmp in place over
+// sT, the state over U); the caller sends the planes to global memory with TMA bulk stores -- the
+// update warp is the critical path of the kernel and its 128-bit global stores with their 64-bit
+// address arithmetic were a quarter of its instructions.
+// Arithmetic: with w_d = metric_d / J * dt folded into three scalars,
+//   dt*k = sum_d w_d * partial_d (+ dt * source),  tmp = A*tmp + dt*k,  u = u + B*tmp
+// (5 fp64 instructions per value; MODE_RHS uses dt = 1 and stores k).
+template <class C, int RP, int T, bool STAGE_TR = false, bool BULK = false>
 __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_t<STAGE_TR, double, const double> *U,
-                                             const double *sT, const double *sP,
+                                             std::conditional_t<BULK, double, const double> *sT, const double *sP,
                                              int tid, int nn, int64_t dof0, int g)
 {
     constexpr int ND = C::ND, NP = C::NP, NV = C::NV, NPTS = C::NPTS, NFP = C::NFP, N = C::N, E = C::E;
     constexpr bool CART = C::CART, FOLD = C::FOLD;
+    static_assert(!BULK || STAGE_TR, "bulk stores go with the in-place update of the shared-memory copy");
     const int64_t ndof = P.ndof;
     const bool need_tmp = (P.mode == MODE_STAGE);
+    const double cs = (P.mode == MODE_RHS) ? 1.0 : P.dt;
+    double w[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) w[d] = (FOLD ? P.cmet[d] : 1.0) * (CART ? P.crjac : 1.0) * cs;
     const int npairs = nn >> 1;
     for (int p0 = tid; p0 < npairs; p0 += RP * T) {
-        double2 acc[RP][NV], tv[RP][NV], uv[RP][NV], rjac[RP];
+        double2 acc[RP][NV], tv[RP][NV], uv[RP][NV];
 #pragma unroll
         for (int r = 0; r < RP; r++) {
             const int n = 2 * min(p0 + r * T, npairs - 1);
+            // apply_sourceterm! (MultielementDiscontinuous.jl:139-146): tabulated source, after the
+            // mass matrix; a warp-uniform branch that the default (no source) never takes
+            double2 rj = make_double2(1.0, 1.0);
+            if (!CART) {
+                const double2 j = __ldg(reinterpret_cast<const double2 *>(P.jac + dof0 + n));
+                rj = make_double2(fast_rcp(j.x), fast_rcp(j.y));
+            }
 #pragma unroll
             for (int v = 0; v < NV; v++) {
                 double2 s = make_double2(0.0, 0.0);
+                if (P.source) {
+                    const double2 sv = __ldg(reinterpret_cast<const double2 *>(P.source + dof0 + n + ndof * v));
+                    s = make_double2(cs * sv.x, cs * sv.y);
+                }
+                if (CART) {
 #pragma unroll
-                for (int d = 0; d < ND; d++) {
-                    const double2 x = *reinterpret_cast<const double2 *>(sP + (d * NV + v) * N + n);
-                    if (FOLD) { s.x = fma(P.cmet[d], x.x, s.x); s.y = fma(P.cmet[d], x.y, s.y); }
-                    else { s.x += x.x; s.y += x.y; }
+                    for (int d = 0; d < ND; d++) {
+                        const double2 x = *reinterpret_cast<const double2 *>(sP + (d * NV + v) * N + n);
+                        s.x = fma(w[d], x.x, s.x); s.y = fma(w[d], x.y, s.y);
+                    }
+                } else {
+                    double2 q = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int d = 0; d < ND; d++) {
+                        const double2 x = *reinterpret_cast<const double2 *>(sP + (d * NV + v) * N + n);
+                        q.x += x.x; q.y += x.y;
+                    }
+                    s.x = fma(q.x, rj.x * cs, s.x); s.y = fma(q.y, rj.y * cs, s.y);
                 }
                 acc[r][v] = s;
                 tv[r][v] = need_tmp ? *reinterpret_cast<const double2 *>(sT + v * N + n) : make_double2(0.0, 0.0);
                 uv[r][v] = *reinterpret_cast<const double2 *>(U + v * N + n);
-            }
-            if (CART) rjac[r] = make_double2(P.crjac, P.crjac);
-            else {
-                const double2 j = __ldg(reinterpret_cast<const double2 *>(P.jac + dof0 + n));
-                rjac[r] = make_double2(fast_rcp(j.x), fast_rcp(j.y));
             }
         }
 #pragma unroll
@@ -1210,29 +1258,23 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
             const int n = 2 * (p0 + r * T);
             if (n >= nn) break;
             const int64_t dof = dof0 + n;
-            // apply_sourceterm! (MultielementDiscontinuous.jl:139-146): tabulated source, after the
-            // mass matrix; a warp-uniform branch that the default (no source) never takes
-            double2 src[NV];
-#pragma unroll
-            for (int v = 0; v < NV; v++)
-                src[v] = P.source ? __ldg(reinterpret_cast<const double2 *>(P.source + dof + ndof * v)) : make_double2(0.0, 0.0);
             if (P.mode == MODE_RHS) {
 #pragma unroll
-                for (int v = 0; v < NV; v++)
-                    __stcs(reinterpret_cast<double2 *>(P.k_out + dof + ndof * v),
-                           make_double2(fma(acc[r][v].x, rjac[r].x, src[v].x), fma(acc[r][v].y, rjac[r].y, src[v].y)));
+                for (int v = 0; v < NV; v++) __stcs(reinterpret_cast<double2 *>(P.k_out + dof + ndof * v), acc[r][v]);
             } else {
                 double2 un[NV];
 #pragma unroll
                 for (int v = 0; v < NV; v++) {
-                    const double kx = fma(acc[r][v].x, rjac[r].x, src[v].x), ky = fma(acc[r][v].y, rjac[r].y, src[v].y);
-                    double2 t;
-                    t.x = need_tmp ? fma(P.dt, kx, P.rkA * tv[r][v].x) : P.dt * kx;
-                    t.y = need_tmp ? fma(P.dt, ky, P.rkA * tv[r][v].y) : P.dt * ky;
-                    __stcs(reinterpret_cast<double2 *>(P.tmp + dof + ndof * v), t);
+                    double2 t = acc[r][v];
+                    if (need_tmp) { t.x = fma(P.rkA, tv[r][v].x, t.x); t.y = fma(P.rkA, tv[r][v].y, t.y); }
                     un[v].x = fma(P.rkB, t.x, uv[r][v].x);
                     un[v].y = fma(P.rkB, t.y, uv[r][v].y);
-                    __stcs(reinterpret_cast<double2 *>(P.u_out + dof + ndof * v), un[v]);
+                    if constexpr (BULK) {
+                        *reinterpret_cast<double2 *>(sT + v * N + n) = t;
+                    } else {
+                        __stcs(reinterpret_cast<double2 *>(P.tmp + dof + ndof * v), t);
+                        __stcs(reinterpret_cast<double2 *>(P.u_out + dof + ndof * v), un[v]);
+                    }
                     if constexpr (STAGE_TR) *reinterpret_cast<double2 *>(U + v * N + n) = un[v];
                 }
                 if (!STAGE_TR && P.colloc) {

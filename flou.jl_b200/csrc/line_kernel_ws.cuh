@@ -47,13 +47,7 @@ __device__ __forceinline__ bool ws_wide(const KParams &P)
 }
 
 template <class C>
-__global__ void
-#ifdef FLOU_LINE_MAXREG
-__maxnreg__(FLOU_LINE_MAXREG)
-#else
-__launch_bounds__(C::T, C::MINB)
-#endif
-line_kernel_ws(const __grid_constant__ KParams P)
+__device__ __forceinline__ void ws_body(const KParams &P)
 {
     constexpr int EQ = C::EQ, VOL = C::VOL, NV = C::NV;
     constexpr int NPTS = C::NPTS, NFACES = C::NFACES, NLINES = C::NLINES;
@@ -182,10 +176,23 @@ line_kernel_ws(const __grid_constant__ KParams P)
                 upd_sync();
             }
             if (wide) {
-                if (N >= 128 && C::NUPD == 1) phase3_pairs<C, 2, TU, true>(P, U, sT, sP, tu, nn, dof0, g);
-                else phase3_pairs<C, 1, TU, true>(P, U, sT, sP, tu, nn, dof0, g);
-                upd_sync();
-                if (P.mode != MODE_RHS && P.colloc) trace_pass<C, TU>(P, U, tu, nact, g);
+                if (N >= 128 && C::NUPD == 1) phase3_pairs<C, 2, TU, true, true>(P, U, sT, sP, tu, nn, dof0, g);
+                else phase3_pairs<C, 1, TU, true, true>(P, U, sT, sP, tu, nn, dof0, g);
+                if (P.mode != MODE_RHS) {
+                    // tmp (in sT) and the new state (in U) leave as TMA bulk stores, one per plane
+                    fence_async_smem();
+                    upd_sync();
+                    if (tu == 0) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++) {
+                            bulk_s2g(P.tmp + dof0 + ndof * v, sT + v * N, (unsigned)(nn * sizeof(double)));
+                            bulk_s2g(P.u_out + dof0 + ndof * v, U + v * N, (unsigned)(nn * sizeof(double)));
+                        }
+                        bulk_commit();
+                    }
+                    if (P.colloc) trace_pass<C, TU>(P, U, tu, nact, g);
+                    if (tu == 0) bulk_wait_read();      // sT and U may be refilled
+                }
             } else if (N >= 32 * C::NUPD) phase3_nodes<C, 2, TU>(P, U, sT, sP, tu, nn, dof0, g);
             else phase3_nodes<C, 1, TU>(P, U, sT, sP, tu, nn, dof0, g);
             upd_sync();                  // every update thread is done with sP, sT and sU[ub]
@@ -271,5 +278,13 @@ line_kernel_ws(const __grid_constant__ KParams P)
         }
     }
 }
+
+// The kernel: register budget either from the launch bounds (MINB CTAs of T threads per SM) or, for
+// the instances with two update warps, as an explicit cap (C::MAXREG: 2 CTAs x 224 threads x 144
+// registers fill the register file; the launch-bounds heuristic would stop at 128 and spill).
+template <class C>
+__global__ void __launch_bounds__(C::T, C::MINB) line_kernel_ws(const __grid_constant__ KParams P) { ws_body<C>(P); }
+template <class C>
+__global__ void __maxnreg__(C::MAXREG > 0 ? C::MAXREG : 255) line_kernel_ws_mr(const __grid_constant__ KParams P) { ws_body<C>(P); }
 
 }  // namespace flou
