@@ -199,6 +199,15 @@ struct LCfg {
 #else
     static constexpr int MAXREG = 0;
 #endif
+    // tmp and the new state leave the update warp as TMA bulk stores from shared memory instead of
+    // 128-bit global stores.  Measured (profiles/r2_kernel_notes.md): neutral at cfg4 (13.98 vs
+    // 13.66-14.16 ms), 7-9 % slower on the small groups of cfg2 / cfg3 (the wait for the stores'
+    // shared-memory reads sits on the update warp's critical path): off by default.
+#ifdef FLOU_LINE_BULK_STORE
+    static constexpr bool BULK_STORE = true;
+#else
+    static constexpr bool BULK_STORE = false;
+#endif
     static constexpr int T = WS ? TL + 32 * NUPD : TL;    // threads per CTA
     static constexpr int N = E * NPTS;                    // nodes of a group = plane stride
     static constexpr int L = E * NLINES;                  // line tasks of a group
@@ -1120,6 +1129,8 @@ __device__ __forceinline__ void phase1_nodes(const KParams &P, const double *U, 
 }
 
 // Phase 3 of a group: sum of the directional partial sums, mass matrix, RK stage update, traces.
+// Same arithmetic, operation by operation, as phase3_pairs (which path a group takes depends on the
+// alignment of its planes, i.e. on the partition: the results must not).
 template <class C, int RU, int T>
 __device__ __forceinline__ void phase3_nodes(const KParams &P, const double *U, const double *sT, const double *sP,
                                              int tid, int nn, int64_t dof0, int g)
@@ -1128,43 +1139,51 @@ __device__ __forceinline__ void phase3_nodes(const KParams &P, const double *U, 
     constexpr bool CART = C::CART, FOLD = C::FOLD;
     const int64_t ndof = P.ndof;
     const bool need_tmp = (P.mode == MODE_STAGE);
+    const double cs = (P.mode == MODE_RHS) ? 1.0 : P.dt;
+    double w[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) w[d] = (FOLD ? P.cmet[d] : 1.0) * (CART ? P.crjac : 1.0) * cs;
     for (int n0 = tid; n0 < nn; n0 += RU * T) {
-        double acc[RU][NV], tv[RU][NV], uv[RU][NV], rjac[RU];
+        double acc[RU][NV], tv[RU][NV], uv[RU][NV];
 #pragma unroll
         for (int u = 0; u < RU; u++) {
             const int n = min(n0 + u * T, nn - 1);
+            const double rj = CART ? 1.0 : fast_rcp(__ldg(P.jac + dof0 + n));
 #pragma unroll
             for (int v = 0; v < NV; v++) {
                 double s = 0.0;
+                const bool src = P.source != nullptr;
+                if (src) s = cs * __ldg(P.source + dof0 + n + ndof * v);
+                if (CART) {
 #pragma unroll
-                for (int d = 0; d < ND; d++) {
-                    const double x = sP[(d * NV + v) * N + n];
-                    s = FOLD ? fma(P.cmet[d], x, s) : s + x;
+                    for (int d = 0; d < ND; d++) {
+                        const double x = sP[(d * NV + v) * N + n];
+                        s = (!src && d == 0) ? w[0] * x : fma(w[d], x, s);
+                    }
+                } else {
+                    double q = 0.0;
+#pragma unroll
+                    for (int d = 0; d < ND; d++) q += sP[(d * NV + v) * N + n];
+                    s = fma(q, rj * cs, s);
                 }
                 acc[u][v] = s;
                 tv[u][v] = need_tmp ? sT[v * N + n] : 0.0;
                 uv[u][v] = U[v * N + n];
             }
-            rjac[u] = CART ? P.crjac : fast_rcp(__ldg(P.jac + dof0 + n));
         }
 #pragma unroll
         for (int u = 0; u < RU; u++) {
             const int n = n0 + u * T;
             if (n >= nn) break;
             const int64_t dof = dof0 + n;
-            // apply_sourceterm! (MultielementDiscontinuous.jl:139-146): tabulated source, after the mass matrix
-            double src[NV];
-#pragma unroll
-            for (int v = 0; v < NV; v++) src[v] = P.source ? __ldg(P.source + dof + ndof * v) : 0.0;
             if (P.mode == MODE_RHS) {
 #pragma unroll
-                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = fma(acc[u][v], rjac[u], src[v]);
+                for (int v = 0; v < NV; v++) P.k_out[dof + ndof * v] = acc[u][v];
             } else {
                 double un[NV];
 #pragma unroll
                 for (int v = 0; v < NV; v++) {
-                    const double kv = fma(acc[u][v], rjac[u], src[v]);
-                    const double t = need_tmp ? fma(P.dt, kv, P.rkA * tv[u][v]) : P.dt * kv;
+                    const double t = need_tmp ? fma(P.rkA, tv[u][v], acc[u][v]) : acc[u][v];
                     P.tmp[dof + ndof * v] = t;
                     un[v] = fma(P.rkB, t, uv[u][v]);
                     P.u_out[dof + ndof * v] = un[v];
@@ -1199,7 +1218,11 @@ __device__ __forceinline__ void phase3_nodes(const KParams &P, const double *U, 
 // Arithmetic: with w_d = metric_d / J * dt folded into three scalars,
 //   dt*k = sum_d w_d * partial_d (+ dt * source),  tmp = A*tmp + dt*k,  u = u + B*tmp
 // (5 fp64 instructions per value; MODE_RHS uses dt = 1 and stores k).
-template <class C, int RP, int T, bool STAGE_TR = false, bool BULK = false>
+// MODE: the pass mode as a compile-time constant (the caller branches once, warp-uniformly) or -1 =
+// read P.mode; SRC: 0 = no source term, 1 = read P.source (may be null).  The specialised copies
+// carry no selects / predicate logic for the other modes: the update warp is the critical path of
+// the kernel and a third of its instructions were such bookkeeping (profiles/r2_kernel_notes.md).
+template <class C, int RP, int T, bool STAGE_TR = false, bool BULK = false, int MODE = -1, int SRC = 1>
 __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_t<STAGE_TR, double, const double> *U,
                                              std::conditional_t<BULK, double, const double> *sT, const double *sP,
                                              int tid, int nn, int64_t dof0, int g)
@@ -1208,8 +1231,9 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
     constexpr bool CART = C::CART, FOLD = C::FOLD;
     static_assert(!BULK || STAGE_TR, "bulk stores go with the in-place update of the shared-memory copy");
     const int64_t ndof = P.ndof;
-    const bool need_tmp = (P.mode == MODE_STAGE);
-    const double cs = (P.mode == MODE_RHS) ? 1.0 : P.dt;
+    const int mode = MODE >= 0 ? MODE : P.mode;
+    const bool need_tmp = (mode == MODE_STAGE);
+    const double cs = (mode == MODE_RHS) ? 1.0 : P.dt;
     double w[ND];
 #pragma unroll
     for (int d = 0; d < ND; d++) w[d] = (FOLD ? P.cmet[d] : 1.0) * (CART ? P.crjac : 1.0) * cs;
@@ -1229,7 +1253,7 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
 #pragma unroll
             for (int v = 0; v < NV; v++) {
                 double2 s = make_double2(0.0, 0.0);
-                if (P.source) {
+                if (SRC && P.source) {
                     const double2 sv = __ldg(reinterpret_cast<const double2 *>(P.source + dof0 + n + ndof * v));
                     s = make_double2(cs * sv.x, cs * sv.y);
                 }
@@ -1237,7 +1261,8 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
 #pragma unroll
                     for (int d = 0; d < ND; d++) {
                         const double2 x = *reinterpret_cast<const double2 *>(sP + (d * NV + v) * N + n);
-                        s.x = fma(w[d], x.x, s.x); s.y = fma(w[d], x.y, s.y);
+                        if (!SRC && d == 0) { s.x = w[0] * x.x; s.y = w[0] * x.y; }
+                        else { s.x = fma(w[d], x.x, s.x); s.y = fma(w[d], x.y, s.y); }
                     }
                 } else {
                     double2 q = make_double2(0.0, 0.0);
@@ -1249,8 +1274,13 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
                     s.x = fma(q.x, rj.x * cs, s.x); s.y = fma(q.y, rj.y * cs, s.y);
                 }
                 acc[r][v] = s;
-                tv[r][v] = need_tmp ? *reinterpret_cast<const double2 *>(sT + v * N + n) : make_double2(0.0, 0.0);
-                uv[r][v] = *reinterpret_cast<const double2 *>(U + v * N + n);
+                if constexpr (MODE >= 0) {      // compile-time mode: only what the mode reads
+                    if (MODE == MODE_STAGE) tv[r][v] = *reinterpret_cast<const double2 *>(sT + v * N + n);
+                    if (MODE != MODE_RHS) uv[r][v] = *reinterpret_cast<const double2 *>(U + v * N + n);
+                } else {
+                    tv[r][v] = need_tmp ? *reinterpret_cast<const double2 *>(sT + v * N + n) : make_double2(0.0, 0.0);
+                    uv[r][v] = *reinterpret_cast<const double2 *>(U + v * N + n);
+                }
             }
         }
 #pragma unroll
@@ -1258,7 +1288,7 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
             const int n = 2 * (p0 + r * T);
             if (n >= nn) break;
             const int64_t dof = dof0 + n;
-            if (P.mode == MODE_RHS) {
+            if (mode == MODE_RHS) {
 #pragma unroll
                 for (int v = 0; v < NV; v++) __stcs(reinterpret_cast<double2 *>(P.k_out + dof + ndof * v), acc[r][v]);
             } else {

@@ -176,9 +176,16 @@ __device__ __forceinline__ void ws_body(const KParams &P)
                 upd_sync();
             }
             if (wide) {
-                if (N >= 128 && C::NUPD == 1) phase3_pairs<C, 2, TU, true, true>(P, U, sT, sP, tu, nn, dof0, g);
-                else phase3_pairs<C, 1, TU, true, true>(P, U, sT, sP, tu, nn, dof0, g);
-                if (P.mode != MODE_RHS) {
+                constexpr int RP3 = (N >= 128 && C::NUPD == 1) ? 2 : 1;
+                // one warp-uniform branch on the pass mode, then code without mode selects
+                if (P.source) phase3_pairs<C, RP3, TU, true, C::BULK_STORE>(P, U, sT, sP, tu, nn, dof0, g);
+                else if (P.mode == MODE_STAGE) phase3_pairs<C, RP3, TU, true, C::BULK_STORE, MODE_STAGE, 0>(P, U, sT, sP, tu, nn, dof0, g);
+                else if (P.mode == MODE_STAGE_FIRST) phase3_pairs<C, RP3, TU, true, C::BULK_STORE, MODE_STAGE_FIRST, 0>(P, U, sT, sP, tu, nn, dof0, g);
+                else phase3_pairs<C, RP3, TU, true, C::BULK_STORE, MODE_RHS, 0>(P, U, sT, sP, tu, nn, dof0, g);
+                if (!C::BULK_STORE) {
+                    upd_sync();
+                    if (P.mode != MODE_RHS && P.colloc) trace_pass<C, TU>(P, U, tu, nact, g);
+                } else if (P.mode != MODE_RHS) {
                     // tmp (in sT) and the new state (in U) leave as TMA bulk stores, one per plane
                     fence_async_smem();
                     upd_sync();
