@@ -54,11 +54,16 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
 // addresses, size a multiple of 16 bytes
 // The state and tmp are streamed exactly once per stage: L2 evict-first, so that the face-flux
 // blocks, which both neighbours of a face read, survive in L2 until their second use.
-__device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gmem_src, unsigned bytes, unsigned bar)
+__device__ __forceinline__ unsigned long long l2_evict_first()
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gmem_src, unsigned bytes, unsigned bar,
+                                         unsigned long long pol)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
@@ -800,7 +805,55 @@ __device__ __forceinline__ void splitdiv_nb_line(const KParams &P, const double 
 // and the buffer pointers used to be spilled to local memory there; with the shared-memory carve-out
 // this kernel asks for, L1 is too small to keep those lines: ncu showed 15 % of the stall samples on
 // the reloads, profiles/r2_kernel_notes.md).
-template <class C, bool FAST>
+// 16-byte aligned planes and an even node count per group: the state moves with TMA bulk copies
+// (and phase 3 works on node pairs); otherwise 8-byte cp.async
+template <class C>
+__device__ __forceinline__ bool ws_wide(const KParams &P)
+{
+    return ((P.ndof & 1) == 0) && (((int64_t)P.elem_first * C::NPTS & 1) == 0) && ((C::N & 1) == 0) &&
+           ((reinterpret_cast<uintptr_t>(P.u_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.tmp) & 15) == 0) &&
+           ((reinterpret_cast<uintptr_t>(P.u_out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.k_out) & 15) == 0) &&
+           (C::CART || (reinterpret_cast<uintptr_t>(P.jac) & 15) == 0);
+}
+
+// TMA loads of the next groups, issued by ONE line thread right after the update warp has released
+// the buffers (freeP): tmp of the group this thread is working on and the state two groups further
+// on, into the buffers phase 3 of the previous group has just finished with.  The update warp is
+// the kernel's critical path and these 12 copies with their descriptors were ~120 of its ~1100
+// instructions per group; the line threads wait at this point anyway.  (`wide` only: the cp.async
+// fallback needs a whole warp and stays on the update warp.)
+template <class C>
+__device__ __forceinline__ void ws_issue_loads(const KParams &P, int i_)
+{
+    extern __shared__ __align__(16) double lsmem[];
+    constexpr int E = C::E, NV = C::NV, N = C::N, NPTS = C::NPTS;
+    int cta, ncta;
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
+    asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(ncta));
+    const int64_t ndof = P.ndof;
+    const unsigned long long pol = l2_evict_first();
+    const int g = cta + i_ * ncta;
+    if (P.mode == MODE_STAGE) {
+        const int nn = min(E, P.elem_count - g * E) * NPTS;
+        const double *s0 = P.tmp + (int64_t)(P.elem_first + g * E) * NPTS;
+        mbar_expect_tx(WsBars<C>::fullT(), (unsigned)(NV * nn * sizeof(double)));
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+            bulk_g2s(lsmem + C::OFF_T + v * N, s0 + ndof * v, (unsigned)(nn * sizeof(double)), WsBars<C>::fullT(), pol);
+    }
+    const int g2 = g + 2 * ncta;
+    if (g2 * E < P.elem_count) {
+        const int ub = (i_ + 2) % 3;
+        const int nn = min(E, P.elem_count - g2 * E) * NPTS;
+        const double *s0 = P.u_in + (int64_t)(P.elem_first + g2 * E) * NPTS;
+        mbar_expect_tx(WsBars<C>::fullU(ub), (unsigned)(NV * nn * sizeof(double)));
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+            bulk_g2s(lsmem + C::OFF_U + ub * (NV * N) + v * N, s0 + ndof * v, (unsigned)(nn * sizeof(double)), WsBars<C>::fullU(ub), pol);
+    }
+}
+
+template <class C, bool FAST, bool ISSUE = true>
 __device__ __forceinline__ bool line_task(const KParams &P, int task, int64_t dof0, const volatile int *it)
 {
     extern __shared__ __align__(16) double lsmem[];
@@ -1015,7 +1068,10 @@ __device__ __forceinline__ bool line_task(const KParams &P, int task, int64_t do
         // kernel: once the update warp has consumed the partial sums of the previous group)
         {
             const int i_ = *it;
-            if (i_ > 0) mbar_wait(WsBars<C>::freeP(), (unsigned)((i_ - 1) & 1));
+            if (i_ > 0) {
+                mbar_wait(WsBars<C>::freeP(), (unsigned)((i_ - 1) & 1));
+                if (ISSUE && task == 0 && ws_wide<C>(P)) ws_issue_loads<C>(P, i_);
+            }
         }
 #pragma unroll
         for (int j = 0; j < NP; j++) {
@@ -1031,7 +1087,7 @@ __device__ __forceinline__ bool line_task(const KParams &P, int task, int64_t do
 template <class C>
 __device__ __noinline__ void line_task_exact(const KParams &P, int task, int64_t dof0, const volatile int *it)
 {
-    line_task<C, false>(P, task, dof0, it);
+    line_task<C, false, false>(P, task, dof0, it);      // redo: the loads were issued by the fast pass
 }
 
 // Node data of the line phase from the conservative state of one node (phase 1):

@@ -35,17 +35,6 @@ namespace flou {
 __device__ __forceinline__ int ws_cta() { int v; asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(v)); return v; }
 __device__ __forceinline__ int ws_nctas() { int v; asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(v)); return v; }
 
-// 16-byte aligned planes and an even node count per group: the update warp moves the state with TMA
-// bulk copies issued by one lane (and works on node pairs); otherwise 8-byte cp.async
-template <class C>
-__device__ __forceinline__ bool ws_wide(const KParams &P)
-{
-    return ((P.ndof & 1) == 0) && (((int64_t)P.elem_first * C::NPTS & 1) == 0) && ((C::N & 1) == 0) &&
-           ((reinterpret_cast<uintptr_t>(P.u_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.tmp) & 15) == 0) &&
-           ((reinterpret_cast<uintptr_t>(P.u_out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P.k_out) & 15) == 0) &&
-           (C::CART || (reinterpret_cast<uintptr_t>(P.jac) & 15) == 0);
-}
-
 template <class C>
 __device__ __forceinline__ void ws_body(const KParams &P)
 {
@@ -90,6 +79,7 @@ __device__ __forceinline__ void ws_body(const KParams &P)
         auto live = [&](int gg) { return gg * E < P.elem_count; };
         const bool need_tmp = (P.mode == MODE_STAGE);
         const bool wide = ws_wide<C>(P);
+        const unsigned long long pol = l2_evict_first();
         double *sU = smem + C::OFF_U, *sT = smem + C::OFF_T, *sP = smem + C::OFF_P, *sFn = smem + C::OFF_F;
         // NV planes of the nodes of group gg -> shared memory, completion on `bar`
         auto issue_planes = [&](const double *src, double *dst, int gg, unsigned bar, bool is_tmp) {
@@ -100,7 +90,7 @@ __device__ __forceinline__ void ws_body(const KParams &P)
                 if (lane == 0) {
                     mbar_expect_tx(bar, (unsigned)(NV * nn * sizeof(double)));
 #pragma unroll
-                    for (int v = 0; v < NV; v++) bulk_g2s(dst + v * N, s0 + ndof * v, (unsigned)(nn * sizeof(double)), bar);
+                    for (int v = 0; v < NV; v++) bulk_g2s(dst + v * N, s0 + ndof * v, (unsigned)(nn * sizeof(double)), bar, pol);
                 }
             } else {
                 for (int n = lane; n < nn; n += 32) {
@@ -206,8 +196,10 @@ __device__ __forceinline__ void ws_body(const KParams &P)
             mbar_arrive(B::freeP());
             {
                 const int i2 = *itU, gs2 = ws_nctas(), g2 = ws_cta() + i2 * gs2, ub2 = i2 % 3;
-                if (need_tmp && live(g2 + gs2)) issue_planes(P.tmp, sT, g2 + gs2, B::fullT(), true);
-                if (live(g2 + 3 * gs2)) issue_planes(P.u_in, sU + ub2 * (NV * N), g2 + 3 * gs2, B::fullU(ub2), false);
+                if (!wide) {     // TMA path: a line thread issues these copies (ws_issue_loads)
+                    if (need_tmp && live(g2 + gs2)) issue_planes(P.tmp, sT, g2 + gs2, B::fullT(), true);
+                    if (live(g2 + 3 * gs2)) issue_planes(P.u_in, sU + ub2 * (NV * N), g2 + 3 * gs2, B::fullU(ub2), false);
+                }
                 cp_async_commit();
                 __syncwarp();
                 if ((tu & 31) == 0) *itU = i2 + 1;
