@@ -213,6 +213,15 @@ struct LCfg {
 #else
     static constexpr bool BULK_STORE = false;
 #endif
+    // TMA loads of tmp / state issued by the line warps (a plane each) after freeP instead of by
+    // the update warp (ws_issue_loads).  Issued by line thread 0 alone the freeP wait dropped from
+    // 13 % to 7.5 % of the samples but warp 0 arrived late at the line threads' barrier (5.7 % ->
+    // 9.8 %): 12.94 vs 12.63 ms.
+#ifdef FLOU_LINE_ISSUE_BY_LINE
+    static constexpr bool LINE_ISSUE = true;
+#else
+    static constexpr bool LINE_ISSUE = false;
+#endif
     static constexpr int T = WS ? TL + 32 * NUPD : TL;    // threads per CTA
     static constexpr int N = E * NPTS;                    // nodes of a group = plane stride
     static constexpr int L = E * NLINES;                  // line tasks of a group
@@ -816,29 +825,30 @@ __device__ __forceinline__ bool ws_wide(const KParams &P)
            (C::CART || (reinterpret_cast<uintptr_t>(P.jac) & 15) == 0);
 }
 
-// TMA loads of the next groups, issued by ONE line thread right after the update warp has released
-// the buffers (freeP): tmp of the group this thread is working on and the state two groups further
-// on, into the buffers phase 3 of the previous group has just finished with.  The update warp is
-// the kernel's critical path and these 12 copies with their descriptors were ~120 of its ~1100
-// instructions per group; the line threads wait at this point anyway.  (`wide` only: the cp.async
-// fallback needs a whole warp and stays on the update warp.)
+// TMA loads of the next groups issued by the LINE warps (C::LINE_ISSUE; lane 0 of line warp w takes
+// the planes w, w + NW, ... of both copies) once the update warp has released the buffers (freeP):
+// tmp of the group the warp is working on and the state two groups further on, into the buffers
+// phase 3 of the previous group has just finished with.  The update warp is the kernel's critical
+// path and these copies with their descriptors are ~120 of its ~1100 instructions per group; spread
+// over the line warps they cost each ~25.  (`wide` only: the cp.async fallback stays on the update
+// warp.)  The mbarriers then count NW arrivals, one per issuing warp.
 template <class C>
-__device__ __forceinline__ void ws_issue_loads(const KParams &P, int i_)
+__device__ __forceinline__ void ws_issue_loads(const KParams &P, int i_, int w)
 {
     extern __shared__ __align__(16) double lsmem[];
-    constexpr int E = C::E, NV = C::NV, N = C::N, NPTS = C::NPTS;
+    constexpr int E = C::E, NV = C::NV, N = C::N, NPTS = C::NPTS, NW = C::TL / 32;
     int cta, ncta;
     asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
     asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(ncta));
     const int64_t ndof = P.ndof;
     const unsigned long long pol = l2_evict_first();
+    const int nplanes = w < NV ? (NV - w + NW - 1) / NW : 0;      // planes w, w + NW, ... of this warp
     const int g = cta + i_ * ncta;
     if (P.mode == MODE_STAGE) {
         const int nn = min(E, P.elem_count - g * E) * NPTS;
         const double *s0 = P.tmp + (int64_t)(P.elem_first + g * E) * NPTS;
-        mbar_expect_tx(WsBars<C>::fullT(), (unsigned)(NV * nn * sizeof(double)));
-#pragma unroll
-        for (int v = 0; v < NV; v++)
+        mbar_expect_tx(WsBars<C>::fullT(), (unsigned)(nplanes * nn * sizeof(double)));
+        for (int v = w; v < NV; v += NW)
             bulk_g2s(lsmem + C::OFF_T + v * N, s0 + ndof * v, (unsigned)(nn * sizeof(double)), WsBars<C>::fullT(), pol);
     }
     const int g2 = g + 2 * ncta;
@@ -846,14 +856,13 @@ __device__ __forceinline__ void ws_issue_loads(const KParams &P, int i_)
         const int ub = (i_ + 2) % 3;
         const int nn = min(E, P.elem_count - g2 * E) * NPTS;
         const double *s0 = P.u_in + (int64_t)(P.elem_first + g2 * E) * NPTS;
-        mbar_expect_tx(WsBars<C>::fullU(ub), (unsigned)(NV * nn * sizeof(double)));
-#pragma unroll
-        for (int v = 0; v < NV; v++)
+        mbar_expect_tx(WsBars<C>::fullU(ub), (unsigned)(nplanes * nn * sizeof(double)));
+        for (int v = w; v < NV; v += NW)
             bulk_g2s(lsmem + C::OFF_U + ub * (NV * N) + v * N, s0 + ndof * v, (unsigned)(nn * sizeof(double)), WsBars<C>::fullU(ub), pol);
     }
 }
 
-template <class C, bool FAST, bool ISSUE = true>
+template <class C, bool FAST>
 __device__ __forceinline__ bool line_task(const KParams &P, int task, int64_t dof0, const volatile int *it)
 {
     extern __shared__ __align__(16) double lsmem[];
@@ -1070,7 +1079,6 @@ __device__ __forceinline__ bool line_task(const KParams &P, int task, int64_t do
             const int i_ = *it;
             if (i_ > 0) {
                 mbar_wait(WsBars<C>::freeP(), (unsigned)((i_ - 1) & 1));
-                if (ISSUE && task == 0 && ws_wide<C>(P)) ws_issue_loads<C>(P, i_);
             }
         }
 #pragma unroll
@@ -1087,7 +1095,7 @@ __device__ __forceinline__ bool line_task(const KParams &P, int task, int64_t do
 template <class C>
 __device__ __noinline__ void line_task_exact(const KParams &P, int task, int64_t dof0, const volatile int *it)
 {
-    line_task<C, false, false>(P, task, dof0, it);      // redo: the loads were issued by the fast pass
+    line_task<C, false>(P, task, dof0, it);
 }
 
 // Node data of the line phase from the conservative state of one node (phase 1):

@@ -51,10 +51,13 @@ __device__ __forceinline__ void ws_body(const KParams &P)
     if (ws_cta() * E >= P.elem_count) return;
     if (threadIdx.x == 0) {
         const bool wide = ws_wide<C>(P);
-        for (int b = 0; b < 3; b++) mbar_init(B::fullU(b), wide ? 1 : 32);
+        // copies of a buffer: one issuing lane (TMA), or one per line warp (LINE_ISSUE), or the 32
+        // lanes of the update warp (cp.async fallback)
+        const unsigned nissue = wide ? (C::LINE_ISSUE ? TL / 32 : 1) : 32;
+        for (int b = 0; b < 3; b++) mbar_init(B::fullU(b), nissue);
         mbar_init(B::fullP(), TL);
         mbar_init(B::freeP(), 32 * C::NUPD);
-        mbar_init(B::fullT(), 1);
+        mbar_init(B::fullT(), wide && C::LINE_ISSUE ? TL / 32 : 1);
         mbar_init(B::fullF(0), 1);
         mbar_init(B::fullF(1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -89,6 +92,7 @@ __device__ __forceinline__ void ws_body(const KParams &P)
             if (wide) {
                 if (lane == 0) {
                     mbar_expect_tx(bar, (unsigned)(NV * nn * sizeof(double)));
+                    if (C::LINE_ISSUE) for (int k = 1; k < TL / 32; k++) mbar_arrive(bar);      // the barrier counts one arrival per line warp
 #pragma unroll
                     for (int v = 0; v < NV; v++) bulk_g2s(dst + v * N, s0 + ndof * v, (unsigned)(nn * sizeof(double)), bar, pol);
                 }
@@ -196,7 +200,7 @@ __device__ __forceinline__ void ws_body(const KParams &P)
             mbar_arrive(B::freeP());
             {
                 const int i2 = *itU, gs2 = ws_nctas(), g2 = ws_cta() + i2 * gs2, ub2 = i2 % 3;
-                if (!wide) {     // TMA path: a line thread issues these copies (ws_issue_loads)
+                if (!wide || !C::LINE_ISSUE) {     // LINE_ISSUE: a line thread issues the TMA copies (ws_issue_loads)
                     if (need_tmp && live(g2 + gs2)) issue_planes(P.tmp, sT, g2 + gs2, B::fullT(), true);
                     if (live(g2 + 3 * gs2)) issue_planes(P.u_in, sU + ub2 * (NV * N), g2 + 3 * gs2, B::fullU(ub2), false);
                 }
@@ -262,6 +266,19 @@ __device__ __forceinline__ void ws_body(const KParams &P)
             if (tid < nl) one_task(tid);
         } else {
             for (int task = tid; task < nl; task += TL) one_task(task);
+        }
+        if constexpr (C::LINE_ISSUE) {
+            // every line warp requests its planes of tmp (this group) and of the state two groups on,
+            // as soon as the update warp is done with the buffers (warps without a line task in a tail
+            // group wait here)
+            int t3;
+            asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t3));
+            const int i3 = *it;
+            if ((t3 & 31) == 0 && i3 > 0 && ws_wide<C>(P)) {
+                mbar_wait(B::freeP(), (unsigned)((i3 - 1) & 1));
+                ws_issue_loads<C>(P, i3, t3 >> 5);
+            }
+            __syncwarp();
         }
         mbar_arrive(B::fullP());
         // connectivity of the next group: in flight during the wait for its state and phase 1
