@@ -568,6 +568,8 @@ def main():
                "h2d_bytes_per_step": int(ndof_global * eq.nv * 8),
                "d2h_bytes_per_step": int(ndof_global * eq.nv * 8),
                "step": f"one timeintegrate() call = upload + {m} RK steps + download",
+               "note": f"the host<->device copies of a call are amortised over {m} RK steps ({m * nstages} stages); "
+                       "the upload is not overlapped with the first stage",
                "calls": args.e2e_calls, "pinned_host": pinned, "ms_per_call": te / args.e2e_calls * 1e3}
 
     ndof_local = disc.ndofs
