@@ -179,15 +179,20 @@ __global__ void __launch_bounds__(128, FLOU_FACE_MIN_BLOCKS)
 face_flux_kernel(const __grid_constant__ KParams P)
 {
     constexpr int NFP = ipow_c(NP, ND - 1);
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // face_reverse: the kernel starts where the element kernel of the previous stage ended (the
+    // tail of u_out / the traces is still in L2) and ends where the next element kernel starts
+    const int64_t blk = P.face_reverse ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const int64_t t = blk * blockDim.x + threadIdx.x;
     if (t >= (int64_t)P.face_count * NFP) return;
     const int fl = (int)(t / NFP), i = (int)(t - (int64_t)fl * NFP);
     const int f = P.face_first + fl;
 #if FLOU_FACE_PREFETCH > 0
     // the record of a face a later CTA will work on: pulled into L2 now, so that the first of the
     // two dependent round trips of that thread (record, then traces) is an L2 hit
-    if (i == 0 && fl + FLOU_FACE_PREFETCH < P.face_count)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.faces + f + FLOU_FACE_PREFETCH));
+    if (i == 0) {
+        const int fp = P.face_reverse ? fl - FLOU_FACE_PREFETCH : fl + FLOU_FACE_PREFETCH;
+        if (fp >= 0 && fp < P.face_count) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.faces + P.face_first + fp));
+    }
 #endif
     const FaceRec rec = P.faces[f];
     // faces keep Flou's global order, in which the master's local face changes rarely: the switch

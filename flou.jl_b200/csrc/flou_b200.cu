@@ -214,9 +214,17 @@ int32_t build_plan(const flou_b200_desc *d, bool cart, Plan &pl)
     {
         std::vector<int> order((size_t)nslots);
         for (int sidx = 0; sidx < nslots; sidx++) order[sidx] = sidx;
-        auto key = [&](int sidx) {
-            const int lfm_ = (int)d->elempos[pl.slot_face[sidx] * 2 + 0] - 1;
-            return (has_ghost[sidx] ? 8 : 0) + (lfm_ & 7);
+        // FLOU_B200_FACE_CHUNK = c > 0: inside each class, blocks of c consecutive master elements,
+        // and the master's local face inside a block (runs of up to c faces per direction keep the
+        // switch warp-uniform): the traces of a block's x-, y- and z-faces are then read close in
+        // time and the element kernel finds the fluxes of an element's own faces side by side.
+        // 0: one run per direction over the whole mesh (round 1).
+        static const long chunk = [] { const char *e = std::getenv("FLOU_B200_FACE_CHUNK"); return e ? std::atol(e) : 256L; }();
+        auto key = [&](int sidx) -> int64_t {
+            const int64_t gf = pl.slot_face[sidx];
+            const int lfm_ = (int)d->elempos[gf * 2 + 0] - 1;
+            const int64_t blk = chunk > 0 ? (d->eleminds[gf * 2 + 0] - 1) / chunk : 0;
+            return ((has_ghost[sidx] ? (int64_t)1 << 40 : 0) + blk) * 8 + (lfm_ & 7);
         };
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
         int n0 = 0;
@@ -983,6 +991,10 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     P.ghost = h->ghost;
     P.ndof = h->ndof;
     P.status = h->status;
+    {
+        const char *e = std::getenv("FLOU_B200_FACE_REVERSE");
+        P.face_reverse = (e && e[0] == '0') ? 0 : 1;
+    }
     // the memsets and table uploads above ran on the legacy default stream, which the handle's
     // non-blocking streams never synchronise with: finish them before the first upload / launch
     {

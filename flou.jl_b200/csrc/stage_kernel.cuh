@@ -135,6 +135,7 @@ struct KParams {
     const int2 *econn;          // [e*2nd + lf] = {flux slot, info: bit0 master, bits 1..3 orientation}
     double *Fn;                 // [(slot*nv + v)*NFP + i]: master-outward normal flux * face jac
     int face_first, face_count;
+    int face_reverse;           // face kernel walks the slots from the last to the first
     int split_faces;            // 1: stage kernel reads Fn instead of evaluating Riemann fluxes
     // halo
     const double *ghost;        // [(slot*nv + v)*NFP + k] in the sender's face-dof order
