@@ -218,8 +218,9 @@ int32_t build_plan(const flou_b200_desc *d, bool cart, Plan &pl)
         // and the master's local face inside a block (runs of up to c faces per direction keep the
         // switch warp-uniform): the traces of a block's x-, y- and z-faces are then read close in
         // time and the element kernel finds the fluxes of an element's own faces side by side.
-        // 0: one run per direction over the whole mesh (round 1).
-        static const long chunk = [] { const char *e = std::getenv("FLOU_B200_FACE_CHUNK"); return e ? std::atol(e) : 256L; }();
+        // 0 (default): one run per direction over the whole mesh.  Measured (profiles/r2j): blocks of
+        // 256 cost the face kernel 3-4 % at config 4 and gain nothing elsewhere.
+        static const long chunk = [] { const char *e = std::getenv("FLOU_B200_FACE_CHUNK"); return e ? std::atol(e) : 0L; }();
         auto key = [&](int sidx) -> int64_t {
             const int64_t gf = pl.slot_face[sidx];
             const int lfm_ = (int)d->elempos[gf * 2 + 0] - 1;

@@ -4,6 +4,8 @@
 O=gpurun_out/r2mg8; mkdir -p $O
 t0=$(date +%s)
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+timeout 600 python -m pytest tests/test_multigpu.py -m gpu -q -s > $O/pytest_multigpu.log 2>&1; echo "pytest rc=$?"; grep -E "multigpu\]|passed|failed" $O/pytest_multigpu.log | tail -8
+echo "t=$(( $(date +%s) - t0 )) s"
 run() {  # name env...
   name=$1; shift
   env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 20 --warmup 5 --no-e2e > $O/bench_n8_$name.json 2> $O/bench_n8_$name.err
