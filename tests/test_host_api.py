@@ -156,3 +156,29 @@ def test_hybrid_operator_constructors_and_descriptor():
     F.MultielementDisc(mesh, _std(2, nodes="GL"), eq, op, {}, create=False)      # Gauss nodes: all-surface form
     with pytest.raises(ValueError):
         F.MultielementDisc(mesh, _std(2, nv=1), F.LinearAdvection(1.0, 1.0), op, {}, create=False)
+
+
+def test_last_step_is_shortened_to_land_on_tfinal():
+    """OrdinaryDiffEq with adaptive=false takes full steps of dt and shortens the last one (tstops);
+    an integer number of steps stays one fused call."""
+    from flou_b200.time import _split_steps
+    assert _split_steps(0.0, 1.0, 0.25) == (4, 0.0)
+    assert _split_steps(0.0, 180 * 1e-4, 1e-4) == (180, 0.0)          # Sod KAT: no round-off remainder
+    n, last = _split_steps(0.0, 1.0, 0.3)
+    assert n == 3 and abs(last - 0.1) < 1e-15
+    n, last = _split_steps(0.5, 0.55, 0.1)
+    assert n == 0 and abs(last - 0.05) < 1e-15
+
+
+def test_source_tabulation_scalar_and_vectorised():
+    x = np.array([[0.0, 1.0], [0.5, 2.0], [1.0, 3.0]])
+    Q = np.arange(12.0).reshape(3, 4)
+    f = lambda q, xi, t: [xi[0], q[1], t, 0.0]
+    fv = lambda q, xx, t: np.stack([xx[:, 0], q[:, 1], np.full(len(xx), t), np.zeros(len(xx))], axis=1)
+    a = F.Source(f).tabulate(Q, x, 2.0, 4)
+    b = F.Source(fv, vectorized=True).tabulate(Q, x, 2.0, 4)
+    assert a.flags.f_contiguous and np.array_equal(a, b)
+    assert np.array_equal(a[:, 0], x[:, 0]) and np.array_equal(a[:, 2], [2.0] * 3)
+    assert F.Source(f, state=False, time=False).dynamic is False and F.Source(f, state=False).dynamic is True
+    # a closure that returns nothing (the reference's default source) adds nothing
+    assert not F.Source(lambda q, xi, t: None).tabulate(Q, x, 0.0, 4).any()
