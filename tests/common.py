@@ -11,8 +11,8 @@ _FLUX_O = {"std": O.FLUX_STDAVG, "lxf": O.FLUX_LXF, "cha": O.FLUX_CHANDRASEKHAR,
            "sca": O.FLUX_SCALARDISS, "mat": O.FLUX_MATRIXDISS}
 
 
-def box(nd):
-    return [0.0] * nd, [1.0 + 0.5 * d for d in range(nd)]
+def box(nd, scale=1.0):
+    return [0.0] * nd, [scale * (1.0 + 0.5 * d) for d in range(nd)]
 
 
 def random_state(ndof, nd, eq, gamma=1.4, seed=SEED, amp=0.5):
@@ -64,8 +64,9 @@ class Case:
 
     def __init__(self, nd, n, npn, nodes="GLL", eq="euler", op="split", tp=None, nf="mat",
                  avg="cha", intensity=1.0, periodic="all", bcs=None, general=False,
-                 perturb_amp=0.0, gamma=1.4, a=(2.0, -1.0, 0.5), blend=1.0):
+                 perturb_amp=0.0, gamma=1.4, a=(2.0, -1.0, 0.5), blend=1.0, box_scale=1.0):
         self.blend = blend
+        self.box_scale = box_scale      # domain = box_scale x the unit box (same dx on a mesh box_scale x finer)
         self.nd, self.n, self.np, self.nodes = nd, tuple(n), npn, nodes
         self.eq, self.op, self.tp, self.nf, self.avg = eq, op, tp, nf, avg
         self.intensity, self.gamma, self.a = intensity, gamma, tuple(a[:nd])
@@ -88,7 +89,7 @@ class Case:
 
     # ---------------------------------------------------------------- oracle side
     def oracle(self):
-        start, finish = box(self.nd)
+        start, finish = box(self.nd, self.box_scale)
         mesh = ocn.cartesian_mesh(start, finish, self.n)
         if self.perturb_amp > 0:
             h = min(mesh.dx)
@@ -119,7 +120,7 @@ class Case:
         line-per-thread element kernel) even on these small test meshes; "auto" lets the library
         pick (fused single-kernel stage below one element group per SM)."""
         import flou_b200 as F
-        start, finish = box(self.nd)
+        start, finish = box(self.nd, self.box_scale)
         mesh = F.CartesianMesh(self.nd, start, finish, self.n)
         if self.perturb_amp > 0:
             h = min(mesh.dx)
