@@ -99,7 +99,7 @@ class ClockSampler:
     """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,enforced.power.limit")
 
     def __init__(self, device):
         self.device, self.proc, self.path = device, None, None
@@ -124,7 +124,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, cap, reasons = [], [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in open(self.path):
@@ -135,6 +135,10 @@ class ClockSampler:
                     sm.append(float(f[1])); mx.append(float(f[2]))
                 except ValueError:
                     continue
+                try:
+                    pw.append(float(f[3])); cap.append(float(f[9]))
+                except (ValueError, IndexError):
+                    pass
                 for name, val in zip(names, f[5:9]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
@@ -158,6 +162,9 @@ class ClockSampler:
             out["sm_mhz"] = float(np.median(sm))
             out["sm_max_mhz"] = float(max(mx))
             out["samples"] = len(sm)
+        if pw and cap:      # board power against its enforced limit: what sw_power_cap refers to
+            out["power_w"] = float(np.median(pw))
+            out["power_limit_w"] = float(max(cap))
         out["reasons"] = sorted(reasons)
         return out
 

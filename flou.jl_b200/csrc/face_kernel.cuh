@@ -7,7 +7,8 @@
 //
 // Traces (project2faces!, Interfaces.jl:51-109) are not materialised for every face: with
 // collocated (GLL) nodes the x-face traces come from the trace array the stage kernel writes
-// with the state, y-/z-face traces are node layers read straight from u; partition-boundary
+// with the state (or from u as well when the handle keeps no array: P.tr_in == nullptr), y-/z-face
+// traces are node layers read straight from u; partition-boundary
 // faces read the halo buffer; Gauss nodes read the interpolated traces of emit_traces_kernel.
 #pragma once
 #include "stage_kernel.cuh"
@@ -23,11 +24,11 @@ __device__ __forceinline__ void load_trace(const KParams &P, int kind, int elem_
         const double *src = P.ghost + (int64_t)elem_or_slot * (NV * NFP) + k;
 #pragma unroll
         for (int v = 0; v < NV; v++) Q[v] = __ldg(src + v * NFP);
-    } else if (lf < 2) {        // x-faces: trace array
+    } else if (lf < 2 && P.tr_in) {     // x-faces: trace array (Gauss nodes; collocated nodes when kept)
         const double *src = P.tr_in + ((int64_t)elem_or_slot * 2 + lf) * (NV * NFP) + k;
 #pragma unroll
         for (int v = 0; v < NV; v++) Q[v] = __ldg(src + v * NFP);
-    } else if (P.colloc) {      // y-/z-faces: node layer of u
+    } else if (P.colloc) {      // node layer of u
         int nb, ns;
         line_of<ND, NP>(lf >> 1, k, nb, ns);
         const double *src = P.u_in + (int64_t)elem_or_slot * NPTS + nb + ((lf & 1) ? (NP - 1) * ns : 0);

@@ -404,6 +404,7 @@ struct flou_b200_handle {
     // two-kernel path
     bool split_faces = true;
     bool line_kernel = true;             // element kernel of the two-kernel stage: line per thread
+    bool keep_xtraces = true;            // FLOU_B200_XTRACE=0: no x-face trace array with collocated nodes
     FaceRec *faces = nullptr;
     int2 *econn = nullptr;
     double *Fn = nullptr;
@@ -418,13 +419,26 @@ struct flou_b200_handle {
 
 namespace {
 
+// The x-face trace array (written by the element kernel with the new state, read by the face
+// kernel / the fused kernel) is needed by the fused kernel and with Gauss nodes.  In the two-kernel
+// stage with collocated nodes the face kernel can read the x-face node layers of u like those of the
+// other directions (FLOU_B200_XTRACE=0).  Measured (profiles/r2m): at config 4 the element kernel
+// writes 4.2 GB less and loses its trace pass (ncu 12.70 -> 11.96 ms at the burst clock, no change
+// under the board's power cap), the face kernel reads u once more (20.8 -> 27.2 GB, 4.49 -> 5.05 ms):
+// stage +2.7 %; config 2 (L2-resident) -4.6 %.  Default: keep the array.
+bool uses_xtraces(const flou_b200_handle *h)
+{
+    return !(h->colloc && h->split_faces) || h->keep_xtraces;
+}
+
 // one RHS / stage pass over the owned elements (halo exchange included when partitioned)
 int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
                  const double *u_in, double *u_out)
 {
     KParams P = h->base;
     const int iin = (u_in == h->u[0]) ? 0 : 1;
-    if (!h->traces_valid) {
+    const bool xtr = uses_xtraces(h);
+    if (xtr && !h->traces_valid) {
         // traces of u_in (first pass after an upload, and every pass with Gauss nodes)
         CUDA_TRY(h->emit->launch(u_in, h->ndof, nullptr, (int)(h->ne_local * 2), 2,
                                  h->base.colloc, h->d_lm, h->d_lp, h->tr[iin], h->stream));
@@ -437,8 +451,8 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
         h->traces_valid = true;
     }
     P.tr_hi = h->tr_all;
-    P.tr_in = h->tr[iin];
-    P.tr_out = h->tr[iin ^ 1];
+    P.tr_in = xtr ? h->tr[iin] : nullptr;
+    P.tr_out = xtr ? h->tr[iin ^ 1] : nullptr;
     P.u_in = u_in;
     P.u_out = u_out;
     P.tmp = h->tmp;
@@ -963,10 +977,16 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         H_TRY(cudaMalloc((void **)&h->tr_all, all_bytes));
         H_TRY(cudaMemset(h->tr_all, 0, all_bytes));
     }
-    H_TRY(cudaMalloc((void **)&h->tr[0], trace_bytes));
-    H_TRY(cudaMalloc((void **)&h->tr[1], trace_bytes));
-    H_TRY(cudaMemset(h->tr[0], 0, trace_bytes));
-    H_TRY(cudaMemset(h->tr[1], 0, trace_bytes));
+    {
+        const char *x = std::getenv("FLOU_B200_XTRACE");
+        h->keep_xtraces = !(x && x[0] == '0');
+    }
+    if (uses_xtraces(h)) {
+        H_TRY(cudaMalloc((void **)&h->tr[0], trace_bytes));
+        H_TRY(cudaMalloc((void **)&h->tr[1], trace_bytes));
+        H_TRY(cudaMemset(h->tr[0], 0, trace_bytes));
+        H_TRY(cudaMemset(h->tr[1], 0, trace_bytes));
+    }
     H_TRY(cudaMemset(h->u[0], 0, state_bytes));
     H_TRY(cudaMemset(h->u[1], 0, state_bytes));
     H_TRY(cudaMemset(h->tmp, 0, state_bytes));
@@ -1203,7 +1223,7 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
     const bool use_graph = !(h->flags & FLOU_B200_FLAG_NO_GRAPH) && nsteps >= 4 && !h->profile &&
                            (h->nranks == 1 || h->nghost == 0 || (h->comm && mg_graph));
     int64_t done = 0;
-    if (use_graph && !h->traces_valid) {
+    if (use_graph && !h->traces_valid && uses_xtraces(h)) {
         // bring the traces of the current state up to date outside the captured region
         CUDA_TRY(h->emit->launch(h->u[h->cur], h->ndof, nullptr, (int)(h->ne_local * 2), 2,
                                  h->base.colloc, h->d_lm, h->d_lp, h->tr[h->cur], h->stream));

@@ -60,6 +60,14 @@ __device__ __forceinline__ unsigned long long l2_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// one lane of a converged warp (elect.sync: the compiler then knows that a single lane issues the
+// copies that follow and emits no loop over the active lanes around every UBLKCP)
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned p;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void bulk_g2s(double *smem_dst, const double *gmem_src, unsigned bytes, unsigned bar,
                                          unsigned long long pol)
 {
@@ -1253,8 +1261,9 @@ __device__ __forceinline__ void phase3_nodes(const KParams &P, const double *U, 
                     P.u_out[dof + ndof * v] = un[v];
                 }
                 // x-face traces of the new state for the next stage (collocated nodes only;
-                // Gauss nodes are handled by emit_traces_kernel)
-                if (P.colloc) {
+                // Gauss nodes are handled by emit_traces_kernel; no trace array: the face kernel
+                // reads the node layers of u)
+                if (P.colloc && P.tr_out) {
                     const int el = n / NPTS, node = n - el * NPTS;
                     int k, ii;
                     node_line<ND, NP>(node, 0, k, ii);
@@ -1338,12 +1347,15 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
                     s.x = fma(q.x, rj.x * cs, s.x); s.y = fma(q.y, rj.y * cs, s.y);
                 }
                 acc[r][v] = s;
+                // U is updated in place below (STAGE_TR): a lane without a pair of its own must not read
+                // the clamped pair, which another lane is about to overwrite (racecheck)
+                const bool own = STAGE_TR ? (p0 + r * T < npairs) : true;
                 if constexpr (MODE >= 0) {      // compile-time mode: only what the mode reads
                     if (MODE == MODE_STAGE) tv[r][v] = *reinterpret_cast<const double2 *>(sT + v * N + n);
-                    if (MODE != MODE_RHS) uv[r][v] = *reinterpret_cast<const double2 *>(U + v * N + n);
+                    if (MODE != MODE_RHS) uv[r][v] = own ? *reinterpret_cast<const double2 *>(U + v * N + n) : make_double2(0.0, 0.0);
                 } else {
                     tv[r][v] = need_tmp ? *reinterpret_cast<const double2 *>(sT + v * N + n) : make_double2(0.0, 0.0);
-                    uv[r][v] = *reinterpret_cast<const double2 *>(U + v * N + n);
+                    uv[r][v] = own ? *reinterpret_cast<const double2 *>(U + v * N + n) : make_double2(0.0, 0.0);
                 }
             }
         }
@@ -1371,7 +1383,7 @@ __device__ __forceinline__ void phase3_pairs(const KParams &P, std::conditional_
                     }
                     if constexpr (STAGE_TR) *reinterpret_cast<double2 *>(U + v * N + n) = un[v];
                 }
-                if (!STAGE_TR && P.colloc) {
+                if (!STAGE_TR && P.colloc && P.tr_out) {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const int m = n + h;

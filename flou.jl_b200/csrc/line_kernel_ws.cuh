@@ -35,6 +35,13 @@ namespace flou {
 __device__ __forceinline__ int ws_cta() { int v; asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(v)); return v; }
 __device__ __forceinline__ int ws_nctas() { int v; asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(v)); return v; }
 
+// FLOU_LINE_NO_ELECT: copies issued under `lane == 0` / a slot per lane (round-2 code before r2m)
+#ifndef FLOU_LINE_NO_ELECT
+#define FLOU_LINE_ELECT 1
+#define FLOU_ELECT (tu < 32 && elect_one())
+#else
+#define FLOU_ELECT (lane == 0)
+#endif
 template <class C>
 __device__ __forceinline__ void ws_body(const KParams &P)
 {
@@ -90,7 +97,7 @@ __device__ __forceinline__ void ws_body(const KParams &P)
             const int nn = min(E, P.elem_count - gg * E) * NPTS;
             const double *s0 = src + (int64_t)(P.elem_first + gg * E) * NPTS;
             if (wide) {
-                if (lane == 0) {
+                if (FLOU_ELECT) {
                     mbar_expect_tx(bar, (unsigned)(NV * nn * sizeof(double)));
                     if (C::LINE_ISSUE) for (int k = 1; k < TL / 32; k++) mbar_arrive(bar);      // the barrier counts one arrival per line warp
 #pragma unroll
@@ -124,15 +131,42 @@ __device__ __forceinline__ void ws_body(const KParams &P)
             const int nrec = min(E, P.elem_count - gg * E) * NFACES;
             const unsigned bar = B::fullF(buf);
             if (tu >= 32) return;
-            if (lane == 0) mbar_expect_tx(bar, (unsigned)(nrec * FNB * sizeof(double)));
             cp_async_wait<0>();          // this lane's slots (requested an iteration ago)
             __syncwarp();
+#ifdef FLOU_LINE_ELECT
+            // one elected lane issues every copy: straight-line uniform-datapath code (a copy per lane
+            // is serialised by a loop over the active lanes with an ELECT / branch pair per copy)
+            if (elect_one()) {
+                mbar_expect_tx(bar, (unsigned)(nrec * FNB * sizeof(double)));
+                auto copy = [&](int r, int slot) {
+                    bulk_g2s_keep(sFn + buf * FSET + r * FNB, P.Fn + (int64_t)slot * FNB, (unsigned)(FNB * sizeof(double)), bar);
+                };
+                if constexpr (E * NFACES <= 16) {
+                    // slots first (the copies are volatile asm: loads are not moved across them)
+                    int sl[E * NFACES];
+#pragma unroll
+                    for (int r = 0; r < E * NFACES; r++) sl[r] = sSlot[r];
+                    if (nrec == E * NFACES) {
+#pragma unroll
+                        for (int r = 0; r < E * NFACES; r++) copy(r, sl[r]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < E * NFACES; r++) if (r < nrec) copy(r, sl[r]);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int r = 0; r < nrec; r++) copy(r, sSlot[r]);
+                }
+            }
+#else
+            if (lane == 0) mbar_expect_tx(bar, (unsigned)(nrec * FNB * sizeof(double)));
 #pragma unroll
             for (int q = 0; q < RN; q++) {
                 const int r = lane + 32 * q;
                 if (r < nrec)
                     bulk_g2s_keep(sFn + buf * FSET + r * FNB, P.Fn + (int64_t)sSlot[r] * FNB, (unsigned)(FNB * sizeof(double)), bar);
             }
+#endif
             __syncwarp();
         };
         {
@@ -155,6 +189,7 @@ __device__ __forceinline__ void ws_body(const KParams &P)
             const int nact = min(E, P.elem_count - g * E), nn = nact * NPTS;
             const int64_t dof0 = (int64_t)(P.elem_first + g * E) * NPTS;
             double *U = sU + ub * (NV * N);
+            bool released = false;       // freeP arrived and tmp of the next group requested early (wide path)
             mbar_wait(B::fullP(), i & 1);
             // every line thread is done with the flux blocks of group i: their buffer takes those of
             // group i+2 (in flight during a whole iteration of the line threads)
@@ -177,8 +212,16 @@ __device__ __forceinline__ void ws_body(const KParams &P)
                 else if (P.mode == MODE_STAGE_FIRST) phase3_pairs<C, RP3, TU, true, C::BULK_STORE, MODE_STAGE_FIRST, 0>(P, U, sT, sP, tu, nn, dof0, g);
                 else phase3_pairs<C, RP3, TU, true, C::BULK_STORE, MODE_RHS, 0>(P, U, sT, sP, tu, nn, dof0, g);
                 if (!C::BULK_STORE) {
+                    // sP and sT are free as soon as phase 3 is through: the line threads may store the
+                    // next partial sums and tmp of the next group may land while the traces are written
                     upd_sync();
-                    if (P.mode != MODE_RHS && P.colloc) trace_pass<C, TU>(P, U, tu, nact, g);
+                    mbar_arrive(B::freeP());
+                    released = true;
+                    if (!C::LINE_ISSUE && need_tmp) {
+                        const int gn = ws_cta() + (*itU + 1) * ws_nctas();      // re-read, not carried across phase 3
+                        if (live(gn)) issue_planes(P.tmp, sT, gn, B::fullT(), true);
+                    }
+                    if (P.mode != MODE_RHS && P.colloc && P.tr_out) trace_pass<C, TU>(P, U, tu, nact, g);
                 } else if (P.mode != MODE_RHS) {
                     // tmp (in sT) and the new state (in U) leave as TMA bulk stores, one per plane
                     fence_async_smem();
@@ -197,11 +240,11 @@ __device__ __forceinline__ void ws_body(const KParams &P)
             } else if (N >= 32 * C::NUPD) phase3_nodes<C, 2, TU>(P, U, sT, sP, tu, nn, dof0, g);
             else phase3_nodes<C, 1, TU>(P, U, sT, sP, tu, nn, dof0, g);
             upd_sync();                  // every update thread is done with sP, sT and sU[ub]
-            mbar_arrive(B::freeP());
+            if (!released) mbar_arrive(B::freeP());
             {
                 const int i2 = *itU, gs2 = ws_nctas(), g2 = ws_cta() + i2 * gs2, ub2 = i2 % 3;
                 if (!wide || !C::LINE_ISSUE) {     // LINE_ISSUE: a line thread issues the TMA copies (ws_issue_loads)
-                    if (need_tmp && live(g2 + gs2)) issue_planes(P.tmp, sT, g2 + gs2, B::fullT(), true);
+                    if (!released && need_tmp && live(g2 + gs2)) issue_planes(P.tmp, sT, g2 + gs2, B::fullT(), true);
                     if (live(g2 + 3 * gs2)) issue_planes(P.u_in, sU + ub2 * (NV * N), g2 + 3 * gs2, B::fullU(ub2), false);
                 }
                 cp_async_commit();

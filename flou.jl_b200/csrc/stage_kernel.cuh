@@ -892,7 +892,7 @@ stage_kernel(const __grid_constant__ KParams P)
 #ifdef FLOU_EXPERIMENT_SKIP_TRACE_WRITE
                 if (P.colloc && P.elem_count < 0) {
 #else
-                if (P.colloc) {
+                if (P.colloc && P.tr_out) {
 #endif
                     {
                         int k, ii;

@@ -28,6 +28,27 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    # the bounded sample the CPU legs time is part of the config (same in both arms)
+    assert d["config"]["cpu_sample"]["elements"] == [32, 32] and d["config"]["cpu_sample"]["ndofs"] == 16384
+    assert "32x32 elements" in d["cpu_baseline"]["sample"]
+
+
+def test_reference_arm_uses_every_host_thread_under_torchrun_environment():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the arm must not silently become a
+    single-threaded baseline, and `cores` must be what OpenMP really uses."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                          "cfg1", "--steps", "1", "--warmup", "0", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip()][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    # ranks other than 0 exit without work and without output
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                          "cfg1", "--steps", "1", "--warmup", "0", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
 
 
 def test_product_arm_fails_loudly_without_a_gpu():
