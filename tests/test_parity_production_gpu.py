@@ -126,3 +126,32 @@ def test_config5_refined_8x8(gpu, tmp_path):
     sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), 5 * dt, dt=dt)
     assert sol is not None and relerr(sol.u[-1], ref) <= STATE_TOL
     disc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [PRODUCTION[0][0], PRODUCTION[1][0], PRODUCTION[5][0], PRODUCTION[8][0]],
+                         ids=lambda c: repr(c))
+def test_stage_without_x_trace_array(gpu, case, monkeypatch):
+    """FLOU_B200_XTRACE=0 (read when a handle is created): the element kernel writes no x-face
+    traces and the face kernel reads the x-face node layers of u like those of the other
+    directions.  Same numbers as the default path, bit for bit, and the oracle's within tolerance."""
+    import flou_b200 as F
+    import oracle as O
+    orc = case.oracle()
+    Q = np.asfortranarray(0.9 * smooth_state(orc.coords, case.nd, case.eq)
+                          + 0.1 * random_state(orc.ndof, case.nd, case.eq, amp=0.3))
+    dt = 2e-5
+    out = {}
+    for xtr in ("1", "0"):
+        monkeypatch.setenv("FLOU_B200_XTRACE", xtr)
+        disc, eq = case.product()
+        dQ = disc.new_state()
+        F.rhs(dQ, Q, F.EquationConfig(disc, eq), 0.0)
+        u = Q.copy(order="F")
+        sol, _ = F.timeintegrate(u, disc, eq, F.ORK256(), 5 * dt, dt=dt)
+        assert sol is not None
+        out[xtr] = (dQ.copy(), np.array(sol.u[-1]))
+        disc.close()
+    assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
+    assert relerr(out["0"][0], orc.rhs(Q)) <= RHS_TOL
+    assert relerr(out["0"][1], orc.lsrk2n(Q, O.ORK256, dt, 5)) <= STATE_TOL
