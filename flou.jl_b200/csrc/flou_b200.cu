@@ -22,6 +22,7 @@
 #include "launch.h"
 #include "cfl_kernel.cuh"
 #include "monitor_kernel.cuh"
+#include "project_kernel.cuh"
 
 using namespace flou;
 
@@ -1331,6 +1332,45 @@ int32_t flou_b200_boundary_traces(flou_b200_handle *h, double *Qin, int64_t *ord
     CUDA_TRY(cudaMemcpyAsync(Qin, h->bd_traces, sizeof(double) * (size_t)n * h->nfp * h->nv,
                              cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return FLOU_B200_OK;
+}
+
+int32_t flou_b200_project_equispaced(flou_b200_handle *h, const double *Q, int32_t neq, const double *node2eq,
+                                     double *Qe)
+{
+    if (!h || !node2eq || !Qe) return fail(FLOU_B200_EINVAL, "null argument");
+    if (neq < 1 || neq > 64) return fail(FLOU_B200_EINVAL, "number of equispaced nodes per direction out of range (1..64)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    double *state = nullptr;
+    if (int32_t rc = query_state(h, Q, &state)) return rc;
+    int64_t nout = neq;
+    for (int d = 1; d < h->nd; d++) nout *= neq;
+    const size_t out_elems = (size_t)h->ne_local * nout * h->nv;
+    // the RHS buffer doubles as the output when it is large enough (neq == np: same size as a state)
+    double *out = h->k, *own = nullptr;
+    if (out_elems > (size_t)h->ndof * h->nv) {
+        CUDA_TRY(cudaMalloc((void **)&own, sizeof(double) * out_elems));
+        out = own;
+    }
+    double *dM = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dM, sizeof(double) * (size_t)neq * h->np);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dM, node2eq, sizeof(double) * (size_t)neq * h->np, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->ne_local, (int64_t)sms * 8));
+        const size_t smem = sizeof(double) * ((size_t)neq * h->np + (size_t)h->npts);
+        project_equispaced_kernel<<<grid, 256, smem, h->stream>>>(state, h->ndof, h->nv, h->nd, h->np, neq, dM,
+                                                                  h->ne_local, out);
+        e = cudaGetLastError();
+        h->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Qe, out, sizeof(double) * out_elems, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dM);
+    cudaFree(own);
+    CUDA_TRY(e);
     return FLOU_B200_OK;
 }
 

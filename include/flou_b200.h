@@ -243,6 +243,17 @@ int32_t flou_b200_boundary_traces(flou_b200_handle *h, double *Qin, int64_t *ord
  * device-resident state, followed by the stage limiter when one is set: the unit the host loops
  * over when source or boundary data change from stage to stage. */
 int32_t flou_b200_lsrk2n_stage(flou_b200_handle *h, double A, double B, double dt, int32_t first);
+/* Snapshot path: the state projected to equispaced nodes, element by element, what
+ * pointdata2VTKHDF (src/FlouSpatial/IO.jl:78-97) computes with project2equispaced!
+ * (StdRegions/StdRegions.jl:232-238) before FlouBiz.add_solution! writes it.
+ * Q: host state (ndofs_local, nv) column-major, or NULL = the device-resident state.
+ * node2eq: the 1-D interpolation matrix std.node2eq of the segment, row-major [neq][np]
+ * (interp_matrix(range(-1, 1, neq), basis), StdSegment.jl:56-58); quads and hexes use its
+ * Kronecker products (StdQuad.jl:52-53, StdHex.jl:57-61), applied here as nested 1-D sums.
+ * Qe: host, Qe[p + npoints*v] with npoints = nelements_local * neq^nd and p = element*neq^nd +
+ * equispaced node (x fastest): one contiguous vector per variable, as the reference appends them. */
+int32_t flou_b200_project_equispaced(flou_b200_handle *h, const double *Q, int32_t neq, const double *node2eq,
+                                     double *Qe);
 
 int32_t flou_b200_synchronize(flou_b200_handle *h);
 /* sticky device flags: bit 0 = non-positive density/pressure or NaN seen since the last

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, evidence run of the committed build on one B200 (repo root on the GPU box)
-O=gpurun_out/r2_final; mkdir -p $O
+O=gpurun_out/r2_final2; mkdir -p $O
 t0=$(date +%s)
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
 timeout 1500 python -m pytest tests -m gpu -q --durations=5 > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_gpu.log
