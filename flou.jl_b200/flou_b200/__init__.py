@@ -11,6 +11,8 @@ from .equations import (ChandrasekharAverage, EulerEquation, EulerInflowBC, Eule
                         HybridDivOperator, ScalarDissipation, SplitDivOperator, StdAverage, StrongDivOperator,
                         gaussian_bump, normal_shockwave, nvariables, soundvelocity, spatialdim,
                         vars_prim2cons)
+from .io import (FlouFile, add_celldata, add_fielddata, add_pointdata, add_solution, close_file,
+                 get_save_callback, open_for_write, pointdata2VTKHDF, vtk_connectivities, vtk_type)
 from .gmshmesh import RawHexMesh, RawMesh, UnstructuredMesh, read_msh, refine, write_msh
 from .monitors import (MonitorOutput, get_cfl_callback, get_limiter, get_limiter_callback, get_monitor,
                        get_monitor_callback, list_limiters, list_monitors, make_callback_list)

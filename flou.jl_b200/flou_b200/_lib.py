@@ -76,6 +76,7 @@ SYMBOLS = {
     "flou_b200_set_bc_table": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "flou_b200_boundary_traces": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "flou_b200_lsrk2n_stage": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int32]),
+    "flou_b200_project_equispaced": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "flou_b200_synchronize": (C.c_int32, [C.c_void_p]),
     "flou_b200_status": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     "flou_b200_last_error": (C.c_char_p, []),

@@ -118,7 +118,7 @@ class DGSEMrec:
 class _StdRegion:
     nd = 0
 
-    def __init__(self, solbasis, rec, nvars=1):
+    def __init__(self, solbasis, rec, nvars=1, nequispaced=None):
         if rec.basis is not solbasis:
             raise ValueError("over-integration (solbasis != flux basis) is outside the B200 hot path")
         b = rec.basis
@@ -141,6 +141,16 @@ class _StdRegion:
         for g_ in wg:
             w = w * g_.reshape(-1, order="F")
         self.w = w
+        # equispaced nodes for output (StdSegment.jl:40,55-58): as many as solution nodes by default;
+        # quads and hexes use the Kronecker products of the 1-D matrix (StdQuad.jl:52-53, StdHex.jl:57-61)
+        ne_ = n if nequispaced is None else int(nequispaced)
+        self.xe1d = np.linspace(-1.0, 1.0, ne_) if ne_ > 1 else np.zeros(1)
+        self.node2eq1d = np.ascontiguousarray(b.interp_matrix(self.xe1d))       # [neq][np]
+        ge = np.meshgrid(*([self.xe1d] * nd), indexing="ij")
+        self.xe = np.stack([g.reshape(-1, order="F") for g in ge], axis=1)      # x fastest
+
+    def nequispaced(self):
+        return len(self.xe)
 
     def ndofs(self):
         return self.np ** self.nd

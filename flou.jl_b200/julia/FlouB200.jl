@@ -324,6 +324,28 @@ lsrk2n_stage!(disc::B200Disc, A, B, dt, first::Bool) =
                 disc.handle, Float64(A), Float64(B), Float64(dt), Int32(first)))
 
 """
+    pointdata2VTKHDF(Q, disc, node2eq1d, nv)
+
+Device version of `FlouBiz.pointdata2VTKHDF(Q, disc::MultielementDisc)` (src/FlouSpatial/IO.jl:78-97):
+the state at the equispaced nodes of every element, one vector per variable, ready for
+`write(file.handler, "VTKHDF/PointData/name", data)`.  `node2eq1d` is the `node2eq` of the SEGMENT
+the element region is built from (`std.face` of a quad, `std.face.face` of a hex: StdQuad.jl:43,
+StdHex.jl:44-45): the 1-D
+interpolation matrix whose Kronecker products the quads and hexes use.  `Q === nothing` projects
+the device-resident state (what a save callback wants between steps).
+"""
+function pointdata2VTKHDF(Q::Union{Nothing,Matrix{Float64}}, disc::B200Disc{ND}, node2eq1d::Matrix{Float64},
+                          nv::Integer) where {ND}
+    neq, np = size(node2eq1d)
+    M = permutedims(node2eq1d)                       # the library reads [neq][np] row-major
+    out = Matrix{Float64}(undef, nelements(disc.disc.mesh) * neq^ND, nv)
+    check(ccall((:flou_b200_project_equispaced, lib), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}),
+                disc.handle, Q === nothing ? C_NULL : Q, Int32(neq), M, out))
+    return [out[:, v] for v in 1:nv]
+end
+
+"""
     timeintegrate_stagewise(Q0, disc, solver, tf, refresh!; dt)
 
 The RK loop for discretisations whose source term or `GenericBC` closures depend on the state or
