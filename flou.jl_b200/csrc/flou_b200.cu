@@ -28,6 +28,16 @@ using namespace flou;
 
 namespace {
 
+// FLOU_B200_SLAB = n > 0: the two-kernel stage of a single-GPU handle runs slab by slab -- face kernel
+// over the faces mastered by n consecutive elements, then the element kernel over those elements --
+// so that a slab's flux blocks (and the state the face kernel has just read) are still in L2 when
+// the element kernel asks for them.  0 (default): one face launch and one element launch per stage.
+long slab_elements()
+{
+    static const long v = [] { const char *e = std::getenv("FLOU_B200_SLAB"); return e ? std::atol(e) : 0L; }();
+    return v;
+}
+
 thread_local std::string g_last_error;
 
 int32_t fail(int32_t code, const std::string &msg)
@@ -221,7 +231,10 @@ int32_t build_plan(const flou_b200_desc *d, bool cart, Plan &pl)
         // time and the element kernel finds the fluxes of an element's own faces side by side.
         // 0 (default): one run per direction over the whole mesh.  Measured (profiles/r2j): blocks of
         // 256 cost the face kernel 3-4 % at config 4 and gain nothing elsewhere.
-        static const long chunk = [] { const char *e = std::getenv("FLOU_B200_FACE_CHUNK"); return e ? std::atol(e) : 0L; }();
+        static const long chunk_env = [] { const char *e = std::getenv("FLOU_B200_FACE_CHUNK"); return e ? std::atol(e) : 0L; }();
+        // slab-wise stage (FLOU_B200_SLAB, single GPU): the face slots are blocked by slab
+        const long slab = slab_elements();
+        const long chunk = (slab > 0 && nranks == 1) ? slab : chunk_env;
         auto key = [&](int sidx) -> int64_t {
             const int64_t gf = pl.slot_face[sidx];
             const int lfm_ = (int)d->elempos[gf * 2 + 0] - 1;
@@ -410,6 +423,9 @@ struct flou_b200_handle {
     int2 *econn = nullptr;
     double *Fn = nullptr;
     int n_faces = 0, n_faces_local_only = 0;
+    // slab-wise stage: launch list {kind (0 face / 1 element), first, count}
+    struct SlabOp { int kind, first, count; };
+    std::vector<SlabOp> slab_ops;
     // source term (row a13) and boundary data that change between stages
     double *source = nullptr;            // [dof + ndof*v], allocated by the first flou_b200_set_source
     int64_t bc_rows = 0;                 // rows (boundary-face nodes) of bc_table
@@ -476,6 +492,20 @@ int32_t run_pass(flou_b200_handle *h, int mode, double A, double B, double dt,
             if (h->profile) {
                 for (auto &e : ev) { CUDA_TRY(cudaEventCreate(&e)); h->prof_events.push_back(e); }
                 CUDA_TRY(cudaEventRecord(ev[0], h->stream));
+            }
+            if (!h->slab_ops.empty() && !h->profile) {
+                for (const auto &op : h->slab_ops) {
+                    if (op.kind == 0) {
+                        P.face_first = op.first; P.face_count = op.count;
+                        CUDA_TRY(h->stage->launch_faces(P, h->stream));
+                    } else {
+                        P.elem_first = op.first; P.elem_count = op.count;
+                        CUDA_TRY(h->stage->launch_lines(P, h->stream));
+                    }
+                }
+                h->launches += (int64_t)h->slab_ops.size();
+                if (mode != MODE_RHS) h->traces_valid = out_traces;
+                return FLOU_B200_OK;
             }
             CUDA_TRY(h->stage->launch_faces(P, h->stream));
             if (h->profile) CUDA_TRY(cudaEventRecord(ev[1], h->stream));
@@ -844,6 +874,32 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
     h->n_faces_local_only = pl.n_faces_local_only;
     H_TRY(upload(&h->faces, pl.faces));
     H_TRY(upload(&h->econn, pl.econn));
+    if (slab_elements() > 0 && h->nranks == 1 && h->split_faces && h->line_kernel && h->ne_local > slab_elements()) {
+        const int64_t slab = slab_elements(), ne = h->ne_local;
+        const int nslab = (int)((ne + slab - 1) / slab), NFc = 2 * nd;
+        // face slots are sorted by the slab of their master element: first slot of every slab
+        std::vector<int> ffirst((size_t)nslab + 1, h->n_faces), blk_of((size_t)h->n_faces, 0);
+        for (int sl = h->n_faces - 1; sl >= 0; sl--) {
+            const int b = (int)(pl.faces[sl].em / slab);
+            blk_of[sl] = b;
+            ffirst[b] = sl;
+        }
+        for (int b = nslab - 1; b >= 0; b--) ffirst[b] = std::min(ffirst[b], ffirst[b + 1]);
+        ffirst[0] = 0;
+        bool sorted = true;
+        for (int sl = 1; sl < h->n_faces; sl++) sorted = sorted && blk_of[sl - 1] <= blk_of[sl];
+        // an element slab can run once the last face slab any of its faces lives in is done
+        std::vector<int> need((size_t)nslab, 0);
+        for (int64_t e = 0; e < ne; e++)
+            for (int lf = 0; lf < NFc; lf++)
+                need[e / slab] = std::max(need[e / slab], blk_of[pl.econn[(size_t)e * NFc + lf].x]);
+        for (int c = 0; c < nslab && sorted; c++) {
+            if (ffirst[c + 1] > ffirst[c]) h->slab_ops.push_back({0, ffirst[c], ffirst[c + 1] - ffirst[c]});
+            for (int b = 0; b < nslab; b++)
+                if (need[b] == c)
+                    h->slab_ops.push_back({1, (int)(b * slab), (int)std::min<int64_t>(slab, ne - b * slab)});
+        }
+    }
     if (h->split_faces)
         H_TRY(cudaMalloc((void **)&h->Fn, sizeof(double) * std::max<size_t>((size_t)h->n_faces * fn_block(h->nv, h->nfp), 2)));
     if (!cart) {
