@@ -418,7 +418,7 @@ struct flou_b200_handle {
     // two-kernel path
     bool split_faces = true;
     bool line_kernel = true;             // element kernel of the two-kernel stage: line per thread
-    bool keep_xtraces = true;            // FLOU_B200_XTRACE=0: no x-face trace array with collocated nodes
+    bool keep_xtraces = true;            // FLOU_B200_XTRACE=0 / 1 overrides the size rule (see uses_xtraces)
     FaceRec *faces = nullptr;
     int2 *econn = nullptr;
     double *Fn = nullptr;
@@ -442,7 +442,7 @@ namespace {
 // other directions (FLOU_B200_XTRACE=0).  Measured (profiles/r2m): at config 4 the element kernel
 // writes 4.2 GB less and loses its trace pass (ncu 12.70 -> 11.96 ms at the burst clock, no change
 // under the board's power cap), the face kernel reads u once more (20.8 -> 27.2 GB, 4.49 -> 5.05 ms):
-// stage +2.7 %; config 2 (L2-resident) -4.6 %.  Default: keep the array.
+// stage +2.7 %; config 2 (L2-resident) -4.6 %.  Default: the array only for states beyond 48 MB.
 bool uses_xtraces(const flou_b200_handle *h)
 {
     return !(h->colloc && h->split_faces) || h->keep_xtraces;
@@ -1035,8 +1035,10 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         H_TRY(cudaMemset(h->tr_all, 0, all_bytes));
     }
     {
+        // default: no x-face trace array while the state fits in L2 (the face kernel's extra reads of u
+        // are L2 hits there: config 2 -4.6 % per stage), the array beyond (config 4: +2.7 % without it)
         const char *x = std::getenv("FLOU_B200_XTRACE");
-        h->keep_xtraces = !(x && x[0] == '0');
+        h->keep_xtraces = x ? x[0] != '0' : state_bytes > ((size_t)48 << 20);
     }
     if (uses_xtraces(h)) {
         H_TRY(cudaMalloc((void **)&h->tr[0], trace_bytes));

@@ -93,7 +93,7 @@ BC_CASES = [
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", BC_CASES, ids=repr)
-def test_rhs_with_boundary_conditions(gpu, case):
+def test_rhs_with_boundary_conditions(gpu, xtrace, case):
     import flou_b200 as F
     orc = case.oracle()
     disc, eq = case.product()
@@ -128,7 +128,7 @@ GENERAL_CASES = [
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", GENERAL_CASES, ids=repr)
-def test_rhs_general_geometry(gpu, case):
+def test_rhs_general_geometry(gpu, xtrace, case):
     import flou_b200 as F
     orc = case.oracle()
     disc, eq = case.product()
@@ -271,7 +271,7 @@ HYBRID_CASES = [
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", HYBRID_CASES, ids=repr)
 @pytest.mark.parametrize("state", ["random", "smooth"])
-def test_hybrid_rhs_matches_oracle(gpu, case, state):
+def test_hybrid_rhs_matches_oracle(gpu, xtrace, case, state):
     """HybridDivOperator (OpDivergence.jl:452-612) on the device vs the oracle restatement that
     reproduces the reference's Shockwave2D value; RHS and the state after a few RK steps."""
     import flou_b200 as F
