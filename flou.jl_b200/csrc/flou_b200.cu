@@ -1279,7 +1279,7 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
     // Measured (profiles/r2mg, r2mg8): direct launches are as fast at 2 GPUs (27.6 vs 27.3 GDOF/s) and
     // 2.5 % faster at 8 (106.2 vs 103.6), so the captured exchange is opt-in: FLOU_B200_MG_GRAPH=1.
     static const bool mg_graph = [] { const char *e = std::getenv("FLOU_B200_MG_GRAPH"); return e && e[0] == '1'; }();
-    const bool use_graph = !(h->flags & FLOU_B200_FLAG_NO_GRAPH) && nsteps >= 4 && !h->profile &&
+    const bool use_graph = !(h->flags & FLOU_B200_FLAG_NO_GRAPH) && nsteps >= 2 && !h->profile &&
                            (h->nranks == 1 || h->nghost == 0 || (h->comm && mg_graph));
     int64_t done = 0;
     if (use_graph && !h->traces_valid && uses_xtraces(h)) {
@@ -1296,26 +1296,34 @@ int32_t flou_b200_lsrk2n_advance(flou_b200_handle *h, int32_t nstages, const dou
         key.insert(key.end(), B, B + nstages);
         key.push_back(h->stage_limiter ? 1.0 : 0.0); key.push_back(h->limiter_minval);
         const int gi = h->cur;           // two steps bring u back to the buffer they started in
-        if (!h->graph[gi] || key != h->graph_key[gi]) {
-            if (h->graph[gi]) cudaGraphExecDestroy(h->graph[gi]);
-            h->graph[gi] = nullptr;
+        // The graphs of BOTH ping-pong parities are built at the first use of a tableau / dt (a run
+        // whose leftover odd step flips the parity would otherwise instantiate the second one in the
+        // middle of a later, possibly timed, call) and uploaded to the device right away.
+        const int cur0 = h->cur;
+        for (int gj : {gi, gi ^ 1}) {
+            if (h->graph[gj] && key == h->graph_key[gj]) continue;
+            if (h->graph[gj]) cudaGraphExecDestroy(h->graph[gj]);
+            h->graph[gj] = nullptr;
             cudaGraph_t g = nullptr;
-            const int cur0 = h->cur;
             const int64_t l0 = h->launches;
+            const bool tv0 = h->traces_valid;
             // Gauss nodes / stage limiter: every captured pass starts with its own trace emit
             if (!h->colloc || h->stage_limiter) h->traces_valid = false;
+            h->cur = gj;
             CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             const int32_t rc = run_steps_direct(h, nstages, A, B, dt, 2);
             cudaError_t e = cudaStreamEndCapture(h->stream, &g);
             h->cur = cur0;
             h->graph_launches_per_replay = h->launches - l0;
             h->launches = l0;
+            if (gj != gi) h->traces_valid = tv0;
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             CUDA_TRY(e);
-            e = cudaGraphInstantiate(&h->graph[gi], g, 0);
+            e = cudaGraphInstantiate(&h->graph[gj], g, 0);
             cudaGraphDestroy(g);
             CUDA_TRY(e);
-            h->graph_key[gi] = key;
+            CUDA_TRY(cudaGraphUpload(h->graph[gj], h->stream));
+            h->graph_key[gj] = key;
         }
         while (nsteps - done >= 2) {
             CUDA_TRY(cudaGraphLaunch(h->graph[gi], h->stream));
