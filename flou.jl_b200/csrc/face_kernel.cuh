@@ -179,6 +179,7 @@ template <int ND, int NP, int EQ, bool CART>
 __global__ void __launch_bounds__(128, FLOU_FACE_MIN_BLOCKS)
 face_flux_kernel(const __grid_constant__ KParams P)
 {
+    pdl_prologue();
     constexpr int NFP = ipow_c(NP, ND - 1);
     // face_reverse: the kernel starts where the element kernel of the previous stage ended (the
     // tail of u_out / the traces is still in L2) and ends where the next element kernel starts

@@ -65,14 +65,37 @@ static int resident_ctas()
     return n;
 }
 
+// FLOU_B200_PDL=1: stage kernels launched as programmatic dependents of the kernel before them in the
+// stream (pdl_prologue in the kernels); captured into the CUDA graph as programmatic edges
+static bool pdl_enabled()
+{
+    static const bool v = [] { const char *e = std::getenv("FLOU_B200_PDL"); return e && e[0] == '1'; }();
+    return v;
+}
+
+static cudaError_t launch_stage_kernel(void (*kernel)(KParams), int grid, int threads, size_t smem, cudaStream_t s,
+                                       const KParams &P)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, P);
+}
+
 template <class C>
 static cudaError_t do_launch(const KParams &P, cudaStream_t s)
 {
     if (P.elem_count <= 0) return cudaSuccess;
     const int ngroups = (P.elem_count + C::EPB - 1) / C::EPB;
     const int grid = ngroups;      // one CTA per group of EPB consecutive elements
-    stage_kernel<C, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(P);
-    return cudaGetLastError();
+    return launch_stage_kernel(stage_kernel<C, false>, grid, C::THREADS, C::SMEM_BYTES, s, P);
 }
 
 template <class C>
@@ -80,8 +103,7 @@ static cudaError_t do_launch_elements(const KParams &P, cudaStream_t s)
 {
     if (P.elem_count <= 0) return cudaSuccess;
     const int grid = (P.elem_count + C::EPB - 1) / C::EPB;
-    stage_kernel<C, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(P);
-    return cudaGetLastError();
+    return launch_stage_kernel(stage_kernel<C, true>, grid, C::THREADS, C::SMEM_BYTES, s, P);
 }
 
 // ---- line-per-thread element kernel (element kernel of the two-kernel stage): warp-specialised,
@@ -144,8 +166,7 @@ static cudaError_t do_launch_lines(const KParams &P0, cudaStream_t s)
     const int ngroups = (P.elem_count + L::E - 1) / L::E;
     const int resident = line_resident_ctas<C>();
     const int grid = ngroups < resident ? ngroups : resident;      // persistent CTAs
-    line_kernel_of<L>()<<<grid, L::T, L::SMEM_BYTES, s>>>(P);
-    return cudaGetLastError();
+    return launch_stage_kernel(line_kernel_of<L>(), grid, L::T, L::SMEM_BYTES, s, P);
 }
 
 template <class C>
@@ -154,8 +175,7 @@ static cudaError_t do_launch_faces(const KParams &P, cudaStream_t s)
     if (P.face_count <= 0) return cudaSuccess;
     const int64_t n = (int64_t)P.face_count * C::NFP;
     const int grid = (int)((n + 127) / 128);
-    face_flux_kernel<C::ND, C::NP, C::EQ, C::CART><<<grid, 128, 0, s>>>(P);
-    return cudaGetLastError();
+    return launch_stage_kernel(face_flux_kernel<C::ND, C::NP, C::EQ, C::CART>, grid, 128, 0, s, P);
 }
 
 template <class C>

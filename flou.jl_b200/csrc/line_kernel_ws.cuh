@@ -55,6 +55,7 @@ __device__ __forceinline__ void ws_body(const KParams &P)
     double *const smem = lsmem;
     constexpr int FNB = C::FNB, FSET = E * NFACES * FNB;
 
+    pdl_prologue();
     if (ws_cta() * E >= P.elem_count) return;
     if (threadIdx.x == 0) {
         const bool wide = ws_wide<C>(P);

@@ -411,10 +411,21 @@ __device__ __forceinline__ Conn pick_conn(const Conn *cn, int j)
 // SPLITF = true: the Riemann fluxes come from face_flux_kernel through P.Fn (each face
 // evaluated once); phase 3 disappears and phase 0 copies the six flux blocks instead of the
 // neighbours' traces.  SPLITF = false: the fully fused single-kernel stage.
+// Programmatic dependent launch (FLOU_B200_PDL=1: the stage kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): the next kernel of the stream may be set up
+// and its CTAs placed while this grid is still running; it then waits here until every grid it
+// depends on has completed and flushed.  Both instructions are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 template <class C, bool SPLITF>
 __global__ void __launch_bounds__(C::THREADS, SPLITF ? C::MIN_BLOCKS_E : C::MIN_BLOCKS)
 stage_kernel(const __grid_constant__ KParams P)
 {
+    pdl_prologue();
     constexpr int ND = C::ND, NP = C::NP, EQ = C::EQ, VOL = C::VOL, NV = C::NV;
     constexpr int NPTS = C::NPTS, NFP = C::NFP, NFACES = C::NFACES, NFT = C::NFT, EPB = C::EPB;
     constexpr int TPT = C::TPT;
