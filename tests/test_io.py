@@ -259,3 +259,22 @@ def test_save_callback_writes_the_reference_files(gpu, tmp_path):
                 assert np.array_equal(got[k], v), k
         assert r.get("/VTKHDF").attrs["Type"] == "UnstructuredGrid"
     disc.close()
+
+
+def test_container_opens_with_libhdf5_where_available(tmp_path):
+    """Not runnable in the build image (no HDF5 library anywhere: the container is pinned only by
+    tests/hdf5_reader.py); wherever h5py exists this reads the same file through libhdf5."""
+    h5py = pytest.importorskip("h5py")
+    import flou_b200 as F
+    case = CASES[1]
+    disc, _ = case.product(create=False)
+    path = str(tmp_path / "mesh.hdf")
+    file = F.open_for_write(path, disc)
+    F.add_fielddata(file, [0.5], "Time")
+    F.close_file(file)
+    want = Reader(path).tree()
+    with h5py.File(path, "r") as f:
+        assert f["VTKHDF"].attrs["Type"] in (b"UnstructuredGrid", "UnstructuredGrid")
+        assert list(f["VTKHDF"].attrs["Version"]) == [1, 0]
+        for k, v in want.items():
+            assert np.array_equal(f[k][...], v), k
