@@ -32,6 +32,16 @@ namespace {
 // over the faces mastered by n consecutive elements, then the element kernel over those elements --
 // so that a slab's flux blocks (and the state the face kernel has just read) are still in L2 when
 // the element kernel asks for them.  0 (default): one face launch and one element launch per stage.
+// a state of 4 GB and more on one GPU (config 4): no x-face trace array and face slots in blocks of
+// 4096 master elements unless FLOU_B200_XTRACE / FLOU_B200_FACE_CHUNK say otherwise
+bool large_single_gpu_state(const flou_b200_desc *d)
+{
+    if (d->nranks > 1) return false;
+    double npts = 1.0;
+    for (int i = 0; i < d->nd; i++) npts *= d->np;
+    return (double)d->ne * npts * d->nv * sizeof(double) >= 4.0 * (1u << 30);
+}
+
 long slab_elements()
 {
     static const long v = [] { const char *e = std::getenv("FLOU_B200_SLAB"); return e ? std::atol(e) : 0L; }();
@@ -231,10 +241,15 @@ int32_t build_plan(const flou_b200_desc *d, bool cart, Plan &pl)
         // time and the element kernel finds the fluxes of an element's own faces side by side.
         // 0 (default): one run per direction over the whole mesh.  Measured (profiles/r2j): blocks of
         // 256 cost the face kernel 3-4 % at config 4 and gain nothing elsewhere.
-        static const long chunk_env = [] { const char *e = std::getenv("FLOU_B200_FACE_CHUNK"); return e ? std::atol(e) : 0L; }();
+        // Together with NO x-face trace array (profiles/r2u, config 4): blocks of 4096 let the y / z node
+        // layers hit in L2 behind the x-face reads of the same elements -- face kernel 20.8 -> 14.1 GB
+        // read, stage 18.5 -> 18.1 ms: the default of a single-GPU state of 4 GB and more.
+        static const long chunk_env = [] { const char *e = std::getenv("FLOU_B200_FACE_CHUNK"); return e ? std::atol(e) : -1L; }();
         // slab-wise stage (FLOU_B200_SLAB, single GPU): the face slots are blocked by slab
         const long slab = slab_elements();
-        const long chunk = (slab > 0 && nranks == 1) ? slab : chunk_env;
+        const long chunk = (slab > 0 && nranks == 1) ? slab
+                           : chunk_env >= 0 ? chunk_env
+                           : large_single_gpu_state(d) ? 4096L : 0L;
         auto key = [&](int sidx) -> int64_t {
             const int64_t gf = pl.slot_face[sidx];
             const int lfm_ = (int)d->elempos[gf * 2 + 0] - 1;
@@ -442,7 +457,9 @@ namespace {
 // other directions (FLOU_B200_XTRACE=0).  Measured (profiles/r2m): at config 4 the element kernel
 // writes 4.2 GB less and loses its trace pass (ncu 12.70 -> 11.96 ms at the burst clock, no change
 // under the board's power cap), the face kernel reads u once more (20.8 -> 27.2 GB, 4.49 -> 5.05 ms):
-// stage +2.7 %; config 2 (L2-resident) -4.6 %.  Default: the array only for states beyond 48 MB.
+// stage +2.7 %; config 2 (L2-resident) -4.6 %.  With the face slots in blocks of 4096 master elements
+// the face kernel reads 14.1 GB instead and the stage is 2.5 % FASTER (profiles/r2u).  Default: no
+// array for states up to 48 MB and for single-GPU states of 4 GB and more (then with the blocks).
 bool uses_xtraces(const flou_b200_handle *h)
 {
     return !(h->colloc && h->split_faces) || h->keep_xtraces;
@@ -1038,7 +1055,7 @@ int32_t flou_b200_create(const flou_b200_desc *d, flou_b200_handle **out)
         // default: no x-face trace array while the state fits in L2 (the face kernel's extra reads of u
         // are L2 hits there: config 2 -4.6 % per stage), the array beyond (config 4: +2.7 % without it)
         const char *x = std::getenv("FLOU_B200_XTRACE");
-        h->keep_xtraces = x ? x[0] != '0' : state_bytes > ((size_t)48 << 20);
+        h->keep_xtraces = x ? x[0] != '0' : (state_bytes > ((size_t)48 << 20) && !large_single_gpu_state(d));
     }
     if (uses_xtraces(h)) {
         H_TRY(cudaMalloc((void **)&h->tr[0], trace_bytes));
