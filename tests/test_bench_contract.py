@@ -59,3 +59,28 @@ def test_product_arm_fails_loudly_without_a_gpu():
     out = _run("--workload", "cfg1", "--steps", "1", "--warmup", "0", "--no-cpu-baseline", "--no-e2e")
     assert out.returncode != 0
     assert "no usable CUDA device" in (out.stderr + out.stdout) or "CUDA" in (out.stderr + out.stdout)
+
+
+def test_clock_sampler_parses_clocks_reasons_and_power(tmp_path):
+    """The `clocks` record of the bench line: median SM clock, throttle reasons and (when nvidia-smi
+    reports them) board power against its enforced limit -- what `sw_power_cap` refers to."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class _Done:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    p = tmp_path / "smi.csv"
+    p.write_text(
+        "0, 1710, 1965, 981.20, 0x0000000000000004, Not Active, Not Active, Not Active, Active, 1000.00\n"
+        "0, 1725, 1965, 990.10, 0x0000000000000004, Not Active, Not Active, Not Active, Active, 1000.00\n"
+        "0, 1740, 1965, [N/A], 0x0000000000000000, Not Active, Not Active, Not Active, Not Active, [N/A]\n"
+        "garbage line\n")
+    s = bench.ClockSampler(0)
+    s.proc, s.path = _Done(), str(p)
+    out = s.stop()
+    assert out["sm_mhz"] == 1725.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["sw_power_cap"]
+    assert abs(out["power_w"] - 985.65) < 1e-9 and out["power_limit_w"] == 1000.0
